@@ -1,0 +1,146 @@
+// C-ABI harness around the UNMODIFIED reference classes (NVStrings / NVCategory / NVText from
+// /root/reference/cpp/include), compiled for the host by oracle/Makefile.  TEST INFRASTRUCTURE ONLY:
+// it is the parity oracle for tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.
+// Nothing under custrings_b200/ links, loads or calls it.
+//
+// All buffers are host buffers (the reference's "device" memory is malloc in this build), columns
+// travel as Arrow-style (chars, int32 offsets[n+1], LSB-first validity bits).
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include <NVStrings.h>
+#include <NVCategory.h>
+#include <NVText.h>
+
+static thread_local std::string g_err;
+#define GUARD(expr, fail)                      \
+    try { expr; }                              \
+    catch (const std::exception& e) { g_err = e.what(); return fail; }
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+void* ref_create(const char* chars, int n, const int* offsets, const unsigned char* mask, int nulls)
+{
+    GUARD(return NVStrings::create_from_offsets(chars, n, offsets, mask, nulls, false), nullptr);
+}
+
+void* ref_create_from_array(const char** strs, unsigned n)
+{
+    GUARD(return NVStrings::create_from_array(strs, n), nullptr);
+}
+
+void ref_destroy(void* h) { if (h) NVStrings::destroy((NVStrings*)h); }
+
+unsigned ref_size(void* h) { return ((NVStrings*)h)->size(); }
+
+// total bytes of all strings (nulls count 0)
+long ref_total_bytes(void* h)
+{
+    NVStrings* s = (NVStrings*)h;
+    std::vector<int> lens(s->size());
+    s->byte_count(lens.data(), false);
+    long t = 0;
+    for (int v : lens) t += v > 0 ? v : 0;
+    return t;
+}
+
+// export to (chars, offsets[n+1], mask[(n+7)/8]); returns null count
+int ref_export(void* h, char* chars, int* offsets, unsigned char* mask)
+{
+    NVStrings* s = (NVStrings*)h;
+    GUARD(return s->create_offsets(chars, offsets, mask, false), -100);
+}
+
+int ref_len(void* h, int* out) { GUARD(return (int)((NVStrings*)h)->len(out, false), -100); }
+int ref_hash(void* h, unsigned* out) { GUARD(return ((NVStrings*)h)->hash(out, false), -100); }
+
+int ref_contains_re(void* h, const char* pat, bool* out) { GUARD(return ((NVStrings*)h)->contains_re(pat, out, false), -100); }
+int ref_match(void* h, const char* pat, bool* out) { GUARD(return ((NVStrings*)h)->match(pat, out, false), -100); }
+int ref_count_re(void* h, const char* pat, int* out) { GUARD(return ((NVStrings*)h)->count_re(pat, out, false), -100); }
+
+void* ref_replace_re(void* h, const char* pat, const char* repl, int maxrepl)
+{
+    GUARD(return ((NVStrings*)h)->replace_re(pat, repl, maxrepl), nullptr);
+}
+void* ref_replace_re_multi(void* h, const char** pats, int npats, void* repls)
+{
+    std::vector<const char*> v(pats, pats + npats);
+    GUARD(return ((NVStrings*)h)->replace_re(v, *(NVStrings*)repls), nullptr);
+}
+void* ref_replace(void* h, const char* str, const char* repl, int maxrepl)
+{
+    GUARD(return ((NVStrings*)h)->replace(str, repl, maxrepl), nullptr);
+}
+void* ref_replace_multi(void* h, void* tgts, void* repls)
+{
+    GUARD(return ((NVStrings*)h)->replace(*(NVStrings*)tgts, *(NVStrings*)repls), nullptr);
+}
+
+int ref_find(void* h, const char* str, int start, int end, int* out) { GUARD(return (int)((NVStrings*)h)->find(str, start, end, out, false), -100); }
+int ref_rfind(void* h, const char* str, int start, int end, int* out) { GUARD(return (int)((NVStrings*)h)->rfind(str, start, end, out, false), -100); }
+int ref_contains(void* h, const char* str, bool* out) { GUARD(return ((NVStrings*)h)->contains(str, out, false), -100); }
+int ref_startswith(void* h, const char* str, bool* out) { GUARD(return (int)((NVStrings*)h)->startswith(str, out, false), -100); }
+int ref_endswith(void* h, const char* str, bool* out) { GUARD(return (int)((NVStrings*)h)->endswith(str, out, false), -100); }
+int ref_find_multiple(void* h, void* strs, int* out) { GUARD(return (int)((NVStrings*)h)->find_multiple(*(NVStrings*)strs, out, false), -100); }
+
+// column-major split; delimiter NULL => whitespace variant. Writes up to cap handles; returns #columns.
+int ref_split(void* h, const char* delim, int maxsplit, int right, void** out, int cap)
+{
+    NVStrings* s = (NVStrings*)h;
+    std::vector<NVStrings*> res;
+    try {
+        if (right) { if (delim) s->rsplit(delim, maxsplit, res); else s->rsplit(maxsplit, res); }
+        else       { if (delim) s->split(delim, maxsplit, res);  else s->split(maxsplit, res); }
+    } catch (const std::exception& e) { g_err = e.what(); return -100; }
+    int n = (int)res.size();
+    for (int i = 0; i < n; ++i) { if (i < cap) out[i] = res[i]; else NVStrings::destroy(res[i]); }
+    return n;
+}
+
+// row-major split; out must hold size() handles (NULL for null rows); returns total tokens
+int ref_split_record(void* h, const char* delim, int maxsplit, int right, void** out)
+{
+    NVStrings* s = (NVStrings*)h;
+    std::vector<NVStrings*> res;
+    int rc;
+    try {
+        if (right) rc = delim ? s->rsplit_record(delim, maxsplit, res) : s->rsplit_record(maxsplit, res);
+        else       rc = delim ? s->split_record(delim, maxsplit, res)  : s->split_record(maxsplit, res);
+    } catch (const std::exception& e) { g_err = e.what(); return -100; }
+    for (size_t i = 0; i < res.size(); ++i) out[i] = res[i];
+    return rc;
+}
+
+int ref_partition(void* h, const char* delim, int right, void** out)
+{
+    NVStrings* s = (NVStrings*)h;
+    std::vector<NVStrings*> res;
+    int rc;
+    GUARD(rc = right ? s->rpartition(delim, res) : s->partition(delim, res), -100);
+    for (size_t i = 0; i < res.size(); ++i) out[i] = res[i];
+    return rc;
+}
+
+void* ref_tokenize(void* h, const char* delim) { GUARD(return NVText::tokenize(*(NVStrings*)h, delim), nullptr); }
+void* ref_tokenize_multi(void* h, void* delims) { GUARD(return NVText::tokenize(*(NVStrings*)h, *(NVStrings*)delims), nullptr); }
+int ref_token_count(void* h, const char* delim, unsigned* out) { GUARD(return (int)NVText::token_count(*(NVStrings*)h, delim, out, false), -100); }
+
+void* ref_cat_create(void* h) { GUARD(return NVCategory::create_from_strings(*(NVStrings*)h), nullptr); }
+void* ref_cat_create_multi(void** hs, int n)
+{
+    std::vector<NVStrings*> v;
+    for (int i = 0; i < n; ++i) v.push_back((NVStrings*)hs[i]);
+    GUARD(return NVCategory::create_from_strings(v), nullptr);
+}
+void ref_cat_destroy(void* c) { if (c) NVCategory::destroy((NVCategory*)c); }
+unsigned ref_cat_size(void* c) { return ((NVCategory*)c)->size(); }
+unsigned ref_cat_keys_size(void* c) { return ((NVCategory*)c)->keys_size(); }
+void* ref_cat_keys(void* c) { GUARD(return ((NVCategory*)c)->get_keys(), nullptr); }
+int ref_cat_values(void* c, int* out) { GUARD(return ((NVCategory*)c)->get_values(out, false), -100); }
+void* ref_cat_to_strings(void* c) { GUARD(return ((NVCategory*)c)->to_strings(), nullptr); }
+
+}  // extern "C"
