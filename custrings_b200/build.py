@@ -1,0 +1,68 @@
+"""Builds libcustr.so (hand-written sm_100a CUDA + host C++) in-tree with nvcc.  No torch involved."""
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libcustr.so")
+NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
+
+SOURCES = ["column.cu", "regex.cu", "regex_bits.cu", "regex_compile.cpp", "find.cu", "split.cu", "category.cu"]
+
+
+def _stale(out, deps):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inc"))]
+    hs.append(os.path.join(ROOT, "include", "custr.h"))
+    return hs
+
+
+def _compile(src, verbose):
+    path = os.path.join(CSRC, src)
+    obj = os.path.join(OBJ, src.rsplit(".", 1)[0] + ".o")
+    if not _stale(obj, [path] + _headers()):
+        return obj
+    cmd = [NVCC] + ARCH + COMMON + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return obj
+
+
+def build(verbose=False, force=False):
+    os.makedirs(OBJ, exist_ok=True)
+    flags_inc = os.path.join(CSRC, "unicode_flags.inc")
+    gen = os.path.join(ROOT, "tools", "gen_unicode_flags.py")
+    if force or _stale(flags_inc, [gen, os.path.join(ROOT, "tools", "unicode_delta.txt")]):
+        subprocess.run([sys.executable, gen], check=True, capture_output=True)
+    if force:
+        shutil.rmtree(OBJ)
+        os.makedirs(OBJ)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
+    if _stale(LIB, objs):
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

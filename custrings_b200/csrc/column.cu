@@ -1,0 +1,592 @@
+// Column life-cycle, import/export and the cheap per-row attributes.
+// Replaces (reference, rapidsai/custrings): NVStrings::create_from_offsets NVStrings.cu:109-119 ->
+// NVStringsImpl.cu:328-444, create_from_array NVStrings.cu:74-86, create_offsets :402-482,
+// set_null_bitarray :493-544, byte_count/len attrs.cu:32-110, hash convert.cu:34-63 + custring.inl:164-232.
+// The reference rebuilds a pointer-per-string object heap on import (3 passes + memmove per row); here the
+// Arrow triple IS the storage, so import is two memcpys and export is one.
+#include "common.cuh"
+#include "device_utils.cuh"
+#include <cub/cub.cuh>
+
+namespace custr {
+
+thread_local std::string g_error;
+thread_local cudaStream_t g_stream = 0;
+std::atomic<long long> g_launches{0};
+
+DeviceBuf::DeviceBuf(size_t n) : bytes(n)
+{
+    static bool pool_ready = false;
+    if (!pool_ready) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        pool_ready = true;
+    }
+    cudaError_t e = cudaMallocAsync(&ptr, n, g_stream);
+    if (e != cudaSuccess) {
+        g_error = std::string("device allocation of ") + std::to_string(n) + " bytes failed: " + cudaGetErrorString(e);
+        cudaGetLastError();
+        throw CudaError{e};
+    }
+}
+DeviceBuf::~DeviceBuf()
+{
+    if (ptr) cudaFreeAsync(ptr, g_stream);
+}
+
+int num_sms()
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+BufPtr upload(const void* host, size_t bytes)
+{
+    BufPtr b = dev_alloc(bytes);
+    if (bytes) CUSTR_CUDA(cudaMemcpyAsync(b->ptr, host, bytes, cudaMemcpyHostToDevice, g_stream));
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void k_rebase_offsets(int32_t* offsets, int32_t n1, int32_t base)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n1) offsets[i] -= base;
+}
+
+// lengths with nulls forced to zero; flags a null row that carries bytes
+__global__ void k_valid_lengths(ColView c, int32_t* lengths, int* dirty)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    int len = c.offsets[i + 1] - c.offsets[i];
+    if (!c.valid(i)) {
+        if (len) *dirty = 1;
+        len = 0;
+    }
+    lengths[i] = len;
+}
+
+// one warp per row copy (rows are ~100 B; coalesced 32-lane byte copy)
+__global__ void k_gather_rows(const char* __restrict__ src, const int32_t* __restrict__ src_off,
+                              const int32_t* __restrict__ rows, char* __restrict__ dst,
+                              const int32_t* __restrict__ dst_off, int32_t n)
+{
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    int r = rows ? rows[warp] : warp;
+    int d0 = dst_off[warp], len = dst_off[warp + 1] - d0;
+    if (len <= 0) return;
+    const char* s = src + src_off[r];
+    for (int j = lane; j < len; j += 32) dst[d0 + j] = s[j];
+}
+
+__global__ void k_pack_bits(const uint8_t* __restrict__ flags, uint8_t* __restrict__ bits, int32_t n)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int nb = (n + 7) >> 3;
+    if (b >= nb) return;
+    unsigned v = 0;
+    for (int k = 0; k < 8; ++k) {
+        int i = b * 8 + k;
+        if (i < n && flags[i]) v |= 1u << k;
+    }
+    bits[b] = (uint8_t)v;
+}
+
+__global__ void k_count_valid(const uint8_t* __restrict__ bits, int32_t vbit0, int32_t n, unsigned long long* total)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int v = 0;
+    if (i < n) {
+        int b = vbit0 + i;
+        v = (bits[b >> 3] >> (b & 7)) & 1;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(total, (unsigned long long)__popc(m));
+}
+
+// validity re-aligned to bit 0; rows past n are 0; optionally clears empties
+__global__ void k_export_validity(ColView c, uint8_t* __restrict__ out, int empty_is_null, unsigned long long* cleared)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int nb = (c.n + 7) >> 3;
+    if (b >= nb) return;
+    unsigned v = 0;
+    int zeros = 0;
+    for (int k = 0; k < 8; ++k) {
+        int i = b * 8 + k;
+        if (i >= c.n) break;
+        bool ok = c.valid(i);
+        if (ok && empty_is_null && c.offsets[i + 1] == c.offsets[i]) ok = false;
+        if (ok) v |= 1u << k; else ++zeros;
+    }
+    out[b] = (uint8_t)v;
+    if (zeros && cleared) atomicAdd(cleared, (unsigned long long)zeros);
+}
+
+__global__ void k_byte_count(ColView c, int32_t* __restrict__ lengths, unsigned long long* total)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int len = 0;
+    if (i < c.n) {
+        bool ok = c.valid(i);
+        len = ok ? c.offsets[i + 1] - c.offsets[i] : 0;
+        if (lengths) lengths[i] = ok ? len : -1;
+    }
+    for (int o = 16; o; o >>= 1) len += __shfl_down_sync(0xffffffffu, len, o);
+    if ((threadIdx.x & 31) == 0 && len) atomicAdd(total, (unsigned long long)len);
+}
+
+__global__ void k_char_len(ColView c, int32_t* __restrict__ lengths)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!c.valid(i)) { lengths[i] = -1; return; }
+    int b = c.offsets[i], e = c.offsets[i + 1], cnt = 0;
+    for (int j = b; j < e; ++j) cnt += ((uint8_t)c.chars[j] & 0xC0) != 0x80;
+    lengths[i] = cnt;
+}
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+// MurmurHash3_x86_32, seed 31 (published algorithm; the reference's variant is custring.inl:164-232)
+__global__ void k_murmur3(ColView c, uint32_t* __restrict__ out, unsigned long long* nonzero)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t h = 0;
+    if (i < c.n && c.valid(i)) {
+        const uint8_t* p = (const uint8_t*)c.chars + c.offsets[i];
+        int len = c.offsets[i + 1] - c.offsets[i];
+        h = 31u;
+        int nblocks = len >> 2;
+        for (int b = 0; b < nblocks; ++b) {
+            uint32_t k = p[4 * b] | (p[4 * b + 1] << 8) | (p[4 * b + 2] << 16) | ((uint32_t)p[4 * b + 3] << 24);
+            k *= 0xcc9e2d51u; k = rotl32(k, 15); k *= 0x1b873593u;
+            h ^= k; h = rotl32(h, 13); h = h * 5u + 0xe6546b64u;
+        }
+        const uint8_t* t = p + 4 * nblocks;
+        uint32_t k = 0;
+        int rem = len & 3;
+        if (rem == 3) k ^= t[2] << 16;
+        if (rem >= 2) k ^= t[1] << 8;
+        if (rem >= 1) { k ^= t[0]; k *= 0xcc9e2d51u; k = rotl32(k, 15); k *= 0x1b873593u; h ^= k; }
+        h ^= (uint32_t)len;
+        h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    }
+    if (i < c.n) out[i] = h;
+    unsigned m = __ballot_sync(0xffffffffu, h != 0);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(nonzero, (unsigned long long)__popc(m));
+}
+
+__global__ void k_gather_lengths(ColView c, const int32_t* __restrict__ idx, int32_t m, int32_t* __restrict__ lengths,
+                                 uint8_t* __restrict__ valid)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int r = idx[i];
+    bool ok = r >= 0 && r < c.n && c.valid(r);
+    lengths[i] = ok ? c.offsets[r + 1] - c.offsets[r] : 0;
+    valid[i] = ok;
+}
+
+__global__ void k_clamp_rows(int32_t* idx, int32_t m, int32_t n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m && (idx[i] < 0 || idx[i] >= n)) idx[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+static inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+int64_t scan_lengths_to_offsets(const int32_t* lengths, int32_t* offsets, int32_t n)
+{
+    // offsets[0..n-1] = exclusive scan; offsets[n] = total
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, lengths, offsets, n + 1, g_stream);
+    BufPtr tmp = dev_alloc(tmp_bytes);
+    // lengths must have n+1 readable entries (callers allocate n+1 and zero the last)
+    CUSTR_CUDA(cub::DeviceScan::ExclusiveSum(tmp->ptr, tmp_bytes, lengths, offsets, n + 1, g_stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    int32_t total = 0;
+    CUSTR_CUDA(cudaMemcpyAsync(&total, offsets + n, sizeof(int32_t), cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    return total;
+}
+
+void pack_bits(const uint8_t* flags, uint8_t* bits, int32_t n)
+{
+    if (n > 0) LAUNCH(k_pack_bits, blocks_for((n + 7) / 8, 256), 256, 0, flags, bits, n);
+}
+
+int32_t count_zero_bits(const uint8_t* bits, int32_t vbit0, int32_t n)
+{
+    if (!bits || n == 0) return 0;
+    Scratch<unsigned long long> total(1);
+    CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
+    LAUNCH(k_count_valid, blocks_for(n, 256), 256, 0, bits, vbit0, n, total.get());
+    unsigned long long h = 0;
+    CUSTR_CUDA(cudaMemcpyAsync(&h, total.get(), 8, cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    return n - (int32_t)h;
+}
+
+custr_column* make_column(BufPtr chars, BufPtr offsets, BufPtr validity, int32_t n, int32_t nulls, int64_t nbytes)
+{
+    custr_column* c = new custr_column;
+    c->chars_buf = chars;
+    c->offsets_buf = offsets;
+    c->validity_buf = (nulls > 0) ? validity : nullptr;
+    c->chars = chars ? (const char*)chars->ptr : nullptr;
+    c->offsets = (const int32_t*)offsets->ptr;
+    c->validity = c->validity_buf ? (const uint8_t*)c->validity_buf->ptr : nullptr;
+    c->n = n;
+    c->nulls = nulls;
+    c->nbytes = nbytes;
+    c->first_off = 0;
+    return c;
+}
+
+custr_column* all_null_column(int32_t n)
+{
+    BufPtr off = dev_alloc(sizeof(int32_t) * (size_t)(n + 1));
+    CUSTR_CUDA(cudaMemsetAsync(off->ptr, 0, sizeof(int32_t) * (size_t)(n + 1), g_stream));
+    BufPtr val = dev_alloc((n + 7) / 8);
+    CUSTR_CUDA(cudaMemsetAsync(val->ptr, 0, (n + 7) / 8, g_stream));
+    return make_column(dev_alloc(1), off, val, n, n, 0);
+}
+
+// compacting copy: rows (or all rows when rows==nullptr) of `src` with nulls forced empty
+static custr_column* compact_copy(const custr_column* src)
+{
+    int32_t n = src->n;
+    Scratch<int32_t> lens((size_t)n + 1);
+    Scratch<int> dirty(1);
+    CUSTR_CUDA(cudaMemsetAsync(lens.get() + n, 0, sizeof(int32_t), g_stream));
+    CUSTR_CUDA(cudaMemsetAsync(dirty.get(), 0, sizeof(int), g_stream));
+    LAUNCH(k_valid_lengths, blocks_for(n, 256), 256, 0, view_of(src), lens.get(), dirty.get());
+    BufPtr off = dev_alloc(sizeof(int32_t) * (size_t)(n + 1));
+    int64_t total = scan_lengths_to_offsets(lens.get(), (int32_t*)off->ptr, n);
+    BufPtr chars = dev_alloc((size_t)total);
+    LAUNCH(k_gather_rows, blocks_for((int64_t)n * 32, 256), 256, 0, src->chars, src->offsets, (const int32_t*)nullptr,
+           (char*)chars->ptr, (const int32_t*)off->ptr, n);
+    BufPtr val;
+    if (src->validity) {
+        val = dev_alloc((n + 7) / 8);
+        LAUNCH(k_export_validity, blocks_for((n + 7) / 8, 256), 256, 0, view_of(src), (uint8_t*)val->ptr, 0,
+               (unsigned long long*)nullptr);
+    }
+    return make_column(chars, off, val, n, src->nulls, total);
+}
+
+static bool null_rows_carry_bytes(const custr_column* c)
+{
+    if (!c->validity || c->n == 0) return false;
+    Scratch<int32_t> lens((size_t)c->n + 1);
+    Scratch<int> dirty(1);
+    CUSTR_CUDA(cudaMemsetAsync(dirty.get(), 0, sizeof(int), g_stream));
+    LAUNCH(k_valid_lengths, blocks_for(c->n, 256), 256, 0, view_of(c), lens.get(), dirty.get());
+    int h = 0;
+    CUSTR_CUDA(cudaMemcpyAsync(&h, dirty.get(), sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    return h != 0;
+}
+
+static custr_column* create_from_offsets_impl(const char* chars, int32_t count, const int32_t* offsets,
+                                              const uint8_t* validity, int32_t nulls, int devmem, bool adopt)
+{
+    if (count < 0 || (count > 0 && !offsets)) throw ArgError{fail(CUSTR_ERR_ARG, "create_from_offsets: null offsets")};
+    if (count == 0) {
+        BufPtr off = dev_alloc(sizeof(int32_t));
+        CUSTR_CUDA(cudaMemsetAsync(off->ptr, 0, sizeof(int32_t), g_stream));
+        return make_column(dev_alloc(1), off, nullptr, 0, 0, 0);
+    }
+    cudaMemcpyKind kind = devmem ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    int32_t ends[2];
+    if (devmem) {
+        CUSTR_CUDA(cudaMemcpyAsync(&ends[0], offsets, sizeof(int32_t), cudaMemcpyDeviceToHost, g_stream));
+        CUSTR_CUDA(cudaMemcpyAsync(&ends[1], offsets + count, sizeof(int32_t), cudaMemcpyDeviceToHost, g_stream));
+        CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    } else {
+        ends[0] = offsets[0];
+        ends[1] = offsets[count];
+    }
+    if (ends[1] < ends[0]) throw ArgError{fail(CUSTR_ERR_ARG, "create_from_offsets: offsets not ascending")};
+    int64_t nbytes = (int64_t)ends[1] - ends[0];
+    if (nbytes > 0 && !chars) throw ArgError{fail(CUSTR_ERR_ARG, "create_from_offsets: null chars")};
+    bool use_mask = validity != nullptr && nulls != 0;
+
+    custr_column* c = new custr_column;
+    std::unique_ptr<custr_column> guard(c);
+    c->n = count;
+    c->nbytes = nbytes;
+    if (adopt) {
+        c->chars = chars;
+        c->offsets = offsets;
+        c->validity = use_mask ? validity : nullptr;
+        c->first_off = ends[0];
+    } else {
+        c->offsets_buf = dev_alloc(sizeof(int32_t) * (size_t)(count + 1));
+        CUSTR_CUDA(cudaMemcpyAsync(c->offsets_buf->ptr, offsets, sizeof(int32_t) * (size_t)(count + 1), kind, g_stream));
+        if (ends[0] != 0)
+            LAUNCH(k_rebase_offsets, blocks_for(count + 1, 256), 256, 0, (int32_t*)c->offsets_buf->ptr, count + 1, ends[0]);
+        c->chars_buf = dev_alloc((size_t)nbytes);
+        if (nbytes) CUSTR_CUDA(cudaMemcpyAsync(c->chars_buf->ptr, chars + ends[0], (size_t)nbytes, kind, g_stream));
+        if (use_mask) {
+            c->validity_buf = dev_alloc((count + 7) / 8);
+            CUSTR_CUDA(cudaMemcpyAsync(c->validity_buf->ptr, validity, (count + 7) / 8, kind, g_stream));
+        }
+        c->chars = (const char*)c->chars_buf->ptr;
+        c->offsets = (const int32_t*)c->offsets_buf->ptr;
+        c->validity = use_mask ? (const uint8_t*)c->validity_buf->ptr : nullptr;
+        c->first_off = 0;
+    }
+    if (use_mask) {
+        c->nulls = count_zero_bits(c->validity, 0, count);
+        if (c->nulls == 0) { c->validity = nullptr; c->validity_buf = nullptr; }
+        else if (null_rows_carry_bytes(c)) {
+            custr_column* fixed = compact_copy(c);
+            return fixed;  // guard frees the raw view
+        }
+    }
+    if (!devmem) CUSTR_CUDA(cudaStreamSynchronize(g_stream));  // host buffers may be reused by the caller
+    return guard.release();
+}
+
+}  // namespace custr
+
+using namespace custr;
+
+extern "C" {
+
+const char* custr_last_error(void) { return g_error.c_str(); }
+const char* custr_version(void) { return "custrings_b200 0.1 (sm_100a)"; }
+
+int custr_set_device(int device)
+{
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(CUSTR_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return CUSTR_OK;
+}
+void custr_set_stream(void* s) { g_stream = (cudaStream_t)s; }
+int custr_sync(void)
+{
+    cudaError_t e = cudaStreamSynchronize(g_stream);
+    if (e != cudaSuccess) return fail(CUSTR_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+    return CUSTR_OK;
+}
+long long custr_launch_count(void) { return g_launches.load(); }
+
+custr_column* custr_create_from_offsets(const char* chars, int32_t count, const int32_t* offsets, const uint8_t* validity,
+                                        int32_t nulls, int devmem)
+{
+    return guarded([&] { return create_from_offsets_impl(chars, count, offsets, validity, nulls, devmem, false); },
+                   (custr_column*)nullptr, (custr_column*)nullptr);
+}
+
+custr_column* custr_adopt_device(const char* chars, int32_t count, const int32_t* offsets, const uint8_t* validity, int32_t nulls)
+{
+    return guarded([&] { return create_from_offsets_impl(chars, count, offsets, validity, nulls, 1, true); },
+                   (custr_column*)nullptr, (custr_column*)nullptr);
+}
+
+custr_column* custr_create_from_array(const char* const* strs, uint32_t count)
+{
+    return guarded(
+        [&]() -> custr_column* {
+            if (count && !strs) throw ArgError{fail(CUSTR_ERR_ARG, "create_from_array: null array")};
+            std::vector<int32_t> off(count + 1, 0);
+            std::vector<uint8_t> val((count + 7) / 8, 0);
+            int32_t nulls = 0;
+            size_t total = 0;
+            for (uint32_t i = 0; i < count; ++i) {
+                if (strs[i]) { total += strlen(strs[i]); val[i >> 3] |= 1u << (i & 7); }
+                else ++nulls;
+                if (total > 0x7fffffffULL) throw ArgError{fail(CUSTR_ERR_ARG, "create_from_array: more than 2 GiB of chars")};
+                off[i + 1] = (int32_t)total;
+            }
+            std::vector<char> chars(total ? total : 1);
+            for (uint32_t i = 0; i < count; ++i)
+                if (strs[i]) memcpy(chars.data() + off[i], strs[i], off[i + 1] - off[i]);
+            return create_from_offsets_impl(chars.data(), (int32_t)count, off.data(), val.data(), nulls, 0, false);
+        },
+        (custr_column*)nullptr, (custr_column*)nullptr);
+}
+
+void custr_column_free(custr_column* col) { delete col; }
+uint32_t custr_size(const custr_column* col) { return col ? (uint32_t)col->n : 0; }
+int64_t custr_chars_bytes(const custr_column* col) { return col ? col->nbytes : 0; }
+int32_t custr_null_count(const custr_column* col) { return col ? col->nulls : 0; }
+const char* custr_chars_ptr(const custr_column* col) { return col->chars + col->first_off; }
+const int32_t* custr_offsets_ptr(const custr_column* col) { return col->offsets; }
+const uint8_t* custr_validity_ptr(const custr_column* col) { return col->validity; }
+
+int custr_create_offsets(const custr_column* col, char* chars, int32_t* offsets, uint8_t* validity, int devmem)
+{
+    return guarded(
+        [&]() -> int {
+            if (!col) return fail(CUSTR_ERR_ARG, "create_offsets: null column");
+            int32_t n = col->n;
+            cudaMemcpyKind kind = devmem ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+            if (chars && col->nbytes)
+                CUSTR_CUDA(cudaMemcpyAsync(chars, col->chars + col->first_off, (size_t)col->nbytes, kind, g_stream));
+            if (offsets) {
+                if (col->first_off == 0)
+                    CUSTR_CUDA(cudaMemcpyAsync(offsets, col->offsets, sizeof(int32_t) * (size_t)(n + 1), kind, g_stream));
+                else {
+                    Scratch<int32_t> tmp((size_t)n + 1);
+                    CUSTR_CUDA(cudaMemcpyAsync(tmp.get(), col->offsets, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyDeviceToDevice, g_stream));
+                    LAUNCH(k_rebase_offsets, blocks_for(n + 1, 256), 256, 0, tmp.get(), n + 1, col->first_off);
+                    CUSTR_CUDA(cudaMemcpyAsync(offsets, tmp.get(), sizeof(int32_t) * (size_t)(n + 1), kind, g_stream));
+                    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+                }
+            }
+            if (validity && n) {
+                ResultBuf<uint8_t> out(validity, (n + 7) / 8, devmem);
+                LAUNCH(k_export_validity, blocks_for((n + 7) / 8, 256), 256, 0, view_of(col), out.dev, 0, (unsigned long long*)nullptr);
+                out.finish();
+            }
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            return 0;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
+int custr_set_null_bitarray(const custr_column* col, uint8_t* bitarray, int empty_is_null, int devmem)
+{
+    return guarded(
+        [&]() -> int {
+            if (!col || !bitarray) return fail(CUSTR_ERR_ARG, "set_null_bitarray: null argument");
+            int32_t n = col->n;
+            if (n == 0) return 0;
+            ResultBuf<uint8_t> out(bitarray, (n + 7) / 8, devmem);
+            Scratch<unsigned long long> cleared(1);
+            CUSTR_CUDA(cudaMemsetAsync(cleared.get(), 0, 8, g_stream));
+            LAUNCH(k_export_validity, blocks_for((n + 7) / 8, 256), 256, 0, view_of(col), out.dev, empty_is_null, cleared.get());
+            out.finish();
+            unsigned long long h = 0;
+            CUSTR_CUDA(cudaMemcpyAsync(&h, cleared.get(), 8, cudaMemcpyDeviceToHost, g_stream));
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            return (int)h;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
+int64_t custr_byte_count(const custr_column* col, int32_t* lengths, int devmem)
+{
+    return guarded(
+        [&]() -> int64_t {
+            if (!col) return fail(CUSTR_ERR_ARG, "byte_count: null column");
+            int32_t n = col->n;
+            if (n == 0) return 0;
+            if (!lengths) return col->nbytes;
+            ResultBuf<int32_t> out(lengths, n, devmem);
+            Scratch<unsigned long long> total(1);
+            CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
+            LAUNCH(k_byte_count, blocks_for(n, 256), 256, 0, view_of(col), out.dev, total.get());
+            out.finish();
+            return col->nbytes;
+        },
+        (int64_t)CUSTR_ERR_ARG, (int64_t)CUSTR_ERR_CUDA);
+}
+
+int custr_len(const custr_column* col, int32_t* lengths, int devmem)
+{
+    return guarded(
+        [&]() -> int {
+            if (!col || !lengths) return fail(CUSTR_ERR_ARG, "len: null argument");
+            int32_t n = col->n;
+            if (n == 0) return 0;
+            ResultBuf<int32_t> out(lengths, n, devmem);
+            LAUNCH(k_char_len, blocks_for(n, 256), 256, 0, view_of(col), out.dev);
+            out.finish();
+            return n - col->nulls;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
+int custr_hash(const custr_column* col, uint32_t* results, int devmem)
+{
+    return guarded(
+        [&]() -> int {
+            if (!col || !results || col->n == 0) return fail(CUSTR_ERR_ARG, "hash: null argument or empty column");
+            int32_t n = col->n;
+            ResultBuf<uint32_t> out(results, n, devmem);
+            Scratch<unsigned long long> nz(1);
+            CUSTR_CUDA(cudaMemsetAsync(nz.get(), 0, 8, g_stream));
+            LAUNCH(k_murmur3, blocks_for(n, 256), 256, 0, view_of(col), out.dev, nz.get());
+            out.finish();
+            unsigned long long h = 0;
+            CUSTR_CUDA(cudaMemcpyAsync(&h, nz.get(), 8, cudaMemcpyDeviceToHost, g_stream));
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            return (int)h;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
+custr_column* custr_slice_rows(const custr_column* col, int32_t first, int32_t last)
+{
+    return guarded(
+        [&]() -> custr_column* {
+            if (!col || first < 0 || last < first || last > col->n) throw ArgError{fail(CUSTR_ERR_ARG, "slice_rows: bad range")};
+            custr_column* v = new custr_column(*col);  // shares the buffers
+            v->n = last - first;
+            v->offsets = col->offsets + first;
+            v->vbit0 = col->vbit0 + first;
+            int32_t ends[2] = {0, 0};
+            CUSTR_CUDA(cudaMemcpyAsync(&ends[0], col->offsets + first, sizeof(int32_t), cudaMemcpyDeviceToHost, g_stream));
+            CUSTR_CUDA(cudaMemcpyAsync(&ends[1], col->offsets + last, sizeof(int32_t), cudaMemcpyDeviceToHost, g_stream));
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            v->first_off = ends[0];
+            v->nbytes = ends[1] - ends[0];
+            v->nulls = col->validity ? count_zero_bits(col->validity, v->vbit0, v->n) : 0;
+            if (v->nulls == 0) { v->validity = nullptr; v->vbit0 = 0; }
+            return v;
+        },
+        (custr_column*)nullptr, (custr_column*)nullptr);
+}
+
+custr_column* custr_gather(const custr_column* col, const int32_t* indices, int32_t count, int devmem)
+{
+    return guarded(
+        [&]() -> custr_column* {
+            if (!col || count < 0 || (count && !indices)) throw ArgError{fail(CUSTR_ERR_ARG, "gather: bad argument")};
+            BufPtr idx;
+            const int32_t* d_idx = indices;
+            if (!devmem) { idx = upload(indices, sizeof(int32_t) * (size_t)count); d_idx = (const int32_t*)idx->ptr; }
+            Scratch<int32_t> lens((size_t)count + 1);
+            Scratch<uint8_t> ok((size_t)count + 1);
+            CUSTR_CUDA(cudaMemsetAsync(lens.get() + count, 0, sizeof(int32_t), g_stream));
+            if (count) LAUNCH(k_gather_lengths, blocks_for(count, 256), 256, 0, view_of(col), d_idx, count, lens.get(), ok.get());
+            BufPtr off = dev_alloc(sizeof(int32_t) * (size_t)(count + 1));
+            int64_t total = scan_lengths_to_offsets(lens.get(), (int32_t*)off->ptr, count);
+            BufPtr chars = dev_alloc((size_t)total);
+            // rows with invalid indices have zero length, so clamping them to row 0 is harmless
+            Scratch<int32_t> safe((size_t)count + 1);
+            if (count) {
+                CUSTR_CUDA(cudaMemcpyAsync(safe.get(), d_idx, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToDevice, g_stream));
+                LAUNCH(k_clamp_rows, blocks_for(count, 256), 256, 0, safe.get(), count, col->n);
+                if (col->n > 0)
+                    LAUNCH(k_gather_rows, blocks_for((int64_t)count * 32, 256), 256, 0, col->chars, col->offsets,
+                           (const int32_t*)safe.get(), (char*)chars->ptr, (const int32_t*)off->ptr, count);
+            }
+            BufPtr val = dev_alloc((count + 7) / 8 + 1);
+            pack_bits(ok.get(), (uint8_t*)val->ptr, count);
+            int32_t nulls = count_zero_bits((const uint8_t*)val->ptr, 0, count);
+            return make_column(chars, off, val, count, nulls, total);
+        },
+        (custr_column*)nullptr, (custr_column*)nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,399 @@
+// Regex entry points of the C-ABI: contains_re / match / count_re / replace_re (+ multi-pattern form).
+// Replaces NVStrings::contains_re count.cu:59-110, match :113-165, count_re :199-250, replace_re
+// replace.cu:110-189 and replace_multi.cu:110-197 of the reference.
+//
+// Execution tiers:
+//   bitstream  - regex_bits.cu: whole-buffer bit-parallel evaluation for boolean results, when the pattern
+//                lowers to a bitstream program that is provably equivalent to the reference's NFA semantics
+//   pikevm     - this file + regex_vm.cuh: exact thread-per-row Pike VM, any pattern, also yields spans
+#include "common.cuh"
+#include "regex_vm.cuh"
+#include "regex_bits.h"
+#include <cub/cub.cuh>
+#include <list>
+#include <map>
+#include <mutex>
+
+namespace custr {
+
+static const uint8_t k_unicode_flags_host[65536] = {
+#include "unicode_flags.inc"
+};
+const uint8_t* host_unicode_flags() { return k_unicode_flags_host; }
+const uint8_t* device_unicode_flags()
+{
+    static std::once_flag once;
+    static uint8_t* d = nullptr;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] {
+        err = cudaMalloc(&d, 65536);
+        if (err == cudaSuccess) err = cudaMemcpy(d, k_unicode_flags_host, 65536, cudaMemcpyHostToDevice);
+    });
+    if (err != cudaSuccess) CUSTR_CUDA(err);
+    return d;
+}
+
+thread_local const char* g_last_tier = "none";
+thread_local int g_forced_tier = 0;
+
+// ---- compiled-program cache ------------------------------------------------------------------------------
+struct Compiled {
+    rx::Program prog;
+    std::vector<uint8_t> image;
+    BufPtr dev_image;
+    std::shared_ptr<bits::Plan> plan_contains, plan_match;  // bitstream lowering (may be null = not eligible)
+    bool plans_built = false;
+};
+using CompiledPtr = std::shared_ptr<Compiled>;
+
+static CompiledPtr get_compiled(const char* pattern)
+{
+    static std::mutex mu;
+    static std::list<std::pair<std::string, CompiledPtr>> lru;
+    std::lock_guard<std::mutex> lock(mu);
+    std::string key(pattern);
+    for (auto it = lru.begin(); it != lru.end(); ++it)
+        if (it->first == key) {
+            lru.splice(lru.begin(), lru, it);
+            return lru.front().second;
+        }
+    CompiledPtr c = std::make_shared<Compiled>();
+    c->prog = rx::compile(pattern);
+    c->image = rx::serialize(c->prog, host_unicode_flags());
+    c->dev_image = upload(c->image.data(), c->image.size());
+    // the image must be resident before another stream/thread uses the cached entry
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    lru.emplace_front(key, c);
+    if (lru.size() > 64) lru.pop_back();
+    return c;
+}
+
+static int cap_tier(int ninsts)
+{
+    if (ninsts <= 32) return 32;
+    if (ninsts <= 256) return 256;
+    if (ninsts <= 1024) return 1024;
+    return 0;
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------------
+constexpr int VM_THREADS = 128;
+constexpr int SMEM_PROG_MAX = 40 * 1024;
+
+__device__ __forceinline__ const uint8_t* stage_program(const uint8_t* img, int img_bytes, uint8_t* smem)
+{
+    if (img_bytes > SMEM_PROG_MAX) return img;
+    for (int i = threadIdx.x * 4; i < img_bytes; i += blockDim.x * 4) *(uint32_t*)(smem + i) = *(const uint32_t*)(img + i);
+    __syncthreads();
+    return smem;
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(VM_THREADS)
+k_vm_bool(ColView col, const uint8_t* __restrict__ img, int img_bytes, const uint8_t* __restrict__ uflags, int anchored,
+          uint8_t* __restrict__ out, unsigned long long* __restrict__ total)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    rxdev::DevProg P = rxdev::bind_program(stage_program(img, img_bytes, smem), uflags);
+    rxdev::Lists<CAP> L;
+    L.init();
+    for (int base = blockIdx.x * blockDim.x; base < col.n; base += gridDim.x * blockDim.x) {
+        int i = base + threadIdx.x;
+        int hit = 0;
+        if (i < col.n) {
+            if (col.valid(i)) {
+                int b = col.offsets[i], n = col.offsets[i + 1] - b;
+                int mb, me;
+                hit = rxdev::vm_find<CAP>(P, (const uint8_t*)col.chars + b, n, 0, anchored ? 1 : n, mb, me, L);
+            }
+            out[i] = (uint8_t)hit;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(total, (unsigned long long)__popc(m));
+    }
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(VM_THREADS)
+k_vm_count(ColView col, const uint8_t* __restrict__ img, int img_bytes, const uint8_t* __restrict__ uflags,
+           int32_t* __restrict__ out, unsigned long long* __restrict__ total)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    rxdev::DevProg P = rxdev::bind_program(stage_program(img, img_bytes, smem), uflags);
+    rxdev::Lists<CAP> L;
+    L.init();
+    for (int base = blockIdx.x * blockDim.x; base < col.n; base += gridDim.x * blockDim.x) {
+        int i = base + threadIdx.x;
+        int found = 0;
+        if (i < col.n) {
+            if (col.valid(i)) {
+                int b = col.offsets[i], n = col.offsets[i + 1] - b;
+                found = rxdev::row_count<CAP>(P, (const uint8_t*)col.chars + b, n, L);
+            }
+            out[i] = found;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, found != 0);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(total, (unsigned long long)__popc(m));
+    }
+}
+
+// replace.cu:39-107 — pass 1 (out_chars == nullptr) writes the new byte length per row, pass 2 writes bytes
+template <int CAP>
+__global__ void __launch_bounds__(VM_THREADS)
+k_vm_replace(ColView col, const uint8_t* __restrict__ img, int img_bytes, const uint8_t* __restrict__ uflags,
+             const char* __restrict__ repl, int repl_len, int maxrepl, int32_t* __restrict__ out_len,
+             const int32_t* __restrict__ out_off, char* __restrict__ out_chars)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    rxdev::DevProg P = rxdev::bind_program(stage_program(img, img_bytes, smem), uflags);
+    rxdev::Lists<CAP> L;
+    L.init();
+    for (int base = blockIdx.x * blockDim.x; base < col.n; base += gridDim.x * blockDim.x) {
+        int i = base + threadIdx.x;
+        if (i >= col.n) continue;
+        if (!col.valid(i)) { if (!out_chars) out_len[i] = 0; continue; }
+        int b = col.offsets[i], n = col.offsets[i + 1] - b;
+        const uint8_t* s = (const uint8_t*)col.chars + b;
+        int total = rxdev::row_replace<CAP>(P, s, n, repl, repl_len, maxrepl, out_chars ? out_chars + out_off[i] : nullptr, L);
+        if (!out_chars) out_len[i] = total;
+    }
+}
+
+// replace_multi.cu:40-106 — at every character position try each program anchored there, first hit wins
+struct MultiProgs {
+    const uint8_t* const* images;  // device array of device images
+    int count;
+};
+template <int CAP>
+__global__ void __launch_bounds__(VM_THREADS)
+k_vm_replace_multi(ColView col, MultiProgs progs, const uint8_t* __restrict__ uflags, ColView repls, int32_t* __restrict__ out_len,
+                   const int32_t* __restrict__ out_off, char* __restrict__ out_chars)
+{
+    rxdev::Lists<CAP> L;
+    L.init();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < col.n; i += gridDim.x * blockDim.x) {
+        if (!col.valid(i)) { if (!out_chars) out_len[i] = 0; continue; }
+        int b = col.offsets[i], n = col.offsets[i + 1] - b;
+        const uint8_t* s = (const uint8_t*)col.chars + b;
+        int total = rxdev::row_replace_multi<CAP>(progs.images, progs.count, uflags, repls, s, n,
+                                                  out_chars ? out_chars + out_off[i] : nullptr, L);
+        if (!out_chars) out_len[i] = total;
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+static inline int vm_grid(int n)
+{
+    int want = (n + VM_THREADS - 1) / VM_THREADS;
+    int cap = num_sms() * 16;
+    return want < cap ? (want > 0 ? want : 1) : cap;
+}
+
+#define DISPATCH_CAP(cap, KERNEL, grid, smem, ...)                                         \
+    do {                                                                                   \
+        if ((cap) == 32) LAUNCH(KERNEL<32>, grid, VM_THREADS, smem, __VA_ARGS__);          \
+        else if ((cap) == 256) LAUNCH(KERNEL<256>, grid, VM_THREADS, smem, __VA_ARGS__);   \
+        else LAUNCH(KERNEL<1024>, grid, VM_THREADS, smem, __VA_ARGS__);                    \
+    } while (0)
+
+static int check_cap(const Compiled& c, const char* who)
+{
+    int cap = cap_tier((int)c.prog.insts.size());
+    if (!cap)
+        throw ArgError{fail(CUSTR_ERR_INVALID, std::string(who) + ": number of instructions (" +
+                                                   std::to_string(c.prog.insts.size()) + ") exceeds available memory")};
+    return cap;
+}
+
+static int smem_for(const Compiled& c) { return (int)c.image.size() <= SMEM_PROG_MAX ? (int)((c.image.size() + 15) & ~15ull) : 0; }
+
+static unsigned long long read_counter(unsigned long long* d)
+{
+    unsigned long long h = 0;
+    CUSTR_CUDA(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    return h;
+}
+
+static int bool_search(const custr_column* col, const char* pattern, uint8_t* results, int devmem, bool anchored, const char* who)
+{
+    if (!col || !pattern || !results) return fail(CUSTR_ERR_ARG, std::string(who) + ": null argument");
+    int32_t n = col->n;
+    if (n == 0) return 0;
+    CompiledPtr c = get_compiled(pattern);
+    ResultBuf<uint8_t> out(results, n, devmem);
+    Scratch<unsigned long long> total(1);
+    CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
+    bool done = false;
+    if (g_forced_tier != 1) {
+        if (!c->plans_built) {
+            c->plan_contains = bits::lower(c->prog, false, host_unicode_flags());
+            c->plan_match = bits::lower(c->prog, true, host_unicode_flags());
+            c->plans_built = true;
+        }
+        const std::shared_ptr<bits::Plan>& plan = anchored ? c->plan_match : c->plan_contains;
+        if (plan) {
+            bits::run(*plan, col, out.dev, total.get());
+            g_last_tier = "bitstream";
+            done = true;
+        }
+    }
+    if (!done) {
+        int cap = check_cap(*c, who);
+        DISPATCH_CAP(cap, k_vm_bool, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
+                     (int)c->image.size(), device_unicode_flags(), anchored ? 1 : 0, out.dev, total.get());
+        g_last_tier = "pikevm";
+    }
+    int matches = (int)read_counter(total.get());
+    out.finish();
+    return matches;
+}
+
+static custr_column* finish_replace(const custr_column* col, Scratch<int32_t>& lens, BufPtr& off, int64_t& total)
+{
+    off = dev_alloc(sizeof(int32_t) * (size_t)(col->n + 1));
+    total = scan_lengths_to_offsets(lens.get(), (int32_t*)off->ptr, col->n);
+    if (total > 0x7fffffffLL) throw ArgError{fail(CUSTR_ERR_INVALID, "replace: result exceeds 2 GiB of chars (int32 offsets)")};
+    return nullptr;
+}
+
+static BufPtr copy_validity(const custr_column* col)
+{
+    if (!col->validity) return nullptr;
+    BufPtr v = dev_alloc((col->n + 7) / 8);
+    // re-aligned copy through the export helper
+    custr_create_offsets(col, nullptr, nullptr, (uint8_t*)v->ptr, 1);
+    return v;
+}
+
+}  // namespace custr
+
+using namespace custr;
+
+extern "C" {
+
+const char* custr_last_regex_tier(void) { return g_last_tier; }
+void custr_set_regex_tier(int tier) { g_forced_tier = tier; }
+
+int custr_regex_describe(const char* pattern, char* buf, size_t buflen)
+{
+    if (!pattern) return CUSTR_ERR_ARG;
+    rx::Program p = rx::compile(pattern);
+    std::string d = p.describe();
+    std::shared_ptr<bits::Plan> plan = bits::lower(p, false, host_unicode_flags());
+    d += plan ? "bitstream: " + bits::describe(*plan) + "\n" : "bitstream: not eligible\n";
+    if (buf && buflen) {
+        size_t k = d.size() < buflen - 1 ? d.size() : buflen - 1;
+        memcpy(buf, d.data(), k);
+        buf[k] = 0;
+    }
+    return (int)p.insts.size();
+}
+
+int custr_contains_re(const custr_column* col, const char* pattern, uint8_t* results, int devmem)
+{
+    return guarded([&] { return bool_search(col, pattern, results, devmem, false, "contains_re"); }, (int)CUSTR_ERR_ARG,
+                   (int)CUSTR_ERR_CUDA);
+}
+
+int custr_match(const custr_column* col, const char* pattern, uint8_t* results, int devmem)
+{
+    return guarded([&] { return bool_search(col, pattern, results, devmem, true, "match"); }, (int)CUSTR_ERR_ARG,
+                   (int)CUSTR_ERR_CUDA);
+}
+
+int custr_count_re(const custr_column* col, const char* pattern, int32_t* results, int devmem)
+{
+    return guarded(
+        [&]() -> int {
+            if (!col || !pattern || !results) return fail(CUSTR_ERR_ARG, "count_re: null argument");
+            int32_t n = col->n;
+            if (n == 0) return 0;
+            CompiledPtr c = get_compiled(pattern);
+            int cap = check_cap(*c, "count_re");
+            ResultBuf<int32_t> out(results, n, devmem);
+            Scratch<unsigned long long> total(1);
+            CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
+            DISPATCH_CAP(cap, k_vm_count, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
+                         (int)c->image.size(), device_unicode_flags(), out.dev, total.get());
+            g_last_tier = "pikevm";
+            int matches = (int)read_counter(total.get());
+            out.finish();
+            return matches;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
+custr_column* custr_replace_re(const custr_column* col, const char* pattern, const char* repl, int32_t maxrepl)
+{
+    return guarded(
+        [&]() -> custr_column* {
+            if (!col) throw ArgError{fail(CUSTR_ERR_ARG, "replace_re: null column")};
+            if (!pattern || !*pattern) throw ArgError{fail(CUSTR_ERR_INVALID, "nvstrings::replace_re: pattern parameter cannot be null or empty")};
+            if (!repl) repl = "";
+            int32_t n = col->n;
+            if (n == 0) return custr_create_from_offsets(nullptr, 0, nullptr, nullptr, 0, 0);
+            CompiledPtr c = get_compiled(pattern);
+            int cap = check_cap(*c, "replace_re");
+            int repl_len = (int)strlen(repl);
+            BufPtr d_repl = upload(repl, repl_len ? repl_len : 1);
+            Scratch<int32_t> lens((size_t)n + 1);
+            CUSTR_CUDA(cudaMemsetAsync(lens.get() + n, 0, sizeof(int32_t), g_stream));
+            DISPATCH_CAP(cap, k_vm_replace, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
+                         (int)c->image.size(), device_unicode_flags(), (const char*)d_repl->ptr, repl_len, maxrepl, lens.get(),
+                         (const int32_t*)nullptr, (char*)nullptr);
+            BufPtr off;
+            int64_t total = 0;
+            finish_replace(col, lens, off, total);
+            BufPtr chars = dev_alloc((size_t)total);
+            DISPATCH_CAP(cap, k_vm_replace, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
+                         (int)c->image.size(), device_unicode_flags(), (const char*)d_repl->ptr, repl_len, maxrepl,
+                         (int32_t*)nullptr, (const int32_t*)off->ptr, (char*)chars->ptr);
+            g_last_tier = "pikevm";
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));  // d_repl / lens die with this scope
+            return make_column(chars, off, copy_validity(col), n, col->nulls, total);
+        },
+        (custr_column*)nullptr, (custr_column*)nullptr);
+}
+
+custr_column* custr_replace_re_multi(const custr_column* col, const char* const* patterns, int32_t npatterns,
+                                     const custr_column* repls)
+{
+    return guarded(
+        [&]() -> custr_column* {
+            if (!col || !repls) throw ArgError{fail(CUSTR_ERR_ARG, "replace_re: null column")};
+            if (npatterns <= 0 || !patterns) throw ArgError{fail(CUSTR_ERR_INVALID, "replace_re patterns is empty")};
+            if (repls->n != npatterns && repls->n != 1)
+                throw ArgError{fail(CUSTR_ERR_INVALID, "replace_re patterns and repls must have the same number of strings")};
+            int32_t n = col->n;
+            if (n == 0) return custr_create_from_offsets(nullptr, 0, nullptr, nullptr, 0, 0);
+            std::vector<CompiledPtr> progs;
+            std::vector<const uint8_t*> imgs;
+            int cap = 32;
+            for (int t = 0; t < npatterns; ++t) {
+                if (!patterns[t]) throw ArgError{fail(CUSTR_ERR_INVALID, "replace_re: null pattern")};
+                progs.push_back(get_compiled(patterns[t]));
+                int k = check_cap(*progs.back(), "replace_re");
+                if (k > cap) cap = k;
+                imgs.push_back((const uint8_t*)progs.back()->dev_image->ptr);
+            }
+            BufPtr d_imgs = upload(imgs.data(), imgs.size() * sizeof(void*));
+            MultiProgs mp{(const uint8_t* const*)d_imgs->ptr, npatterns};
+            Scratch<int32_t> lens((size_t)n + 1);
+            CUSTR_CUDA(cudaMemsetAsync(lens.get() + n, 0, sizeof(int32_t), g_stream));
+            DISPATCH_CAP(cap, k_vm_replace_multi, vm_grid(n), 0, view_of(col), mp, device_unicode_flags(), view_of(repls),
+                         lens.get(), (const int32_t*)nullptr, (char*)nullptr);
+            BufPtr off;
+            int64_t total = 0;
+            finish_replace(col, lens, off, total);
+            BufPtr chars = dev_alloc((size_t)total);
+            DISPATCH_CAP(cap, k_vm_replace_multi, vm_grid(n), 0, view_of(col), mp, device_unicode_flags(), view_of(repls),
+                         (int32_t*)nullptr, (const int32_t*)off->ptr, (char*)chars->ptr);
+            g_last_tier = "pikevm";
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            return make_column(chars, off, copy_validity(col), n, col->nulls, total);
+        },
+        (custr_column*)nullptr, (custr_column*)nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,274 @@
+// Exact per-row Pike VM over the compiled program (regex_prog.h).  This is the engine of record: it
+// reproduces the reference's dreprog::regexec (cpp/src/regex/regexec.inl:204-442) step for step — seed order,
+// breadth-wise epsilon rounds, first-activation-wins de-duplication, END cutting lower-priority threads — so
+// that match existence AND match spans are bit-identical.  The faster bit-parallel tier (regex_bits.cu) is only
+// used for patterns it can prove equivalent; everything else runs here.
+//
+// Differences in mechanism (not in results): positions are byte offsets (the reference walks char indices and
+// re-derives byte offsets with O(n) scans, custring_view.inl:261-281); lists live in per-thread local arrays
+// sized by instruction-count tier; resetting a list clears only the bits it set; ASCII class tests are a
+// 128-bit bitmap lookup.
+#pragma once
+#include "common.cuh"
+#include "device_utils.cuh"
+#include "regex_prog.h"
+
+namespace custr {
+namespace rxdev {
+
+struct DevProg {
+    const rx::DevHeader* h;
+    const rx::Inst* insts;
+    const int32_t* starts;
+    const rx::DevClass* classes;
+    const uint32_t* ranges;
+    const uint8_t* uflags;
+};
+
+CUSTR_HD DevProg bind_program(const uint8_t* img, const uint8_t* uflags)
+{
+    DevProg p;
+    p.h = (const rx::DevHeader*)img;
+    p.insts = (const rx::Inst*)(img + sizeof(rx::DevHeader));
+    p.starts = (const int32_t*)(p.insts + p.h->ninsts);
+    p.classes = (const rx::DevClass*)(p.starts + p.h->nstarts);
+    p.ranges = (const uint32_t*)(p.classes + p.h->nclasses);
+    p.uflags = uflags;
+    return p;
+}
+
+CUSTR_HD bool class_match(const DevProg& P, int cls, uint32_t c)
+{
+    const rx::DevClass& k = P.classes[cls];
+    if (c < 128u) return (k.ascii[c >> 5] >> (c & 31)) & 1u;
+    const uint32_t* r = P.ranges + k.range_begin;
+    for (int i = 0; i < k.range_count; i += 2)
+        if (c >= r[i] && c <= r[i + 1]) return true;
+    int b = k.builtins;
+    if (!b) return false;
+    uint32_t cp = packed_to_cp(c);
+    if (cp > 0xFFFFu) return false;
+    uint32_t f = CUSTR_LDG(P.uflags + cp);
+    bool alnum = (f & 15u) != 0, space = (f & 16u) != 0, digit = (f & 4u) != 0;
+    if ((b & rx::CB_W) && alnum) return true;
+    if ((b & rx::CB_S) && space) return true;
+    if ((b & rx::CB_D) && digit) return true;
+    if ((b & rx::CB_NW) && !alnum) return true;   // c is not '\n' / '_' here (non-ASCII)
+    if ((b & rx::CB_NS) && !space) return true;
+    if ((b & rx::CB_ND) && !digit) return true;
+    return false;
+}
+
+template <int CAP>
+struct Lists {
+    uint16_t id[2][CAP];
+    int32_t beg[2][CAP];
+    uint32_t mask[2][(CAP + 31) / 32];
+    int size[2];
+
+    CUSTR_HD void init()
+    {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            for (int w = 0; w < (CAP + 31) / 32; ++w) mask[k][w] = 0;
+            size[k] = 0;
+        }
+    }
+    CUSTR_HD void reset(int k)
+    {
+        for (int i = 0; i < size[k]; ++i) {
+            int v = id[k][i];
+            mask[k][v >> 5] &= ~(1u << (v & 31));
+        }
+        size[k] = 0;
+    }
+    CUSTR_HD void activate(int k, int inst, int b)
+    {
+        uint32_t bit = 1u << (inst & 31);
+        if (mask[k][inst >> 5] & bit) return;
+        mask[k][inst >> 5] |= bit;
+        id[k][size[k]] = (uint16_t)inst;
+        beg[k][size[k]] = b;
+        ++size[k];
+    }
+};
+
+// Search row bytes s[0..n) starting at byte offset `begin`; new threads are seeded at offset `off` only while
+// off < seed_limit (n for an unanchored search; begin+1 for "match only here": reference `end = begin+1`).
+// On success mbeg/mend are the byte offsets of the winning match.
+template <int CAP>
+__host__ __device__ int vm_find(const DevProg& P, const uint8_t* __restrict__ s, int n, int begin, int seed_limit, int& mbeg,
+                       int& mend, Lists<CAP>& L)
+{
+    int match = 0;
+    int off = begin;
+    int cur = 0;
+    L.reset(0);
+    L.reset(1);
+    const int ninsts = P.h->ninsts;
+    const int nstarts = P.h->nstarts;
+    const int start_op = P.h->start_op;
+    const uint32_t start_arg = P.h->start_arg;
+    uint32_t prev = (begin > 0 && begin <= n) ? utf8_packed_before(s + begin, s) : 0;
+    uint32_t c;
+    do {
+        if (L.size[cur] == 0) {  // start-skip (regexec.inl:217-246); result-neutral, saves work
+            if (start_op == rx::OP_CHAR && start_arg != 0 && start_arg < 0x80u) {
+                int o = off;
+                while (o < n && s[o] != (uint8_t)start_arg) ++o;
+                if (o >= n) return match;
+                if (o != off) { off = o; prev = utf8_packed_before(s + off, s); }
+            } else if (start_op == rx::OP_BOL && off != 0 && start_arg != '^')
+                return match;
+        }
+        if (off < seed_limit && !match)
+            for (int i = 0; i < nstarts; ++i) L.activate(cur, P.starts[i], off);
+
+        int w = 1;
+        c = off < n ? utf8_packed(s + off, s + n, w) : 0;
+
+        // ---- epsilon rounds: rebuild the list until nothing expands
+        bool expanded;
+        int rounds = 0;
+        do {
+            const int nxt = cur ^ 1;
+            L.reset(nxt);
+            expanded = false;
+            for (int i = 0; i < L.size[cur]; ++i) {
+                const int id = L.id[cur][i];
+                const int b = L.beg[cur][i];
+                const rx::Inst in = P.insts[id];
+                int go = -1;
+                switch (in.op) {
+                case rx::OP_CHAR: case rx::OP_ANY: case rx::OP_ANYNL: case rx::OP_CLASS: case rx::OP_NCLASS: case rx::OP_END:
+                    go = id;
+                    break;
+                case rx::OP_LBRA: case rx::OP_RBRA:
+                    go = in.next; expanded = true;
+                    break;
+                case rx::OP_BOL:
+                    if (off == 0 || (in.arg == '^' && prev == '\n')) { go = in.next; expanded = true; }
+                    break;
+                case rx::OP_EOL:
+                    if (c == 0 || (in.arg == '$' && c == '\n')) { go = in.next; expanded = true; }
+                    break;
+                case rx::OP_BOW: case rx::OP_NBOW: {
+                    bool ca = is_alnum_packed(c, P.uflags);
+                    bool pa = is_alnum_packed(off ? prev : 0, P.uflags);
+                    if ((ca != pa) == (in.op == rx::OP_BOW)) { go = in.next; expanded = true; }
+                    break;
+                }
+                case rx::OP_SPLIT:
+                    L.activate(nxt, in.other, b);
+                    go = in.next; expanded = true;
+                    break;
+                default: break;  // OP_BAD: thread dies
+                }
+                if (go >= 0) L.activate(nxt, go, b);
+            }
+            cur = nxt;
+        } while (expanded && ++rounds <= ninsts + 1);
+
+        // ---- consume c
+        {
+            const int nxt = cur ^ 1;
+            L.reset(nxt);
+            for (int i = 0; i < L.size[cur]; ++i) {
+                const int id = L.id[cur][i];
+                const rx::Inst in = P.insts[id];
+                bool take = false;
+                switch (in.op) {
+                case rx::OP_CHAR: take = in.arg == c; break;
+                case rx::OP_ANY: take = c != '\n'; break;
+                case rx::OP_ANYNL: take = true; break;
+                case rx::OP_CLASS: take = class_match(P, (int)in.arg, c); break;
+                case rx::OP_NCLASS: take = !class_match(P, (int)in.arg, c); break;
+                case rx::OP_END:
+                    match = 1;
+                    mbeg = L.beg[cur][i];
+                    mend = off;
+                    i = L.size[cur];  // cut every lower-priority thread
+                    break;
+                default: break;
+                }
+                if (take) L.activate(nxt, in.next, L.beg[cur][i]);
+            }
+            cur = nxt;
+        }
+        off += w;
+        prev = c;
+    } while (c && (L.size[cur] > 0 || !match));
+    return match;
+}
+
+// ---- per-row drivers (shared by the kernels in regex.cu and by the host simulation in tests/sim) ----------
+
+// count.cu:168-196: number of non-overlapping matches
+template <int CAP>
+__host__ __device__ int row_count(const DevProg& P, const uint8_t* __restrict__ s, int n, Lists<CAP>& L)
+{
+    int found = 0, begin = 0;
+    while (begin <= n) {
+        int mb = 0, me = 0;
+        if (!vm_find<CAP>(P, s, n, begin, n, mb, me, L)) break;
+        ++found;
+        if (me > mb) begin = me;
+        else begin = mb + (mb < n ? utf8_width(s[mb]) : 1);
+    }
+    return found;
+}
+
+// replace.cu:39-107: returns the new byte length; writes the new bytes when o != nullptr
+template <int CAP>
+__host__ __device__ int row_replace(const DevProg& P, const uint8_t* __restrict__ s, int n, const char* __restrict__ repl,
+                                    int repl_len, int maxrepl, char* o, Lists<CAP>& L)
+{
+    int budget = maxrepl < 0 ? utf8_count_chars(s, n) : maxrepl;
+    int total = n, last = 0, begin = 0;
+    while (budget > 0) {
+        int mb = 0, me = 0;
+        if (!vm_find<CAP>(P, s, n, begin, n, mb, me, L)) break;
+        total += repl_len - (me - mb);
+        if (o) {
+            for (int k = last; k < mb; ++k) *o++ = (char)s[k];
+            for (int k = 0; k < repl_len; ++k) *o++ = repl[k];
+            last = me;
+        }
+        begin = me;
+        --budget;
+    }
+    if (o) for (int k = last; k < n; ++k) *o++ = (char)s[k];
+    return total;
+}
+
+// replace_multi.cu:40-106: at every character position try each program anchored there, first hit wins
+template <int CAP>
+__host__ __device__ int row_replace_multi(const uint8_t* const* images, int nprogs, const uint8_t* uflags, const ColView& repls,
+                                          const uint8_t* __restrict__ s, int n, char* o, Lists<CAP>& L)
+{
+    int total = n, last = 0, pos = 0;
+    while (pos < n) {
+        int adv = utf8_width(s[pos]);
+        for (int t = 0; t < nprogs; ++t) {
+            DevProg P = bind_program(images[t], uflags);
+            int mb = 0, me = 0;
+            if (!vm_find<CAP>(P, s, n, pos, pos + 1, mb, me, L)) continue;
+            int r = repls.n == 1 ? 0 : t;
+            int rb = repls.offsets[r], rl = repls.valid(r) ? repls.offsets[r + 1] - rb : 0;
+            total += rl - (me - mb);
+            if (o) {
+                for (int k = last; k < mb; ++k) *o++ = (char)s[k];
+                for (int k = 0; k < rl; ++k) *o++ = repls.chars[rb + k];
+                last = me;
+            }
+            if (me > pos) adv = me - pos;  // the reference spins forever on an empty match; we step on
+            break;
+        }
+        pos += adv;
+    }
+    if (o) for (int k = last; k < n; ++k) *o++ = (char)s[k];
+    return total;
+}
+
+}  // namespace rxdev
+}  // namespace custr

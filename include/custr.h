@@ -1,0 +1,141 @@
+/*
+ * custr.h — thin C-ABI of the B200-native string-column engine (libcustr.so).
+ *
+ * This is the drop-in boundary below the NVStrings / NVCategory / NVText classes: every entry point
+ * replaces one reference method (cited per function as file:line under rapidsai/custrings) and takes only
+ * plain pointers, sizes and opaque handles.  Conventions:
+ *   - a column is an immutable Arrow-style triple resident in HBM: chars uint8[], offsets int32[n+1],
+ *     validity bits (LSB-first, 1 = valid; NULL pointer = no nulls).  Replaces the reference's
+ *     custring_view*[N] + object buffer (cpp/src/strings/NVStringsImpl.h:25-57).
+ *   - functions returning int return >= 0 on success (usually the reference method's own return value) or a
+ *     negative custr_status; custr_last_error() gives the message (thread local).  Nothing throws.
+ *   - `devmem != 0` means the result / input array pointer is a device pointer, exactly like the
+ *     reference's `bool devmem` / `bool todevice` arguments.
+ *   - all work is enqueued on the stream set with custr_set_stream() (default: the legacy stream 0, as in
+ *     the reference, cpp/src/strings/count.cu:66) and the call returns after the host-visible results exist.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails with
+ *     CUSTR_ERR_CUDA.
+ */
+#ifndef CUSTR_H
+#define CUSTR_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct custr_column custr_column;      /* device string column (offsets, chars, validity) */
+typedef struct custr_category custr_category;  /* dictionary: keys column + int32 values[n]       */
+
+enum custr_status {
+    CUSTR_OK = 0,
+    CUSTR_ERR_ARG = -1,     /* reference returns -1 for null pattern/results (count.cu:61-62)             */
+    CUSTR_ERR_INVALID = -2, /* reference throws std::invalid_argument (replace.cu:112, modify.cu:111)     */
+    CUSTR_ERR_CUDA = -3,    /* reference throws std::runtime_error via CUDA_TRY (util.h:47-55)            */
+    CUSTR_ERR_ALLOC = -4    /* reference throws std::runtime_error from device_alloc (util.inl:96-107)    */
+};
+
+const char* custr_last_error(void);
+const char* custr_version(void);
+int  custr_set_device(int device);
+void custr_set_stream(void* cuda_stream);      /* cudaStream_t; thread local                              */
+int  custr_sync(void);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+long long custr_launch_count(void);
+/* name of the regex execution tier used by the last regex call on this thread ("bitstream", "pikevm") */
+const char* custr_last_regex_tier(void);
+/* force a tier for A/B testing: 0 = auto, 1 = exact Pike VM only */
+void custr_set_regex_tier(int tier);
+
+/* ---- column create / export  (NVStrings::create_from_offsets NVStrings.cu:109-119, create_from_array :74-86,
+ *      create_offsets :402-482, to_host :266-346, set_null_bitarray :493-544, byte_count/len attrs.cu:32,72) ---- */
+/* Copies host or device (devmem) buffers into a new column. validity may be NULL. Null rows are kept null
+ * whatever their offsets say; bytes of null rows are not copied semantically (exported as zero length). */
+custr_column* custr_create_from_offsets(const char* chars, int32_t count, const int32_t* offsets,
+                                        const uint8_t* validity, int32_t nulls, int devmem);
+/* Zero-copy view over caller-owned device buffers (must outlive the column). */
+custr_column* custr_adopt_device(const char* chars, int32_t count, const int32_t* offsets, const uint8_t* validity, int32_t nulls);
+/* Host array of NUL-terminated strings, NULL entries = null rows. */
+custr_column* custr_create_from_array(const char* const* strs, uint32_t count);
+void     custr_column_free(custr_column* col);
+uint32_t custr_size(const custr_column* col);
+int64_t  custr_chars_bytes(const custr_column* col);     /* bytes in the chars buffer                      */
+int32_t  custr_null_count(const custr_column* col);
+const char*    custr_chars_ptr(const custr_column* col);     /* device pointers                             */
+const int32_t* custr_offsets_ptr(const custr_column* col);
+const uint8_t* custr_validity_ptr(const custr_column* col);  /* NULL if no nulls                            */
+/* Export to (chars, offsets[n+1], validity[(n+7)/8]); any of the three may be NULL to skip. Null rows export
+ * as zero length (NVStrings.cu:427-432). Returns the null count. */
+int custr_create_offsets(const custr_column* col, char* chars, int32_t* offsets, uint8_t* validity, int devmem);
+/* bitarray bit=1 valid; emptyIsNull also clears bits of empty rows. Returns the number of cleared bits. */
+int custr_set_null_bitarray(const custr_column* col, uint8_t* bitarray, int empty_is_null, int devmem);
+/* per-row byte length (-1 for null rows) / character length (-1 for null); either pointer may be NULL.
+ * Returns total bytes (byte_count) or number of non-null rows (len). */
+int64_t custr_byte_count(const custr_column* col, int32_t* lengths, int devmem);
+int     custr_len(const custr_column* col, int32_t* lengths, int devmem);
+/* MurmurHash3_x86_32 seed 31 over the row bytes, 0 for nulls (custring.inl:164-232, convert.cu:34-63). */
+int custr_hash(const custr_column* col, uint32_t* results, int devmem);
+
+/* ---- regex (Reprog NFA): NVStrings::contains_re count.cu:59-110, match :113-165, count_re :199-250 ---- */
+int custr_contains_re(const custr_column* col, const char* pattern, uint8_t* results, int devmem);
+int custr_match(const custr_column* col, const char* pattern, uint8_t* results, int devmem);
+int custr_count_re(const custr_column* col, const char* pattern, int32_t* results, int devmem);
+/* NVStrings::replace_re replace.cu:110-189; multi-pattern form replace_multi.cu:110-197 */
+custr_column* custr_replace_re(const custr_column* col, const char* pattern, const char* repl, int32_t maxrepl);
+custr_column* custr_replace_re_multi(const custr_column* col, const char* const* patterns, int32_t npatterns,
+                                     const custr_column* repls);
+/* Debug/inspection: compile a pattern and print its instruction listing into buf (host). Returns #instructions. */
+int custr_regex_describe(const char* pattern, char* buf, size_t buflen);
+
+/* ---- literal find / replace: NVStrings::find find.cu:75-120, rfind :163-199, contains :237-272,
+ *      startswith/endswith :316-387, find_multiple :202-233; replace modify.cu:109-192, multi :263-299 ---- */
+int custr_find(const custr_column* col, const char* str, int32_t start, int32_t end, int32_t* results, int devmem);
+int custr_rfind(const custr_column* col, const char* str, int32_t start, int32_t end, int32_t* results, int devmem);
+int custr_contains(const custr_column* col, const char* str, uint8_t* results, int devmem);
+int custr_startswith(const custr_column* col, const char* str, uint8_t* results, int devmem);
+int custr_endswith(const custr_column* col, const char* str, uint8_t* results, int devmem);
+int custr_find_multiple(const custr_column* col, const custr_column* targets, int32_t* results, int devmem);
+custr_column* custr_replace(const custr_column* col, const char* str, const char* repl, int32_t maxrepl);
+custr_column* custr_replace_multi(const custr_column* col, const custr_column* targets, const custr_column* repls);
+
+/* ---- split: NVStrings::split split.cu:734-822 (delimiter) / :863-956 (whitespace when delimiter==NULL),
+ *      rsplit :960-1160, split_record :125-223 / :270-430 ---- */
+/* Column-major. Writes up to `cap` new columns into out[]; returns the number of columns (call again with a
+ * larger cap if the return value exceeds cap; extra columns are discarded). */
+int custr_split(const custr_column* col, const char* delimiter, int32_t maxsplit, custr_column** out, int32_t cap);
+int custr_rsplit(const custr_column* col, const char* delimiter, int32_t maxsplit, custr_column** out, int32_t cap);
+/* Row-major, as ONE flat allocation instead of the reference's N objects: *tokens holds every token of every
+ * row in row order, row_offsets[n+1] (caller array, host or device per devmem) delimits each row's slice;
+ * null input rows get an empty slice and are distinguishable through the input validity. Returns total tokens. */
+int custr_split_record(const custr_column* col, const char* delimiter, int32_t maxsplit, custr_column** tokens,
+                       int32_t* row_offsets, int devmem);
+int custr_rsplit_record(const custr_column* col, const char* delimiter, int32_t maxsplit, custr_column** tokens,
+                        int32_t* row_offsets, int devmem);
+/* sub-range view [first, last) of a column as a new column (used to materialise one row of split_record). */
+custr_column* custr_slice_rows(const custr_column* col, int32_t first, int32_t last);
+/* gather rows by index (device or host int32 indices; negative/out-of-range -> null row). */
+custr_column* custr_gather(const custr_column* col, const int32_t* indices, int32_t count, int devmem);
+
+/* ---- NVText::tokenize tokens.cu:123-155 (delimiter==NULL: whitespace), token_count :337-361 ---- */
+custr_column* custr_tokenize(const custr_column* col, const char* delimiter);
+int custr_token_count(const custr_column* col, const char* delimiter, uint32_t* results, int devmem);
+
+/* ---- NVCategory: create_from_strings NVCategory.cu:327-356, NVCategoryImpl_init :220-304,
+ *      get_keys :724-750, get_values :866-878, values_cptr :880-883 ---- */
+custr_category* custr_category_create(const custr_column* const* cols, int32_t ncols);
+void custr_category_free(custr_category* cat);
+uint32_t custr_category_size(const custr_category* cat);
+uint32_t custr_category_keys_size(const custr_category* cat);
+custr_column* custr_category_keys(const custr_category* cat);              /* new column (copy)         */
+int custr_category_values(const custr_category* cat, int32_t* results, int devmem);
+const int32_t* custr_category_values_cptr(const custr_category* cat);      /* device pointer            */
+/* Multi-GPU merge step (NVCategory::create_from_categories NVCategory.cu:430-514 is the reference's analogue):
+ * given this shard's category and the union of all shards' keys (any order, duplicates allowed) returns a new
+ * category whose keys are the sorted distinct union and whose values are remapped. */
+custr_category* custr_category_remap_to_union(const custr_category* cat, const custr_column* all_keys);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUSTR_H */

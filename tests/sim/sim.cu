@@ -1,0 +1,129 @@
+// Host-side simulation harness: runs the SAME __host__ __device__ per-row code the CUDA kernels run
+// (custrings_b200/csrc/regex_vm.cuh, rowops.cuh) on the CPU, one row at a time, so that the engine logic can be
+// fuzzed against the oracle in the GPU-less container (`-m "not gpu"` tests).  Test infrastructure only — it is
+// not a CPU fallback: nothing in custrings_b200/ links or loads it.
+#include "../../custrings_b200/csrc/regex_vm.cuh"
+#include "../../custrings_b200/csrc/rowops.cuh"
+#include "../../custrings_b200/csrc/regex_bits_core.cuh"
+#include <vector>
+#include <string>
+
+using namespace custr;
+
+static const uint8_t k_flags[65536] = {
+#include "../../custrings_b200/csrc/unicode_flags.inc"
+};
+
+namespace {
+struct Prog {
+    rx::Program prog;
+    std::vector<uint8_t> img;
+    rxdev::DevProg P;
+    explicit Prog(const char* pattern)
+    {
+        prog = rx::compile(pattern);
+        img = rx::serialize(prog, k_flags);
+        P = rxdev::bind_program(img.data(), k_flags);
+    }
+};
+using L = rxdev::Lists<1024>;
+}  // namespace
+
+extern "C" {
+
+int sim_describe(const char* pattern, char* buf, int buflen)
+{
+    Prog p(pattern);
+    std::string d = p.prog.describe();
+    std::shared_ptr<bits::Plan> plan = bits::lower(p.prog, false, k_flags);
+    d += plan ? "bitstream: " + bits::describe(*plan) + "\n" : "bitstream: not eligible\n";
+    snprintf(buf, buflen, "%s", d.c_str());
+    return (int)p.prog.insts.size();
+}
+
+int sim_bool(const char* chars, const int32_t* off, const uint8_t* validity, int n, const char* pattern, int anchored, uint8_t* out)
+{
+    Prog p(pattern);
+    if (p.prog.insts.size() > 1024) return -2;
+    ColView col{chars, off, validity, 0, n};
+    L* lists = new L;
+    lists->init();
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        int hit = 0;
+        if (col.valid(i)) {
+            int len = off[i + 1] - off[i], mb, me;
+            hit = rxdev::vm_find<1024>(p.P, (const uint8_t*)chars + off[i], len, 0, anchored ? 1 : len, mb, me, *lists);
+        }
+        out[i] = (uint8_t)hit;
+        total += hit;
+    }
+    delete lists;
+    return total;
+}
+
+int sim_count(const char* chars, const int32_t* off, const uint8_t* validity, int n, const char* pattern, int32_t* out)
+{
+    Prog p(pattern);
+    if (p.prog.insts.size() > 1024) return -2;
+    ColView col{chars, off, validity, 0, n};
+    L* lists = new L;
+    lists->init();
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        int c = 0;
+        if (col.valid(i)) c = rxdev::row_count<1024>(p.P, (const uint8_t*)chars + off[i], off[i + 1] - off[i], *lists);
+        out[i] = c;
+        total += c != 0;
+    }
+    delete lists;
+    return total;
+}
+
+// out_off[n+1] always written; out_chars written when non-null (second call)
+long sim_replace_re(const char* chars, const int32_t* off, const uint8_t* validity, int n, const char* pattern, const char* repl,
+                    int maxrepl, int32_t* out_off, char* out_chars)
+{
+    Prog p(pattern);
+    if (p.prog.insts.size() > 1024) return -2;
+    ColView col{chars, off, validity, 0, n};
+    L* lists = new L;
+    lists->init();
+    int rl = (int)strlen(repl);
+    long run = 0;
+    for (int i = 0; i < n; ++i) {
+        out_off[i] = (int32_t)run;
+        if (col.valid(i))
+            run += rxdev::row_replace<1024>(p.P, (const uint8_t*)chars + off[i], off[i + 1] - off[i], repl, rl, maxrepl,
+                                            out_chars ? out_chars + run : nullptr, *lists);
+    }
+    out_off[n] = (int32_t)run;
+    delete lists;
+    return run;
+}
+
+long sim_replace_re_multi(const char* chars, const int32_t* off, const uint8_t* validity, int n, const char* const* patterns,
+                          int npat, const char* rchars, const int32_t* roff, const uint8_t* rvalid, int nrepl, int32_t* out_off,
+                          char* out_chars)
+{
+    std::vector<Prog*> progs;
+    std::vector<const uint8_t*> imgs;
+    for (int t = 0; t < npat; ++t) { progs.push_back(new Prog(patterns[t])); imgs.push_back(progs.back()->img.data()); }
+    ColView col{chars, off, validity, 0, n};
+    ColView repls{rchars, roff, rvalid, 0, nrepl};
+    L* lists = new L;
+    lists->init();
+    long run = 0;
+    for (int i = 0; i < n; ++i) {
+        out_off[i] = (int32_t)run;
+        if (col.valid(i))
+            run += rxdev::row_replace_multi<1024>(imgs.data(), npat, k_flags, repls, (const uint8_t*)chars + off[i],
+                                                  off[i + 1] - off[i], out_chars ? out_chars + run : nullptr, *lists);
+    }
+    out_off[n] = (int32_t)run;
+    delete lists;
+    for (Prog* q : progs) delete q;
+    return run;
+}
+
+}  // extern "C"

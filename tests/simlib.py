@@ -1,0 +1,79 @@
+"""ctypes access to the host simulation harness (tests/sim) — test infrastructure."""
+import ctypes as C
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        from tests.sim.build_sim import build
+        _lib = C.CDLL(build())
+        _lib.sim_replace_re.restype = C.c_long
+        _lib.sim_replace_re_multi.restype = C.c_long
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _cols(chars, offsets, validity):
+    chars = np.ascontiguousarray(chars, np.uint8)
+    if chars.size == 0:
+        chars = np.zeros(1, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    validity = None if validity is None else np.ascontiguousarray(validity, np.uint8)
+    return chars, offsets, validity
+
+
+def describe(pattern):
+    buf = C.create_string_buffer(1 << 16)
+    lib().sim_describe(pattern.encode() if isinstance(pattern, str) else pattern, buf, len(buf))
+    return buf.value.decode(errors="replace")
+
+
+def bool_search(chars, offsets, validity, pattern, anchored):
+    chars, offsets, validity = _cols(chars, offsets, validity)
+    n = len(offsets) - 1
+    out = np.zeros(max(n, 1), np.uint8)
+    rc = lib().sim_bool(_p(chars), _p(offsets), _p(validity), n, pattern.encode() if isinstance(pattern, str) else pattern, int(anchored), _p(out))
+    return out[:n].astype(bool), rc
+
+
+def count(chars, offsets, validity, pattern):
+    chars, offsets, validity = _cols(chars, offsets, validity)
+    n = len(offsets) - 1
+    out = np.zeros(max(n, 1), np.int32)
+    rc = lib().sim_count(_p(chars), _p(offsets), _p(validity), n, pattern.encode() if isinstance(pattern, str) else pattern, _p(out))
+    return out[:n], rc
+
+
+def replace_re(chars, offsets, validity, pattern, repl, maxrepl=-1):
+    chars, offsets, validity = _cols(chars, offsets, validity)
+    n = len(offsets) - 1
+    pat = pattern.encode() if isinstance(pattern, str) else pattern
+    rp = repl.encode() if isinstance(repl, str) else repl
+    ooff = np.zeros(n + 1, np.int32)
+    total = lib().sim_replace_re(_p(chars), _p(offsets), _p(validity), n, pat, rp, maxrepl, _p(ooff), None)
+    ochars = np.zeros(max(total, 1), np.uint8)
+    lib().sim_replace_re(_p(chars), _p(offsets), _p(validity), n, pat, rp, maxrepl, _p(ooff), _p(ochars))
+    return ochars[:total], ooff
+
+
+def replace_re_multi(chars, offsets, validity, patterns, rchars, roffsets, rvalidity):
+    chars, offsets, validity = _cols(chars, offsets, validity)
+    rchars, roffsets, rvalidity = _cols(rchars, roffsets, rvalidity)
+    n = len(offsets) - 1
+    arr = (C.c_char_p * len(patterns))(*[p.encode() if isinstance(p, str) else p for p in patterns])
+    ooff = np.zeros(n + 1, np.int32)
+    args = (_p(chars), _p(offsets), _p(validity), n, arr, len(patterns), _p(rchars), _p(roffsets), _p(rvalidity), len(roffsets) - 1)
+    total = lib().sim_replace_re_multi(*args, _p(ooff), None)
+    ochars = np.zeros(max(total, 1), np.uint8)
+    lib().sim_replace_re_multi(*args, _p(ooff), _p(ochars))
+    return ochars[:total], ooff
