@@ -1,0 +1,316 @@
+// NVCategory key build: keys = sorted distinct strings (null first), values = int32 index of each row's key.
+// Replaces NVCategory::create_from_strings NVCategory.cu:327-356 -> NVCategoryImpl_init :220-304 (a string-compare
+// merge sort over all N rows + un-sort + unique), get_keys :724-750, get_values :866-878, values_cptr :880-883.
+//
+// B200 design: only the K distinct keys are ever compared as strings.
+//   1. 64-bit hash per row                                  (reads chars once, coalesced per warp)
+//   2. radix sort (hash,row) pairs                          (cub, 8 passes over 12 B/row)
+//   3. adjacent compare: group heads + EXACT byte check inside equal-hash runs (collision => re-hash, new seed)
+//   4. scan heads -> group ids, K representatives
+//   5. merge-sort the K representatives with the reference's comparator (custring.inl:240-261, null first)
+//   6. scatter ranks back: values[row] = rank[group(row)]
+// Observable contract is identical to the reference (keys order, null key first, values); the hash is internal.
+#include "common.cuh"
+#include "rowops.cuh"
+#include <cub/cub.cuh>
+
+namespace custr {
+
+constexpr int CAT_THREADS = 256;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+// one warp per row would waste lanes on 16-byte keys: thread-per-row, 8 bytes at a time
+__global__ void __launch_bounds__(CAT_THREADS)
+k_hash_rows(ColView col, uint64_t seed, uint64_t* __restrict__ hashes, int32_t* __restrict__ rows)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < col.n; i += gridDim.x * blockDim.x) {
+        uint64_t h = 0;
+        if (col.valid(i)) {
+            const uint8_t* s = (const uint8_t*)col.chars + col.offsets[i];
+            int n = col.offsets[i + 1] - col.offsets[i];
+            h = seed ^ ((uint64_t)n * 0x9E3779B97F4A7C15ULL);
+            int k = 0;
+            for (; k + 8 <= n; k += 8) {
+                uint64_t v = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v |= (uint64_t)s[k + j] << (8 * j);
+                h = mix64(h ^ v) + 0x9E3779B97F4A7C15ULL;
+            }
+            uint64_t v = 0;
+            for (int j = 0; k + j < n; ++j) v |= (uint64_t)s[k + j] << (8 * j);
+            h = mix64(h ^ v);
+            if (h == 0) h = 1;  // 0 is reserved for null rows
+        }
+        hashes[i] = h;
+        rows[i] = i;
+    }
+}
+
+__device__ __forceinline__ bool rows_equal(const ColView& col, int a, int b)
+{
+    bool va = col.valid(a), vb = col.valid(b);
+    if (!va || !vb) return va == vb;
+    int ao = col.offsets[a], an = col.offsets[a + 1] - ao;
+    int bo = col.offsets[b], bn = col.offsets[b + 1] - bo;
+    if (an != bn) return false;
+    return row::bytes_equal((const uint8_t*)col.chars + ao, (const uint8_t*)col.chars + bo, an);
+}
+
+__global__ void __launch_bounds__(CAT_THREADS)
+k_group_heads(ColView col, const uint64_t* __restrict__ hashes, const int32_t* __restrict__ rows, int32_t* __restrict__ heads,
+              int* __restrict__ collision)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < col.n; j += gridDim.x * blockDim.x) {
+        int head = 1;
+        if (j > 0 && hashes[j] == hashes[j - 1]) {
+            head = 0;
+            if (!rows_equal(col, rows[j], rows[j - 1])) *collision = 1;
+        }
+        heads[j] = head;
+    }
+}
+
+// gid = inclusive_scan(heads) - 1 (in place array `gids`); representatives[gid] = row at each head
+__global__ void __launch_bounds__(CAT_THREADS)
+k_representatives(const int32_t* __restrict__ heads, const int32_t* __restrict__ gids, const int32_t* __restrict__ rows, int n,
+                  int32_t* __restrict__ reps, int32_t* __restrict__ group_ids)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+        if (heads[j]) { int g = gids[j] - 1; reps[g] = rows[j]; group_ids[g] = g; }
+}
+
+struct KeyLess {
+    ColView col;
+    __device__ bool operator()(const int32_t& a, const int32_t& b) const
+    {
+        bool va = col.valid(a), vb = col.valid(b);
+        if (!va || !vb) return !va && vb;  // null sorts first
+        int ao = col.offsets[a], bo = col.offsets[b];
+        return row::compare_bytes((const uint8_t*)col.chars + ao, col.offsets[a + 1] - ao, (const uint8_t*)col.chars + bo,
+                                  col.offsets[b + 1] - bo) < 0;
+    }
+};
+
+__global__ void k_rank_of_group(const int32_t* __restrict__ sorted_groups, int k, int32_t* __restrict__ rank)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < k) rank[sorted_groups[r]] = r;
+}
+
+__global__ void __launch_bounds__(CAT_THREADS)
+k_scatter_values(const int32_t* __restrict__ rows, const int32_t* __restrict__ gids, const int32_t* __restrict__ rank, int n,
+                 int32_t* __restrict__ values)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) values[rows[j]] = rank[gids[j] - 1];
+}
+
+// concat helper
+__global__ void k_concat_offsets(const int32_t* __restrict__ src, int n, int32_t first_off, int32_t base_bytes, int32_t* __restrict__ dst)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) dst[i] = src[i] - first_off + base_bytes;
+}
+__global__ void k_valid_flags(ColView c, uint8_t* __restrict__ flags)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c.n) flags[i] = c.valid(i);
+}
+
+// binary search of each local key in the (sorted, distinct) global keys
+__global__ void k_lookup_keys(ColView local, ColView global, int32_t* __restrict__ map)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= local.n) return;
+    if (!local.valid(i)) { map[i] = 0; return; }  // null key is key 0 wherever it exists
+    const uint8_t* s = (const uint8_t*)local.chars + local.offsets[i];
+    int n = local.offsets[i + 1] - local.offsets[i];
+    int lo = 0, hi = global.n - 1, found = -1;
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        int c;
+        if (!global.valid(mid)) c = 1;
+        else {
+            int go = global.offsets[mid];
+            c = row::compare_bytes(s, n, (const uint8_t*)global.chars + go, global.offsets[mid + 1] - go);
+        }
+        if (c == 0) { found = mid; break; }
+        if (c < 0) hi = mid - 1; else lo = mid + 1;
+    }
+    map[i] = found;
+}
+__global__ void k_remap_values(const int32_t* __restrict__ in, const int32_t* __restrict__ map, int n, int32_t* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = map[in[i]];
+}
+
+static inline int row_grid(int n)
+{
+    int want = (n + CAT_THREADS - 1) / CAT_THREADS;
+    int cap = num_sms() * 32;
+    return want < cap ? (want > 0 ? want : 1) : cap;
+}
+
+static custr_column* concat_columns(const custr_column* const* cols, int ncols)
+{
+    int64_t rows = 0, bytes = 0;
+    int32_t nulls = 0;
+    for (int k = 0; k < ncols; ++k) { rows += cols[k]->n; bytes += cols[k]->nbytes; nulls += cols[k]->nulls; }
+    if (rows > 0x7fffffffLL || bytes > 0x7fffffffLL) throw ArgError{fail(CUSTR_ERR_INVALID, "category: more than 2^31 rows or bytes")};
+    BufPtr off = dev_alloc(sizeof(int32_t) * (size_t)(rows + 1)), chars = dev_alloc((size_t)bytes);
+    Scratch<uint8_t> flags((size_t)rows + 1);
+    int64_t r0 = 0, b0 = 0;
+    for (int k = 0; k < ncols; ++k) {
+        const custr_column* c = cols[k];
+        if (c->nbytes) CUSTR_CUDA(cudaMemcpyAsync((char*)chars->ptr + b0, c->chars + c->first_off, (size_t)c->nbytes, cudaMemcpyDeviceToDevice, g_stream));
+        LAUNCH(k_concat_offsets, (c->n + 256) / 256, 256, 0, c->offsets, c->n, c->first_off, (int32_t)b0, (int32_t*)off->ptr + r0);
+        if (c->n) LAUNCH(k_valid_flags, (c->n + 255) / 256, 256, 0, view_of(c), flags.get() + r0);
+        r0 += c->n;
+        b0 += c->nbytes;
+    }
+    BufPtr bits;
+    if (nulls) { bits = dev_alloc((rows + 7) / 8); pack_bits(flags.get(), (uint8_t*)bits->ptr, (int32_t)rows); }
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    return make_column(chars, off, bits, (int32_t)rows, nulls, bytes);
+}
+
+static custr_category* build_category(const custr_column* col)
+{
+    const int32_t n = col->n;
+    custr_category* cat = new custr_category;
+    std::unique_ptr<custr_category, void (*)(custr_category*)> guard(cat, [](custr_category* c) { custr_category_free(c); });
+    cat->n = n;
+    cat->values_buf = dev_alloc(sizeof(int32_t) * (size_t)(n ? n : 1));
+    if (n == 0) {
+        cat->keys = custr_create_from_offsets(nullptr, 0, nullptr, nullptr, 0, 0);
+        return guard.release();
+    }
+    Scratch<uint64_t> h_in(n), h_out(n);
+    Scratch<int32_t> r_in(n), r_out(n), heads(n), gids(n);
+    Scratch<int> collision(1);
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, h_in.get(), h_out.get(), r_in.get(), r_out.get(), n, 0, 64, g_stream);
+    cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, heads.get(), gids.get(), n, g_stream);
+    BufPtr tmp = dev_alloc(sort_bytes > scan_bytes ? sort_bytes : scan_bytes);
+    uint64_t seed = 0x243F6A8885A308D3ULL;
+    for (int attempt = 0;; ++attempt) {
+        LAUNCH(k_hash_rows, row_grid(n), CAT_THREADS, 0, view_of(col), seed, h_in.get(), r_in.get());
+        CUSTR_CUDA(cub::DeviceRadixSort::SortPairs(tmp->ptr, sort_bytes, h_in.get(), h_out.get(), r_in.get(), r_out.get(), n, 0, 64, g_stream));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUSTR_CUDA(cudaMemsetAsync(collision.get(), 0, sizeof(int), g_stream));
+        LAUNCH(k_group_heads, row_grid(n), CAT_THREADS, 0, view_of(col), (const uint64_t*)h_out.get(), (const int32_t*)r_out.get(),
+               heads.get(), collision.get());
+        int hit = 0;
+        CUSTR_CUDA(cudaMemcpyAsync(&hit, collision.get(), sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+        CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+        if (!hit) break;
+        if (attempt == 3) throw ArgError{fail(CUSTR_ERR_INVALID, "category: persistent 64-bit hash collisions")};
+        seed = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+    }
+    CUSTR_CUDA(cub::DeviceScan::InclusiveSum(tmp->ptr, scan_bytes, heads.get(), gids.get(), n, g_stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    int32_t nkeys = 0;
+    CUSTR_CUDA(cudaMemcpyAsync(&nkeys, gids.get() + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    Scratch<int32_t> reps(nkeys), groups(nkeys), rank(nkeys);
+    LAUNCH(k_representatives, row_grid(n), CAT_THREADS, 0, (const int32_t*)heads.get(), (const int32_t*)gids.get(),
+           (const int32_t*)r_out.get(), n, reps.get(), groups.get());
+    size_t merge_bytes = 0;
+    KeyLess less{view_of(col)};
+    cub::DeviceMergeSort::SortPairs(nullptr, merge_bytes, reps.get(), groups.get(), nkeys, less, g_stream);
+    BufPtr mtmp = dev_alloc(merge_bytes);
+    CUSTR_CUDA(cub::DeviceMergeSort::SortPairs(mtmp->ptr, merge_bytes, reps.get(), groups.get(), nkeys, less, g_stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    LAUNCH(k_rank_of_group, (nkeys + 255) / 256, 256, 0, (const int32_t*)groups.get(), nkeys, rank.get());
+    LAUNCH(k_scatter_values, row_grid(n), CAT_THREADS, 0, (const int32_t*)r_out.get(), (const int32_t*)gids.get(),
+           (const int32_t*)rank.get(), n, (int32_t*)cat->values_buf->ptr);
+    cat->keys = custr_gather(col, reps.get(), nkeys, 1);
+    if (!cat->keys) throw CudaError{cudaErrorUnknown};
+    cat->has_null_key = col->nulls > 0;
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    return guard.release();
+}
+
+}  // namespace custr
+
+using namespace custr;
+
+extern "C" {
+
+custr_category* custr_category_create(const custr_column* const* cols, int32_t ncols)
+{
+    return guarded(
+        [&]() -> custr_category* {
+            if (!cols || ncols <= 0) throw ArgError{fail(CUSTR_ERR_ARG, "category: no input columns")};
+            for (int k = 0; k < ncols; ++k)
+                if (!cols[k]) throw ArgError{fail(CUSTR_ERR_ARG, "category: null input column")};
+            if (ncols == 1) return build_category(cols[0]);
+            std::unique_ptr<custr_column> all(concat_columns(cols, ncols));
+            return build_category(all.get());
+        },
+        (custr_category*)nullptr, (custr_category*)nullptr);
+}
+
+void custr_category_free(custr_category* cat)
+{
+    if (!cat) return;
+    custr_column_free(cat->keys);
+    delete cat;
+}
+
+uint32_t custr_category_size(const custr_category* cat) { return cat ? (uint32_t)cat->n : 0; }
+uint32_t custr_category_keys_size(const custr_category* cat) { return cat && cat->keys ? (uint32_t)cat->keys->n : 0; }
+
+custr_column* custr_category_keys(const custr_category* cat)
+{
+    if (!cat || !cat->keys) return nullptr;
+    return custr_slice_rows(cat->keys, 0, cat->keys->n);  // shares the immutable buffers
+}
+
+int custr_category_values(const custr_category* cat, int32_t* results, int devmem)
+{
+    return guarded(
+        [&]() -> int {
+            if (!cat || !results) return fail(CUSTR_ERR_ARG, "get_values: null argument");
+            if (cat->n == 0) return 0;
+            cudaMemcpyKind kind = devmem ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+            CUSTR_CUDA(cudaMemcpyAsync(results, cat->values_buf->ptr, sizeof(int32_t) * (size_t)cat->n, kind, g_stream));
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            return cat->n;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
+const int32_t* custr_category_values_cptr(const custr_category* cat) { return cat ? (const int32_t*)cat->values_buf->ptr : nullptr; }
+
+custr_category* custr_category_remap_to_union(const custr_category* cat, const custr_column* all_keys)
+{
+    return guarded(
+        [&]() -> custr_category* {
+            if (!cat || !all_keys) throw ArgError{fail(CUSTR_ERR_ARG, "remap_to_union: null argument")};
+            std::unique_ptr<custr_category, void (*)(custr_category*)> uni(build_category(all_keys), [](custr_category* c) { custr_category_free(c); });
+            custr_category* out = new custr_category;
+            out->n = cat->n;
+            out->values_buf = dev_alloc(sizeof(int32_t) * (size_t)(cat->n ? cat->n : 1));
+            out->keys = uni->keys;
+            uni->keys = nullptr;
+            out->has_null_key = out->keys->nulls > 0;
+            int32_t k = cat->keys->n;
+            if (k && cat->n) {
+                Scratch<int32_t> map(k);
+                LAUNCH(k_lookup_keys, (k + 255) / 256, 256, 0, view_of(cat->keys), view_of(out->keys), map.get());
+                LAUNCH(k_remap_values, (cat->n + 255) / 256, 256, 0, (const int32_t*)cat->values_buf->ptr, (const int32_t*)map.get(),
+                       cat->n, (int32_t*)out->values_buf->ptr);
+                CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            }
+            return out;
+        },
+        (custr_category*)nullptr, (custr_category*)nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+"""nvcategory — host-side mirror of the reference shim python/nvcategory.py for the key-build path
+(from_strings :78, keys :242, values :364, keys_size, size), over libcustr.so's C-ABI.
+
+Multi-GPU: from_strings_sharded() builds the local dictionary of a row shard, all-gathers the
+distinct keys of every rank with torch.distributed (NCCL over NVLink on GPUs, gloo in CPU tests of the host
+logic) and remaps the local values onto the global sorted key set.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import as_ptr, check_handle, check_rc, lib
+from . import nvstrings as _nvs
+
+
+def from_strings(*args):
+    """Create an nvcategory from one or more nvstrings.  reference nvcategory.py:78 -> NVCategory.cu:327-356"""
+    cols = []
+    for a in args:
+        cols.extend(a if isinstance(a, (list, tuple)) else [a])
+    for c in cols:
+        if type(c).__name__ != "nvstrings":  # reference checks the type NAME, pycategory.cpp:42-71
+            raise ValueError("from_strings: arguments must be nvstrings")
+    arr = (C.c_void_p * len(cols))(*[c.m_cptr for c in cols])
+    h = lib().custr_category_create(arr, len(cols))
+    return nvcategory(check_handle(h, "from_strings"))
+
+
+def to_device(strs):
+    """reference nvcategory.py:7"""
+    return from_strings(_nvs.to_device(strs))
+
+
+def from_offsets(sbuf, obuf, scount, nbuf=None, ncount=0, bdevmem=False):
+    """reference nvcategory.py:37 -> NVCategory.cu:359-370"""
+    return from_strings(_nvs.from_offsets(sbuf, obuf, scount, nbuf, ncount, bdevmem))
+
+
+def gather_keys_host(local_keys, group=None):
+    """All-gather the key strings of every rank (host lists; the payload is K keys x ~16 B per rank, i.e.
+    latency-bound).  Returns the concatenated list in rank order."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return list(local_keys)
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, list(local_keys), group=group)
+    merged = []
+    for part in out:
+        merged.extend(part)
+    return merged
+
+
+def gather_keys_device(keys, group=None):
+    """All-gather an nvstrings of keys across ranks with tensor collectives (NCCL on GPUs): sizes first, then the
+    max-padded (offsets, chars, validity) payloads.  Returns an nvstrings holding every rank's keys."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return keys
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    chars, offsets, validity = keys.to_arrays()
+    n = len(offsets) - 1
+    meta = torch.tensor([n, int(offsets[-1])], dtype=torch.int64, device=dev)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    metas = [m.cpu().tolist() for m in metas]
+    max_n = max(m[0] for m in metas)
+    max_b = max(m[1] for m in metas)
+    lens = np.zeros(max_n + 1, np.int32)
+    lens[:n] = np.diff(offsets)
+    valid = np.zeros(max_n + 1, np.int32)
+    valid[:n] = np.unpackbits(validity, bitorder="little")[:n] if n else 0
+    payload = np.zeros(max_b + 1, np.uint8)
+    payload[: len(chars)] = chars
+    t_len = torch.from_numpy(lens).to(dev)
+    t_val = torch.from_numpy(valid).to(dev)
+    t_chr = torch.from_numpy(payload).to(dev)
+    g_len = [torch.zeros_like(t_len) for _ in range(world)]
+    g_val = [torch.zeros_like(t_val) for _ in range(world)]
+    g_chr = [torch.zeros_like(t_chr) for _ in range(world)]
+    dist.all_gather(g_len, t_len, group=group)
+    dist.all_gather(g_val, t_val, group=group)
+    dist.all_gather(g_chr, t_chr, group=group)
+    all_lens, all_valid, all_chars = [], [], []
+    for r in range(world):
+        k, b = metas[r]
+        all_lens.append(g_len[r][:k].cpu().numpy())
+        all_valid.append(g_val[r][:k].cpu().numpy().astype(bool))
+        all_chars.append(g_chr[r][:b].cpu().numpy())
+    lens = np.concatenate(all_lens)
+    valid = np.concatenate(all_valid)
+    chars = np.concatenate(all_chars)
+    offs = np.zeros(len(lens) + 1, np.int32)
+    np.cumsum(lens, out=offs[1:])
+    nulls = int((~valid).sum())
+    return _nvs.from_offsets(chars if chars.size else np.zeros(1, np.uint8), offs, len(lens), np.packbits(valid, bitorder="little"), nulls)
+
+
+def from_strings_sharded(strs, group=None):
+    """Row-sharded dictionary build: `strs` is THIS rank's contiguous row range.  Every rank returns a category whose
+    keys() is the global sorted key set and whose values() index into it."""
+    local = from_strings(strs)
+    all_keys = gather_keys_device(local.keys(), group)
+    h = lib().custr_category_remap_to_union(local.m_cptr, all_keys.m_cptr)
+    return nvcategory(check_handle(h, "from_strings_sharded"))
+
+
+class nvcategory:
+    """Dictionary-encoded strings: sorted unique keys + int32 values.  reference nvcategory.py:136"""
+
+    def __init__(self, cptr):
+        self.m_cptr = cptr
+
+    def __del__(self):
+        if getattr(self, "m_cptr", None):
+            try:
+                lib().custr_category_free(self.m_cptr)
+            except Exception:
+                pass
+            self.m_cptr = 0
+
+    def __repr__(self):
+        return "<nvcategory keys={},values={}>".format(self.keys_size(), self.size())
+
+    def size(self):
+        return int(lib().custr_category_size(self.m_cptr))
+
+    def keys_size(self):
+        return int(lib().custr_category_keys_size(self.m_cptr))
+
+    def keys(self):
+        """nvstrings of the sorted distinct keys.  reference nvcategory.py:242 -> NVCategory.cu:724-750"""
+        return _nvs.nvstrings(check_handle(lib().custr_category_keys(self.m_cptr), "keys"))
+
+    def values(self, devptr=0):
+        """int32 key index per row.  reference nvcategory.py:364 -> NVCategory.cu:866-878"""
+        if devptr:
+            check_rc(lib().custr_category_values(self.m_cptr, as_ptr(devptr), 1), "values")
+            return devptr
+        out = np.zeros(max(self.size(), 1), np.int32)
+        check_rc(lib().custr_category_values(self.m_cptr, as_ptr(out), 0), "values")
+        return out[: self.size()].tolist()
+
+    def values_cpointer(self):
+        """Device pointer to the int32 values.  reference nvcategory.py:343"""
+        return int(lib().custr_category_values_cptr(self.m_cptr) or 0)
+
+    def to_strings(self):
+        """reference nvcategory.py:492"""
+        return self.keys().gather(self.values_cpointer(), self.size())
+
+    def __getattr__(self, name):
+        if name.startswith("_") or name == "m_cptr":
+            raise AttributeError(name)
+        raise NotImplementedError("nvcategory.%s is outside the hot path implemented by custrings_b200 (SURVEY.md section 8)" % name)

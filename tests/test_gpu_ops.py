@@ -1,0 +1,120 @@
+"""GPU parity: literal find / replace / split / tokenize / category through the C-ABI vs the reference oracle."""
+import random
+
+import numpy as np
+import pytest
+
+from tests import corpus
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cols(oracle):
+    from custrings_b200 import nvstrings
+    rng = random.Random(3)
+    strs = corpus.STRINGS + corpus.random_strings(rng, 300) + ["a,b,c", "a,,b", ",", ",a,", "Sun,1,a", "Mon,2", "Tues,,b", "  lead", "trail  ",
+                                                               " a  b\tc\n", "é,ü,日", "aéa éé", "ab::cd::ef", "::", "a::"]
+    return strs, nvstrings.to_device(strs), oracle.RefStrings.from_list(strs)
+
+
+def _n(v, lst):
+    return [v if x is None else x for x in lst]
+
+
+NEEDLES = ["a", "é", "ab", "", "the", " ", "\n", "日本", "zzzz", "_", "ll", "a" * 80]
+
+
+def test_find_family(cols):
+    strs, dev, ref = cols
+    for t in NEEDLES:
+        for (s, e) in ((0, None), (2, None), (1, 5), (3, 2), (0, 100)):
+            want, _ = ref.find(t, s, -1 if e is None else e)
+            assert _n(-2, dev.find(t, s, e)) == want.tolist(), (t, s, e)
+            want, _ = ref.rfind(t, s, -1 if e is None else e)
+            assert _n(-2, dev.rfind(t, s, e)) == want.tolist(), ("r", t, s, e)
+        assert _n(False, dev.contains(t, regex=False)) == ref.contains(t)[0].tolist(), t
+        assert _n(False, dev.startswith(t)) == ref.startswith(t)[0].tolist(), t
+        assert _n(False, dev.endswith(t)) == ref.endswith(t)[0].tolist(), t
+
+
+def test_find_multiple(cols, oracle):
+    from custrings_b200 import nvstrings
+    strs, dev, ref = cols
+    tg = ["a", "é", None, "the", "b c"]
+    want, _ = ref.find_multiple(oracle.RefStrings.from_list(tg))
+    got = np.array(dev.find_multiple(nvstrings.to_device(tg)))
+    assert np.array_equal(got, want)
+
+
+def test_replace_literal(cols, oracle):
+    from custrings_b200 import nvstrings
+    strs, dev, ref = cols
+    for t, r, mx in (("a", "X", -1), ("a", "", 1), ("é", "ee", -1), ("ab", "日", 2), (" ", "", -1), ("ll", "LLL", -1), ("::", ",", -1)):
+        want = ref.replace(t, r, mx).to_list()
+        assert oracle.unpack(*dev.replace(t, r, mx, regex=False).to_arrays()) == want, (t, r, mx)
+    tg = ["the", "a", "é", "::"]
+    for rp in (["THE", "A", "E", ";"], ["_"]):
+        want = ref.replace_multi(oracle.RefStrings.from_list(tg), oracle.RefStrings.from_list(rp)).to_list()
+        got = dev.replace_multi(tg, nvstrings.to_device(rp), regex=False)
+        assert oracle.unpack(*got.to_arrays()) == want
+    with pytest.raises(ValueError):
+        dev.replace("", "x", regex=False)
+
+
+def test_split_columns(cols, oracle):
+    strs, dev, ref = cols
+    for d, mx in ((",", -1), (",", 1), (" ", -1), ("::", -1), ("::", 1), (None, -1), (None, 1), (None, 2), ("é", -1), ("", -1), ("zzz", -1)):
+        want = [c.to_list() for c in ref.split(d, mx)]
+        got = [oracle.unpack(*c.to_arrays()) for c in dev.split(d, mx)]
+        assert got == want, (d, mx)
+
+
+def test_split_record(cols, oracle):
+    strs, dev, ref = cols
+    for d, mx in ((",", -1), (",", 2), (None, -1), (None, 1), ("::", -1)):
+        want_rows, want_total = ref.split_record(d, mx)
+        want = [None if r is None else r.to_list() for r in want_rows]
+        tokens, row_off = dev.split_record_flat(d, mx)
+        flat = oracle.unpack(*tokens.to_arrays())
+        got = [None if s is None else flat[row_off[i]:row_off[i + 1]] for i, s in enumerate(strs)]
+        assert got == want, (d, mx)
+        assert tokens.size() == want_total
+    rows = dev.split_record(",")
+    assert rows[14] is None and rows[0].to_host() == ["abc de"]
+
+
+def test_tokenize(cols, oracle):
+    from custrings_b200 import nvtext
+    strs, dev, ref = cols
+    for d in (None, " ", "o", ",:", "é ", "", "日,"):
+        want = ref.tokenize(d).to_list()
+        assert oracle.unpack(*nvtext.tokenize(dev, d).to_arrays()) == want, d
+        wc, _ = ref.token_count(d)
+        assert nvtext.token_count(dev, d) == wc.tolist(), d
+
+
+def test_category(oracle):
+    from custrings_b200 import nvstrings, nvcategory
+    rng = random.Random(5)
+    keys = ["eee", "aaa", "ddd", "ccc", "", "é", "ab", "abc", "a", "日本", "zz" * 20, "B", "b"]
+    strs = [rng.choice(keys + [None]) for _ in range(5000)]
+    cat = nvcategory.from_strings(nvstrings.to_device(strs))
+    ref = oracle.RefCategory(oracle.RefStrings.from_list(strs))
+    assert oracle.unpack(*cat.keys().to_arrays()) == ref.keys().to_list()
+    assert cat.values() == ref.values().tolist()
+    assert cat.keys_size() == ref.keys_size() and cat.size() == ref.size()
+    assert cat.to_strings().to_host() == strs
+    # reference golden (python/tests/test_category.py, cpp/tests/cattest.cu)
+    c2 = nvcategory.to_device(["eee", "aaa", "eee", "ddd", "ccc", "ccc", "ccc", "eee", "aaa"])
+    assert c2.values() == [3, 0, 3, 2, 1, 1, 1, 3, 0] and c2.keys().to_host() == ["aaa", "ccc", "ddd", "eee"]
+    # multiple inputs
+    a, b = nvstrings.to_device(strs[:100]), nvstrings.to_device(strs[100:300])
+    c3 = nvcategory.from_strings(a, b)
+    r3 = oracle.RefCategory([oracle.RefStrings.from_list(strs[:100]), oracle.RefStrings.from_list(strs[100:300])])
+    assert c3.values() == r3.values().tolist() and oracle.unpack(*c3.keys().to_arrays()) == r3.keys().to_list()
+    # all distinct / no nulls
+    uniq = ["k%05d" % i for i in range(3000)]
+    rng.shuffle(uniq)
+    c4 = nvcategory.to_device(uniq)
+    assert c4.keys().to_host() == sorted(uniq) and [sorted(uniq)[v] for v in c4.values()] == uniq

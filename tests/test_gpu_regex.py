@@ -1,0 +1,79 @@
+"""GPU parity: regex entry points through the C-ABI (ctypes -> libcustr.so) vs the reference oracle."""
+import random
+
+import numpy as np
+import pytest
+
+from tests import corpus
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cols(oracle):
+    from custrings_b200 import nvstrings
+    rng = random.Random(7)
+    strs = corpus.STRINGS + corpus.random_strings(rng, 400)
+    return strs, nvstrings.to_device(strs), oracle.RefStrings.from_list(strs)
+
+
+def _none_to(v, lst):
+    return [v if x is None else x for x in lst]
+
+
+@pytest.mark.parametrize("tier", [0, 1])
+def test_contains_match_count_patterns(cols, tier):
+    from custrings_b200._lib import lib
+    strs, dev, ref = cols
+    lib().custr_set_regex_tier(tier)
+    try:
+        pats = [p for p in corpus.PATTERNS if p not in (r"(a|b)*c", r"((a|b)c)*d", "a+*")] + corpus.random_patterns(11, 150)
+        for p in pats:
+            rc, rn = ref.contains_re(p)
+            assert _none_to(False, dev.contains(p)) == rc.tolist(), p
+            rm, _ = ref.match(p)
+            assert _none_to(False, dev.match(p)) == rm.tolist(), p
+            rk, _ = ref.count_re(p)
+            assert _none_to(0, dev.count(p)) == rk.tolist(), p
+    finally:
+        lib().custr_set_regex_tier(0)
+
+
+def test_replace_re(cols):
+    strs, dev, ref = cols
+    pats = [r"\b\w{4,}\b", r"\d+", "a*", "l+", r"\s", "é", r"[^a-c]+", r"\bthe\b|\bfox\b", r"\w+", "x*?y", "^", "$", r"\b"] + corpus.random_patterns(5, 60)
+    for p in pats:
+        for repl, mx in (("<>", -1), ("", 2), ("é日", 1)):
+            want = ref.replace_re(p, repl, mx).to_list()
+            got = dev.replace(p, repl, mx).to_arrays()
+            from oracle.ref import unpack
+            assert unpack(*got) == want, (p, repl, mx)
+
+
+def test_replace_re_multi(cols, oracle):
+    from custrings_b200 import nvstrings
+    strs, dev, ref = cols
+    pats = [r"\d+", "[tT]he", r"\s+", "é"]
+    repls = ["#", "THE", "_", "e"]
+    want = ref.replace_re_multi(pats, oracle.RefStrings.from_list(repls)).to_list()
+    got = dev.replace_multi(pats, nvstrings.to_device(repls), regex=True)
+    assert oracle.unpack(*got.to_arrays()) == want
+    want1 = ref.replace_re_multi(pats, oracle.RefStrings.from_list(["."])).to_list()
+    got1 = dev.replace_multi(pats, ".", regex=True)
+    assert oracle.unpack(*got1.to_arrays()) == want1
+
+
+def test_roundtrip_and_attrs(cols, oracle):
+    strs, dev, ref = cols
+    assert dev.size() == len(strs)
+    a = dev.to_arrays()
+    r = ref.to_arrays()
+    for x, y in zip(a, r):
+        assert np.array_equal(x, y)
+    assert dev.to_host() == strs
+    assert _none_to(-1, dev.len()) == ref.len()[0].tolist()
+    assert _none_to(0, dev.hash()) == ref.hash()[0].tolist()
+    assert dev.null_count() == sum(s is None for s in strs)
+    sub = dev[3:20]
+    assert sub.to_host() == strs[3:20]
+    assert dev.gather([5, 0, 14, 2]).to_host() == [strs[5], strs[0], strs[14], strs[2]]
