@@ -1,0 +1,379 @@
+// Host lowering: rx::Program (NFA graph) -> bits::PlanDev (marker-stream plan), plus a plain host executor of the
+// plan used by tests/sim to validate the lowering against the oracle without a GPU.  See regex_bits_plan.h for the
+// model and the equivalence argument.  A pattern is accepted only when
+//   - every consuming instruction tests an ASCII-decidable class (rows with non-ASCII bytes are re-run exactly),
+//   - the consuming instructions form a DAG apart from self-loops (x*, x+, x{n,}),
+//   - the pattern cannot match the empty string (the reference's rules for empty matches depend on seeding
+//     position, regexec.inl:260-267 — those patterns stay on the exact VM),
+//   - it fits the fixed plan limits.
+#include "regex_bits.h"
+#include "regex_bits_plan.h"
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <set>
+#include <sstream>
+
+namespace custr {
+namespace bits {
+
+struct Plan {
+    PlanDev dev;
+    std::string text;
+};
+
+namespace {
+
+struct Bitmap128 {
+    uint32_t w[4] = {0, 0, 0, 0};
+    bool get(unsigned c) const { return (w[c >> 5] >> (c & 31)) & 1u; }
+    void set(unsigned c) { w[c >> 5] |= 1u << (c & 31); }
+    bool operator<(const Bitmap128& o) const { return memcmp(w, o.w, sizeof(w)) < 0; }
+};
+
+bool decompose_set(const Bitmap128& want, ClassD& out)  // positive set (bit 0 is "don't care")
+{
+    bool rest[128];
+    for (unsigned c = 0; c < 128; ++c) rest[c] = c ? want.get(c) : false;
+    int n = 0;
+    auto covered = [&](uint8_t kind) {
+        AtomD a{kind, 0, 0, 0};
+        bool any = false;
+        for (unsigned c = 1; c < 128; ++c)
+            if (atom_has(a, c)) { if (!want.get(c)) return false; any = any || rest[c]; }
+        return any;
+    };
+    auto take = [&](uint8_t kind) {
+        AtomD a{kind, 0, 0, 0};
+        for (unsigned c = 1; c < 128; ++c) if (atom_has(a, c)) rest[c] = false;
+        if (n < MAX_ATOMS) out.atoms[n] = a;
+        ++n;
+    };
+    for (uint8_t kind : {AK_ANY, AK_WORD, AK_ALNUM, AK_LOWER, AK_UPPER, AK_DIGIT, AK_SPACE})
+        if (covered(kind)) take(kind);
+    for (unsigned c = 1; c < 128;) {
+        if (!rest[c]) { ++c; continue; }
+        unsigned e = c;
+        while (e + 1 < 128 && rest[e + 1]) ++e;
+        // a run may be extended over bytes that are already covered / wanted: keeps atoms few
+        if (n < MAX_ATOMS) out.atoms[n] = AtomD{(uint8_t)(c == e ? AK_EQ : AK_RANGE), (uint8_t)c, (uint8_t)e, 0};
+        ++n;
+        c = e + 1;
+    }
+    if (n > MAX_ATOMS) return false;
+    out.natoms = (uint8_t)n;
+    return true;
+}
+
+bool decompose(const Bitmap128& bm, ClassD& out)
+{
+    ClassD pos{}, neg{};
+    Bitmap128 inv;
+    for (int i = 0; i < 4; ++i) inv.w[i] = ~bm.w[i];
+    bool okp = decompose_set(bm, pos), okn = decompose_set(inv, neg);
+    neg.negate = 1;
+    if (okp && (!okn || pos.natoms <= neg.natoms)) out = pos;
+    else if (okn) out = neg;
+    else return false;
+    for (unsigned c = 1; c < 128; ++c)
+        if (class_has(out, c) != bm.get(c)) return false;  // self-check
+    return true;
+}
+
+struct Edge { int dst; uint8_t mask; };  // dst = inst id, or -1 for END
+
+struct Lowering {
+    const rx::Program& prog;
+    const uint8_t* uflags;
+    bool ok = true;
+    std::string why;
+    explicit Lowering(const rx::Program& p, const uint8_t* f) : prog(p), uflags(f) {}
+
+    void fail(const char* w) { if (ok) { ok = false; why = w; } }
+
+    static bool consuming(int op)
+    {
+        return op == rx::OP_CHAR || op == rx::OP_ANY || op == rx::OP_ANYNL || op == rx::OP_CLASS || op == rx::OP_NCLASS;
+    }
+
+    // all consuming instructions / END reachable from `from` through zero-width instructions
+    void closure(int from, std::vector<Edge>& out)
+    {
+        std::set<std::pair<int, int>> seen;
+        std::vector<int> path;
+        walk(from, 0, seen, path, out);
+    }
+    void walk(int id, uint8_t mask, std::set<std::pair<int, int>>& seen, std::vector<int>& path, std::vector<Edge>& out)
+    {
+        if (!ok) return;
+        if (std::find(path.begin(), path.end(), id) != path.end()) { fail("zero-width loop"); return; }
+        if (!seen.insert({id, mask}).second) return;
+        if (seen.size() > 4096) { fail("closure too large"); return; }
+        const rx::Inst& in = prog.insts[id];
+        if (consuming(in.op)) { out.push_back({id, mask}); return; }
+        if (in.op == rx::OP_END) { out.push_back({-1, mask}); return; }
+        path.push_back(id);
+        switch (in.op) {
+        case rx::OP_SPLIT:
+            walk(in.other, mask, seen, path, out);
+            walk(in.next, mask, seen, path, out);
+            break;
+        case rx::OP_LBRA: case rx::OP_RBRA: walk(in.next, mask, seen, path, out); break;
+        case rx::OP_BOW: walk(in.next, mask | AS_BOW, seen, path, out); break;
+        case rx::OP_NBOW: walk(in.next, mask | AS_NBOW, seen, path, out); break;
+        case rx::OP_BOL: walk(in.next, mask | (in.arg == '^' ? AS_BOL_CARET : AS_BOL_A), seen, path, out); break;
+        case rx::OP_EOL: walk(in.next, mask | (in.arg == '$' ? AS_EOL_DOLLAR : AS_EOL_Z), seen, path, out); break;
+        default: break;  // OP_BAD: dead end
+        }
+        path.pop_back();
+    }
+
+    static void simplify(std::vector<Edge>& e)
+    {
+        std::vector<Edge> keep;
+        for (const Edge& x : e) {
+            if ((x.mask & AS_BOW) && (x.mask & AS_NBOW)) continue;  // contradiction
+            bool dup = false;
+            for (const Edge& k : keep) if (k.dst == x.dst && k.mask == x.mask) dup = true;
+            if (!dup) keep.push_back(x);
+        }
+        // an unconditional edge to dst subsumes every conditional one
+        std::vector<Edge> out;
+        for (const Edge& x : keep) {
+            bool subsumed = false;
+            for (const Edge& k : keep) if (k.dst == x.dst && k.mask != x.mask && (k.mask & ~x.mask) == 0) subsumed = true;
+            if (!subsumed) out.push_back(x);
+        }
+        e.swap(out);
+    }
+
+    bool class_bitmap(const rx::Inst& in, Bitmap128& bm)
+    {
+        switch (in.op) {
+        case rx::OP_CHAR:
+            if (in.arg == 0 || in.arg >= 128) return false;
+            bm.set(in.arg);
+            return true;
+        case rx::OP_ANY: for (unsigned c = 0; c < 128; ++c) if (c != '\n') bm.set(c); return true;
+        case rx::OP_ANYNL: for (unsigned c = 0; c < 128; ++c) bm.set(c); return true;
+        case rx::OP_CLASS: case rx::OP_NCLASS: {
+            if (in.arg >= prog.classes.size()) return false;
+            for (unsigned c = 0; c < 128; ++c)
+                if (rx::class_matches(prog.classes[in.arg], c, uflags) != (in.op == rx::OP_NCLASS)) bm.set(c);
+            return true;
+        }
+        default: return false;
+        }
+    }
+};
+
+}  // namespace
+
+std::shared_ptr<Plan> lower(const rx::Program& prog, bool anchored, const uint8_t* uflags)
+{
+    if (prog.malformed || prog.insts.empty() || prog.insts.size() > 512) return nullptr;
+    Lowering L(prog, uflags);
+    std::vector<Edge> from_start;
+    L.closure(prog.start_inst, from_start);
+    if (!L.ok) return nullptr;
+    Lowering::simplify(from_start);
+    for (const Edge& e : from_start)
+        if (e.dst < 0) return nullptr;  // can match the empty string: stays on the exact VM
+
+    // discover reachable consuming instructions, their out-edges
+    std::map<int, std::vector<Edge>> out_edges;
+    std::vector<int> work;
+    for (const Edge& e : from_start) if (!out_edges.count(e.dst)) { out_edges[e.dst]; work.push_back(e.dst); }
+    while (!work.empty()) {
+        int id = work.back();
+        work.pop_back();
+        std::vector<Edge> ed;
+        L.closure(prog.insts[id].next, ed);
+        if (!L.ok) return nullptr;
+        Lowering::simplify(ed);
+        for (const Edge& e : ed)
+            if (e.dst >= 0 && !out_edges.count(e.dst)) { out_edges[e.dst]; work.push_back(e.dst); }
+        out_edges[id] = ed;
+        if (out_edges.size() > (size_t)MAX_STEPS) return nullptr;
+    }
+    // topological order ignoring self loops
+    std::map<int, int> indeg;
+    for (auto& kv : out_edges) indeg[kv.first];
+    for (auto& kv : out_edges)
+        for (const Edge& e : kv.second) if (e.dst >= 0 && e.dst != kv.first) ++indeg[e.dst];
+    std::vector<int> order, ready;
+    for (auto& kv : indeg) if (kv.second == 0) ready.push_back(kv.first);
+    while (!ready.empty()) {
+        std::sort(ready.begin(), ready.end(), std::greater<int>());
+        int id = ready.back();
+        ready.pop_back();
+        order.push_back(id);
+        for (const Edge& e : out_edges[id])
+            if (e.dst >= 0 && e.dst != id && --indeg[e.dst] == 0) ready.push_back(e.dst);
+    }
+    if (order.size() != out_edges.size()) return nullptr;  // a cycle through more than one instruction
+    std::map<int, int> step_of;
+    for (size_t k = 0; k < order.size(); ++k) step_of[order[k]] = (int)k;
+
+    auto plan = std::make_shared<Plan>();
+    PlanDev& P = plan->dev;
+    memset(&P, 0, sizeof(P));
+    P.anchored = anchored ? 1 : 0;
+    P.nsteps = (uint8_t)order.size();
+    std::map<Bitmap128, int> class_ids;
+    for (size_t k = 0; k < order.size(); ++k) {
+        const rx::Inst& in = prog.insts[order[k]];
+        Bitmap128 bm;
+        if (!L.class_bitmap(in, bm)) return nullptr;
+        bm.w[0] &= ~1u;  // NUL is decided by the exact path
+        auto it = class_ids.find(bm);
+        if (it == class_ids.end()) {
+            if (class_ids.size() >= (size_t)MAX_CLASSES) return nullptr;
+            ClassD cd{};
+            if (!decompose(bm, cd)) return nullptr;
+            int id = (int)class_ids.size();
+            P.classes[id] = cd;
+            it = class_ids.emplace(bm, id).first;
+        }
+        P.steps[k].cls = (uint8_t)it->second;
+    }
+    P.nclasses = (uint8_t)class_ids.size();
+    auto add_pred = [&](int dst_step, uint8_t src, uint8_t mask) {
+        StepD& s = P.steps[dst_step];
+        if (s.npreds >= MAX_PREDS) return false;
+        s.preds[s.npreds++] = PredD{src, mask};
+        P.before_needs |= mask;
+        return true;
+    };
+    for (const Edge& e : from_start)
+        if (!add_pred(step_of[e.dst], SRC_START, e.mask)) return nullptr;
+    for (size_t k = 0; k < order.size(); ++k) {
+        int loops = 0;
+        for (const Edge& e : out_edges[order[k]]) {
+            if (e.dst < 0) {
+                if (P.nends >= MAX_ENDS) return nullptr;
+                P.ends[P.nends++] = EndD{(uint8_t)k, e.mask};
+                P.after_needs |= e.mask;
+            } else if (e.dst == order[k]) {
+                if (++loops > 1) return nullptr;  // two differently-guarded self loops: keep it simple
+                P.steps[k].self_loop = 1;
+                P.steps[k].self_mask = e.mask;
+                P.before_needs |= e.mask;
+            } else if (!add_pred(step_of[e.dst], (uint8_t)k, e.mask))
+                return nullptr;
+        }
+    }
+    if (P.nends == 0) return nullptr;
+    plan->text = describe(*plan);
+    return plan;
+}
+
+std::string describe(const Plan& plan)
+{
+    const PlanDev& P = plan.dev;
+    static const char* an[] = {"EQ", "RANGE", "WORD", "ALNUM", "DIGIT", "SPACE", "LOWER", "UPPER", "ANY"};
+    std::ostringstream o;
+    o << (P.anchored ? "anchored " : "") << "classes=" << (int)P.nclasses << " steps=" << (int)P.nsteps << " ends=" << (int)P.nends << " {";
+    for (int k = 0; k < P.nclasses; ++k) {
+        o << " C" << k << "=" << (P.classes[k].negate ? "!" : "") << "(";
+        for (int a = 0; a < P.classes[k].natoms; ++a) {
+            const AtomD& t = P.classes[k].atoms[a];
+            o << (a ? "|" : "") << an[t.kind];
+            if (t.kind == AK_EQ) o << ":" << (int)t.lo;
+            if (t.kind == AK_RANGE) o << ":" << (int)t.lo << "-" << (int)t.hi;
+        }
+        o << ")";
+    }
+    o << " ;";
+    for (int s = 0; s < P.nsteps; ++s) {
+        o << " S" << s << "=C" << (int)P.steps[s].cls << "[";
+        for (int p = 0; p < P.steps[s].npreds; ++p) {
+            if (p) o << ",";
+            if (P.steps[s].preds[p].src == SRC_START) o << "^"; else o << "S" << (int)P.steps[s].preds[p].src;
+            if (P.steps[s].preds[p].mask) o << "/" << (int)P.steps[s].preds[p].mask;
+        }
+        o << "]";
+        if (P.steps[s].self_loop) { o << "*"; if (P.steps[s].self_mask) o << "/" << (int)P.steps[s].self_mask; }
+    }
+    o << " ; end:";
+    for (int e = 0; e < P.nends; ++e) { o << " S" << (int)P.ends[e].src; if (P.ends[e].mask) o << "/" << (int)P.ends[e].mask; }
+    o << " }";
+    return o.str();
+}
+
+const PlanDev& device_plan(const Plan& plan) { return plan.dev; }
+
+// ---- plain host executor (tests/sim only) ------------------------------------------------------------------------
+void reference_execute(const Plan& plan, const char* chars, const int32_t* offsets, const uint8_t* validity, int32_t n,
+                       uint8_t* out, uint8_t* dirty)
+{
+    const PlanDev& P = plan.dev;
+    const int32_t base = n ? offsets[0] : 0;
+    const int64_t N = n ? offsets[n] - base : 0;
+    const uint8_t* s = (const uint8_t*)chars + base;
+    std::vector<uint8_t> RS(N + 1, 0), A(N, 0), NL(N, 0);
+    auto valid = [&](int i) { return !validity || ((validity[i >> 3] >> (i & 7)) & 1); };
+    for (int i = 0; i < n; ++i) {
+        out[i] = 0;
+        dirty[i] = 0;
+        int b = offsets[i] - base, e = offsets[i + 1] - base;
+        if (e > b) RS[b] = 1;
+        for (int p = b; p < e; ++p) if (s[p] >= 0x80 || s[p] == 0) dirty[i] = 1;
+        (void)valid;
+    }
+    RS[N] = 1;
+    const AtomD alnum{AK_ALNUM, 0, 0, 0};
+    for (int64_t p = 0; p < N; ++p) { A[p] = s[p] < 0x80 && atom_has(alnum, s[p]); NL[p] = s[p] == '\n'; }
+    auto before = [&](uint8_t m, int64_t q) {  // assertions between q-1 and q
+        bool aprev = q > 0 && !RS[q] && A[q - 1];
+        bool nlprev = q > 0 && !RS[q] && NL[q - 1];
+        bool bow = (A[q] != 0) != aprev;
+        if ((m & AS_BOW) && !bow) return false;
+        if ((m & AS_NBOW) && bow) return false;
+        if ((m & AS_BOL_CARET) && !(RS[q] || nlprev)) return false;
+        if ((m & AS_BOL_A) && !RS[q]) return false;
+        if ((m & AS_EOL_DOLLAR) && !NL[q]) return false;
+        if (m & AS_EOL_Z) return false;
+        return true;
+    };
+    auto after = [&](uint8_t m, int64_t p) {  // assertions between p and p+1
+        bool last = RS[p + 1] != 0;
+        bool anext = !last && A[p + 1];
+        bool nlnext = !last && NL[p + 1];
+        bool bow = (A[p] != 0) != anext;
+        if ((m & AS_BOW) && !bow) return false;
+        if ((m & AS_NBOW) && bow) return false;
+        if ((m & AS_BOL_CARET) && !NL[p]) return false;
+        if (m & AS_BOL_A) return false;
+        if ((m & AS_EOL_DOLLAR) && !(last || nlnext)) return false;
+        if ((m & AS_EOL_Z) && !last) return false;
+        return true;
+    };
+    std::vector<std::vector<uint8_t>> M(P.nsteps, std::vector<uint8_t>(N, 0));
+    for (int k = 0; k < P.nsteps; ++k) {
+        const StepD& st = P.steps[k];
+        const ClassD& cd = P.classes[st.cls];
+        for (int64_t q = 0; q < N; ++q) {
+            bool in_class = s[q] < 0x80 && class_has(cd, s[q]);
+            bool entry = false;
+            for (int j = 0; j < st.npreds && !entry; ++j) {
+                const PredD& pr = st.preds[j];
+                bool t = pr.src == SRC_START ? (P.anchored ? RS[q] != 0 : true) : (q > 0 && !RS[q] && M[pr.src][q - 1]);
+                entry = t && before(pr.mask, q);
+            }
+            bool v = entry && in_class;
+            if (!v && st.self_loop && in_class && q > 0 && !RS[q] && M[k][q - 1] && before(st.self_mask, q)) v = true;
+            M[k][q] = v;
+        }
+    }
+    std::vector<uint8_t> E(N, 0);
+    for (int e = 0; e < P.nends; ++e)
+        for (int64_t p = 0; p < N; ++p)
+            if (M[P.ends[e].src][p] && after(P.ends[e].mask, p)) E[p] = 1;
+    for (int i = 0; i < n; ++i)
+        for (int p = offsets[i] - base; p < offsets[i + 1] - base; ++p)
+            if (E[p]) { out[i] = 1; break; }
+}
+
+}  // namespace bits
+}  // namespace custr

@@ -58,7 +58,7 @@ CUSTR_HD int find_chars(const uint8_t* s, int n, const uint8_t* t, int m, int st
     int nchars = utf8_count_chars(s, n);
     bool ascii = nchars == n;
     int count = end - start;
-    if (count < 0) count = nchars;
+    if (count < 0 && !reverse) count = nchars;  // rfind has no such normalisation (custring_view.inl:557-560)
     long long e = (long long)start + count;
     int cend = (e < 0 || e > nchars) ? nchars : (int)e;
     int spos = ascii ? (start < n ? start : n) : utf8_offset_of(s, n, start);
