@@ -23,6 +23,8 @@ _SIGNATURES = {
     "custr_launch_count": (cl, []),
     "custr_last_regex_tier": (cp, []),
     "custr_set_regex_tier": (None, [ci]),
+    "custr_set_profiling": (None, [ci]),
+    "custr_last_kernel_ms": (C.c_float, []),
     "custr_create_from_offsets": (vp, [vp, ci, vp, vp, ci, ci]),
     "custr_adopt_device": (vp, [vp, ci, vp, vp, ci]),
     "custr_create_from_array": (vp, [vp, cu]),

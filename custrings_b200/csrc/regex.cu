@@ -36,6 +36,30 @@ const uint8_t* device_unicode_flags()
 thread_local const char* g_last_tier = "none";
 thread_local int g_forced_tier = 0;
 
+// optional device-side timing of the dominant kernel of a call (bench.py's roofline leg)
+thread_local int g_profile = 0;
+thread_local float g_last_kernel_ms = -1.f;
+struct KernelTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool armed = false;
+    void start()
+    {
+        if (!g_profile) return;
+        if (!a) { CUSTR_CUDA(cudaEventCreate(&a)); CUSTR_CUDA(cudaEventCreate(&b)); }
+        CUSTR_CUDA(cudaEventRecord(a, g_stream));
+        armed = true;
+    }
+    void stop() { if (armed) CUSTR_CUDA(cudaEventRecord(b, g_stream)); }
+    void collect()
+    {
+        if (!armed) return;
+        CUSTR_CUDA(cudaEventSynchronize(b));
+        CUSTR_CUDA(cudaEventElapsedTime(&g_last_kernel_ms, a, b));
+        armed = false;
+    }
+};
+static thread_local KernelTimer g_timer;
+
 // ---- compiled-program cache ------------------------------------------------------------------------------
 struct Compiled {
     rx::Program prog;
@@ -106,6 +130,34 @@ k_vm_bool(ColView col, const uint8_t* __restrict__ img, int img_bytes, const uin
                 int mb, me;
                 hit = rxdev::vm_find<CAP>(P, (const uint8_t*)col.chars + b, n, 0, anchored ? 1 : n, mb, me, L);
             }
+            out[i] = (uint8_t)hit;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(total, (unsigned long long)__popc(m));
+    }
+}
+
+// exact decision for the rows the bitstream tier could not decide (non-ASCII / NUL bytes); the list length is read
+// from device memory so no host round trip sits between the two kernels
+template <int CAP>
+__global__ void __launch_bounds__(VM_THREADS)
+k_vm_bool_rows(ColView col, const uint8_t* __restrict__ img, int img_bytes, const uint8_t* __restrict__ uflags, int anchored,
+               const int32_t* __restrict__ rows, const unsigned int* __restrict__ nrows_ptr, uint8_t* __restrict__ out,
+               unsigned long long* __restrict__ total)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    rxdev::DevProg P = rxdev::bind_program(stage_program(img, img_bytes, smem), uflags);
+    rxdev::Lists<CAP> L;
+    L.init();
+    const int nrows = (int)*nrows_ptr;
+    for (int base = blockIdx.x * blockDim.x; base < nrows; base += gridDim.x * blockDim.x) {
+        int k = base + threadIdx.x;
+        int hit = 0;
+        if (k < nrows) {
+            int i = rows[k];
+            int b = col.offsets[i], n = col.offsets[i + 1] - b;
+            int mb, me;
+            hit = rxdev::vm_find<CAP>(P, (const uint8_t*)col.chars + b, n, 0, anchored ? 1 : n, mb, me, L);
             out[i] = (uint8_t)hit;
         }
         unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -233,18 +285,38 @@ static int bool_search(const custr_column* col, const char* pattern, uint8_t* re
         }
         const std::shared_ptr<bits::Plan>& plan = anchored ? c->plan_match : c->plan_contains;
         if (plan) {
-            bits::run(*plan, col, out.dev, total.get());
-            g_last_tier = "bitstream";
-            done = true;
+            int cap = cap_tier((int)c->prog.insts.size());
+            int32_t* dirty_rows = nullptr;
+            unsigned int* dirty_count = nullptr;
+            BufPtr keep_rows, keep_count;
+            g_timer.start();
+            if (cap && bits::run(*plan, col, out.dev, total.get(), &dirty_rows, &dirty_count, keep_rows, keep_count)) {
+                // rows with non-ASCII / NUL bytes: exact VM over the work list (usually a few % of the rows)
+                int grid = vm_grid(n < 1 << 20 ? n : 1 << 20);
+                DISPATCH_CAP(cap, k_vm_bool_rows, grid, smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
+                             (int)c->image.size(), device_unicode_flags(), anchored ? 1 : 0, (const int32_t*)dirty_rows,
+                             (const unsigned int*)dirty_count, out.dev, total.get());
+                g_timer.stop();
+                g_last_tier = "bitstream";
+                done = true;
+                int matches = (int)read_counter(total.get());  // also keeps the work list alive until the kernels finish
+                g_timer.collect();
+                out.finish();
+                return matches;
+            }
+            g_timer.armed = false;
         }
     }
     if (!done) {
         int cap = check_cap(*c, who);
+        g_timer.start();
         DISPATCH_CAP(cap, k_vm_bool, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
                      (int)c->image.size(), device_unicode_flags(), anchored ? 1 : 0, out.dev, total.get());
+        g_timer.stop();
         g_last_tier = "pikevm";
     }
     int matches = (int)read_counter(total.get());
+    g_timer.collect();
     out.finish();
     return matches;
 }
@@ -273,6 +345,8 @@ using namespace custr;
 extern "C" {
 
 const char* custr_last_regex_tier(void) { return g_last_tier; }
+void custr_set_profiling(int on) { g_profile = on; }
+float custr_last_kernel_ms(void) { return g_last_kernel_ms; }
 void custr_set_regex_tier(int tier) { g_forced_tier = tier; }
 
 int custr_regex_describe(const char* pattern, char* buf, size_t buflen)

@@ -1,7 +1,424 @@
+// Bitstream regex executor (device).  Model, plan format and the equivalence argument: regex_bits_plan.h;
+// host lowering: regex_bits_lower.cpp.  DESIGN.md §4.2 has the roofline accounting.
+//
+// Mapping to the machine
+//   * the flat chars buffer is cut into 1024-byte WINDOWS; one warp evaluates one window at a time, lane L owning the
+//     32 bytes [32L, 32L+32) = one 32-bit word of every stream.  Loads are two LDG.128 per lane, fully coalesced,
+//     software-prefetched one window ahead; no byte is read twice except the two boundary windows of a work item.
+//   * the 32 bytes of a lane are bit-transposed in registers (16 PRMT + 48 SHF/LOP3) into 8 bit planes; character
+//     classes are boolean formulas over the planes, so classification costs a few LOP3 per 32 bytes instead of a
+//     table lookup per byte.
+//   * advance / look-ahead are a warp shuffle + funnel shift; `spread` (x+, x*, and the per-row sticky OR) is a
+//     1024-bit carry-propagating add done with two ballots; inter-window state is one carry bit per stream.
+//   * rows never interact: ROWSTART bits are scattered from the offsets array (shared-memory atomicOr); a work item is a
+//     contiguous ROW range whose bytes start near a 32 KiB boundary (warp-cooperative 32-ary search in offsets), so
+//     warps never exchange state.
+//   * rows holding a byte >= 0x80 or a NUL are appended to a work list and decided by the exact Pike-VM kernel.
 #include "regex_bits.h"
-namespace custr { namespace bits {
-struct Plan { int dummy; };
-std::shared_ptr<Plan> lower(const rx::Program&, bool, const uint8_t*) { return nullptr; }
-std::string describe(const Plan&) { return "stub"; }
-void run(const Plan&, const custr_column*, uint8_t*, unsigned long long*) {}
-}}
+#include "regex_bits_plan.h"
+
+namespace custr {
+namespace bits {
+
+struct Plan {
+    PlanDev dev;
+    std::string text;
+};
+
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+constexpr int WIN = 1024;
+constexpr int ITEM_BYTES = 32 * 1024;
+constexpr unsigned FULL = 0xffffffffu;
+
+// carry bit layout (one uniform 32-bit mask per warp): bits 0..23 = P_s top bit, then:
+constexpr int CY_A = 24, CY_NL = 25, CY_F = 26, CY_D = 27;
+
+struct Args {
+    const char* chars;        // column chars base (offsets are absolute into it)
+    const int32_t* offsets;
+    int32_t n;
+    int32_t first, end;       // byte span [first, end)
+    int32_t nitems;
+    uint8_t* out;
+    unsigned long long* total;
+    int32_t* dirty_rows;
+    unsigned int* dirty_count;
+};
+
+struct WarpSmem {
+    uint32_t slot[MAX_STEPS][32];   // ADV_s = advance(P_s) & ~ROWSTART, per lane
+    uint32_t cls[MAX_CLASSES][32];
+    uint32_t rs[32];
+    uint32_t f[32];
+    uint32_t d[32];
+};
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ uint32_t advance(uint32_t x, uint32_t cin_bit)
+{
+    uint32_t up = __shfl_up_sync(FULL, x, 1);
+    if (lane_id() == 0) up = cin_bit << 31;
+    return __funnelshift_l(up, x, 1);
+}
+__device__ __forceinline__ uint32_t top_bit(uint32_t x) { return __shfl_sync(FULL, x, 31) >> 31; }
+
+__device__ __forceinline__ uint32_t shift_down(uint32_t x, uint32_t next_bit)
+{
+    uint32_t dn = __shfl_down_sync(FULL, x, 1);
+    if (lane_id() == 31) dn = next_bit;
+    return __funnelshift_r(x, dn, 1);
+}
+
+// R[p] = Q[p] | (R[p-1] & K[p]) over the 1024 positions of the window, R[-1] = cin_bit
+__device__ __forceinline__ uint32_t spread(uint32_t q, uint32_t k, uint32_t cin_bit)
+{
+    uint32_t s = advance(q, cin_bit) & k;
+    uint32_t sum = s + k;
+    uint32_t g = __ballot_sync(FULL, sum < s);
+    uint32_t p = __ballot_sync(FULL, sum == 0xffffffffu);
+    // carry into lane i: c[i] = g[i-1] | (p[i-1] & c[i-1])  -- same recurrence, solved with one 32-bit add
+    uint32_t g1 = g << 1, p1 = p << 1;
+    uint32_t s2 = (g1 << 1) & p1;
+    uint32_t c = g1 | ((((s2 + p1) ^ p1) | s2) & p1);
+    sum += (c >> lane_id()) & 1u;
+    return q | (((sum ^ k) | s) & k);
+}
+
+// 32 bytes (8 little-endian words) -> 8 bit planes; bit i of plane b = bit b of byte i
+__device__ __forceinline__ void transpose_planes(const uint4& lo, const uint4& hi, uint32_t (&p)[8])
+{
+    uint32_t a0 = lo.x, a1 = lo.z, a2 = hi.x, a3 = hi.z;  // words 0,2,4,6 -> bytes y, y+8, y+16, y+24 (y<4)
+    uint32_t b0 = lo.y, b1 = lo.w, b2 = hi.y, b3 = hi.w;  // words 1,3,5,7 -> y = 4..7
+    uint32_t t0 = __byte_perm(a0, a1, 0x5140), t1 = __byte_perm(a0, a1, 0x7362);
+    uint32_t t2 = __byte_perm(a2, a3, 0x5140), t3 = __byte_perm(a2, a3, 0x7362);
+    p[0] = __byte_perm(t0, t2, 0x5410); p[1] = __byte_perm(t0, t2, 0x7632);
+    p[2] = __byte_perm(t1, t3, 0x5410); p[3] = __byte_perm(t1, t3, 0x7632);
+    t0 = __byte_perm(b0, b1, 0x5140); t1 = __byte_perm(b0, b1, 0x7362);
+    t2 = __byte_perm(b2, b3, 0x5140); t3 = __byte_perm(b2, b3, 0x7362);
+    p[4] = __byte_perm(t0, t2, 0x5410); p[5] = __byte_perm(t0, t2, 0x7632);
+    p[6] = __byte_perm(t1, t3, 0x5410); p[7] = __byte_perm(t1, t3, 0x7632);
+#define DELTA_SWAP(A, B, S, M)                               \
+    {                                                        \
+        uint32_t na = ((A) & (M)) | (((B) << (S)) & ~(M));   \
+        uint32_t nb = (((A) >> (S)) & (M)) | ((B) & ~(M));   \
+        (A) = na; (B) = nb;                                  \
+    }
+    DELTA_SWAP(p[0], p[4], 4, 0x0F0F0F0Fu) DELTA_SWAP(p[1], p[5], 4, 0x0F0F0F0Fu)
+    DELTA_SWAP(p[2], p[6], 4, 0x0F0F0F0Fu) DELTA_SWAP(p[3], p[7], 4, 0x0F0F0F0Fu)
+    DELTA_SWAP(p[0], p[2], 2, 0x33333333u) DELTA_SWAP(p[1], p[3], 2, 0x33333333u)
+    DELTA_SWAP(p[4], p[6], 2, 0x33333333u) DELTA_SWAP(p[5], p[7], 2, 0x33333333u)
+    DELTA_SWAP(p[0], p[1], 1, 0x55555555u) DELTA_SWAP(p[2], p[3], 1, 0x55555555u)
+    DELTA_SWAP(p[4], p[5], 1, 0x55555555u) DELTA_SWAP(p[6], p[7], 1, 0x55555555u)
+#undef DELTA_SWAP
+}
+
+// ---- character classes as boolean formulas over the planes (ASCII, plane 7 ignored) ---------------------------------
+__device__ __forceinline__ uint32_t cls_digit(const uint32_t (&p)[8])
+{
+    return ~p[6] & p[5] & p[4] & (~p[3] | (~p[2] & ~p[1]));
+}
+__device__ __forceinline__ uint32_t cls_letter5(const uint32_t (&p)[8])  // low five bits in 1..26
+{
+    uint32_t nz = p[4] | p[3] | p[2] | p[1] | p[0];
+    uint32_t gt26 = p[4] & p[3] & (p[2] | (p[1] & p[0]));
+    return nz & ~gt26;
+}
+__device__ __forceinline__ uint32_t cls_alnum(const uint32_t (&p)[8]) { return (p[6] & cls_letter5(p)) | cls_digit(p); }
+__device__ __forceinline__ uint32_t cls_underscore(const uint32_t (&p)[8])
+{
+    return p[6] & ~p[5] & p[4] & p[3] & p[2] & p[1] & p[0];
+}
+__device__ __forceinline__ uint32_t cls_space(const uint32_t (&p)[8])
+{
+    uint32_t hi0 = ~p[6] & ~p[5];
+    uint32_t c9_13 = hi0 & ~p[4] & p[3] & ((~p[2] & (p[1] | p[0])) | (p[2] & ~p[1]));
+    uint32_t c28_31 = hi0 & p[4] & p[3] & p[2];
+    uint32_t c32 = ~p[6] & p[5] & ~(p[4] | p[3] | p[2] | p[1] | p[0]);
+    return c9_13 | c28_31 | c32;
+}
+__device__ __forceinline__ uint32_t cls_eq(const uint32_t (&p)[8], uint32_t c)
+{
+    uint32_t t = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 7; ++b) t &= ((c >> b) & 1u) ? p[b] : ~p[b];
+    return t;
+}
+// bytes >= c (7-bit compare, MSB first)
+__device__ __forceinline__ uint32_t cls_ge(const uint32_t (&p)[8], uint32_t c)
+{
+    uint32_t gt = 0, eq = 0xffffffffu;
+#pragma unroll
+    for (int b = 6; b >= 0; --b) {
+        if ((c >> b) & 1u) eq &= p[b];
+        else { gt |= eq & p[b]; eq &= ~p[b]; }
+    }
+    return gt | eq;
+}
+__device__ __forceinline__ uint32_t cls_atom(const uint32_t (&p)[8], const AtomD a)
+{
+    switch (a.kind) {
+    case AK_EQ: return cls_eq(p, a.lo);
+    case AK_RANGE: return cls_ge(p, a.lo) & ~(a.hi >= 127 ? 0u : cls_ge(p, a.hi + 1u));
+    case AK_WORD: return cls_alnum(p) | cls_underscore(p);
+    case AK_ALNUM: return cls_alnum(p);
+    case AK_DIGIT: return cls_digit(p);
+    case AK_SPACE: return cls_space(p);
+    case AK_LOWER: return p[6] & p[5] & cls_letter5(p);
+    case AK_UPPER: return p[6] & ~p[5] & cls_letter5(p);
+    default: return 0xffffffffu;
+    }
+}
+
+struct Assertions {  // zero-width assertion streams of the current window
+    uint32_t rs, bow_b, bolc_b, nl, bow_a, lb, eold_a;
+};
+__device__ __forceinline__ uint32_t apply_before(uint32_t t, uint32_t m, const Assertions& a)
+{
+    if (m & AS_BOW) t &= a.bow_b;
+    if (m & AS_NBOW) t &= ~a.bow_b;
+    if (m & AS_BOL_CARET) t &= a.bolc_b;
+    if (m & AS_BOL_A) t &= a.rs;
+    if (m & AS_EOL_DOLLAR) t &= a.nl;
+    if (m & AS_EOL_Z) t = 0;
+    return t;
+}
+__device__ __forceinline__ uint32_t apply_after(uint32_t t, uint32_t m, const Assertions& a)
+{
+    if (m & AS_BOW) t &= a.bow_a;
+    if (m & AS_NBOW) t &= ~a.bow_a;
+    if (m & AS_BOL_CARET) t &= a.nl;
+    if (m & AS_BOL_A) t = 0;
+    if (m & AS_EOL_DOLLAR) t &= a.eold_a;
+    if (m & AS_EOL_Z) t &= a.lb;
+    return t;
+}
+
+// first index r in [0, n] with offsets[r] >= target (offsets has n+1 ascending entries); warp-cooperative 32-ary search
+__device__ int warp_lower_bound(const int32_t* __restrict__ offsets, int n, int target)
+{
+    int lo = 0, hi = n + 1;  // answer in [lo, hi]
+    while (hi - lo > 0) {
+        int span = hi - lo;
+        int stepsz = (span + 31) / 32;
+        int idx = lo + (int)lane_id() * stepsz;
+        bool ge = idx >= hi ? true : (__ldg(offsets + idx) >= target);
+        unsigned m = __ballot_sync(FULL, ge);
+        int first_ge = m ? __ffs(m) - 1 : 32;   // lanes before it are < target
+        int new_hi = lo + first_ge * stepsz;
+        if (new_hi > hi) new_hi = hi;
+        int new_lo = first_ge == 0 ? lo : lo + (first_ge - 1) * stepsz + 1;
+        if (first_ge == 0) return lo;
+        lo = new_lo;
+        hi = new_hi;
+        if (stepsz == 1) return hi;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void load_window(const char* __restrict__ chars, int ws, int end, uint4& lo, uint4& hi)
+{
+    int b = ws + 32 * (int)lane_id();
+    if (b + 32 <= end) {
+        const uint4* q = (const uint4*)(chars + b);
+        lo = __ldg(q);
+        hi = __ldg(q + 1);
+    } else {
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t v = 0;
+            for (int k = 0; k < 4; ++k) {
+                int pos = b + 4 * j + k;
+                if (pos < end && pos >= 0) v |= (uint32_t)(uint8_t)chars[pos] << (8 * k);
+            }
+            w[j] = v;
+        }
+        lo = make_uint4(w[0], w[1], w[2], w[3]);
+        hi = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+k_bitstream(const __grid_constant__ PlanDev plan, const Args A)
+{
+    __shared__ WarpSmem smem[WARPS];
+    WarpSmem& S = smem[threadIdx.x >> 5];
+    const uint32_t lane = lane_id();
+    const int warps_total = gridDim.x * WARPS;
+    unsigned long long my_matches = 0;
+
+    for (int item = blockIdx.x * WARPS + (threadIdx.x >> 5); item < A.nitems; item += warps_total) {
+        // ---- rows of this item: first row starting at or after the item's byte boundary
+        const int lo_byte = A.first + item * ITEM_BYTES;
+        int ra = item == 0 ? 0 : warp_lower_bound(A.offsets, A.n, lo_byte);
+        int rb = item == A.nitems - 1 ? A.n : warp_lower_bound(A.offsets, A.n, lo_byte + ITEM_BYTES);
+        if (ra >= rb) continue;
+        const int byte_a = __ldg(A.offsets + ra), byte_b = __ldg(A.offsets + rb);
+        if (byte_a >= byte_b) continue;  // only empty rows: results stay 0 (pre-cleared)
+        int krs = ra;       // next offset index whose ROWSTART bit is not set yet
+        int kfin = ra + 1;  // next offset index j whose row j-1 is not finalised yet
+        uint32_t carry = 0;
+        int ws = byte_a & ~(WIN - 1);
+        uint4 cur_lo, cur_hi, nxt_lo, nxt_hi;
+        load_window(A.chars, ws, A.end, cur_lo, cur_hi);
+
+        for (; ws < byte_b; ws += WIN) {
+            const int we = ws + WIN;
+            if (we < byte_b) load_window(A.chars, we, A.end, nxt_lo, nxt_hi);  // prefetch
+
+            // ---- ROWSTART bits from the offsets array
+            S.rs[lane] = 0;
+            __syncwarp();
+            for (;;) {
+                int j = krs + (int)lane;
+                int o = j <= rb ? __ldg(A.offsets + j) : 0x7fffffff;
+                bool in = o < we;
+                if (in && o >= ws) atomicOr(&S.rs[(o - ws) >> 5], 1u << ((o - ws) & 31));
+                unsigned m = __ballot_sync(FULL, in);
+                krs += __popc(m);
+                if (m != FULL) break;
+            }
+            __syncwarp();
+            Assertions as;
+            as.rs = S.rs[lane];
+            const uint32_t nrs = ~as.rs;
+            const uint32_t rs_next = (krs <= rb && __ldg(A.offsets + krs) == we) || we >= A.end;
+            const uint32_t next_byte = (!rs_next && we < A.end) ? (uint8_t)A.chars[we] : 0;
+
+            // ---- bit planes, dirty bytes
+            uint32_t p[8];
+            transpose_planes(cur_lo, cur_hi, p);
+            const uint32_t dirty_bits = p[7] | ~(p[0] | p[1] | p[2] | p[3] | p[4] | p[5] | p[6] | p[7]);
+
+            // ---- class streams
+            for (int k = 0; k < plan.nclasses; ++k) {
+                uint32_t v = 0;
+                for (int a = 0; a < plan.classes[k].natoms; ++a) v |= cls_atom(p, plan.classes[k].atoms[a]);
+                if (plan.classes[k].negate) v = ~v;
+                S.cls[k][lane] = v;
+            }
+            // ---- assertion streams (only what the plan uses)
+            uint32_t carry_out = 0;
+            as.bow_b = as.bow_a = as.bolc_b = as.nl = as.lb = as.eold_a = 0;
+            const uint32_t needs = plan.before_needs | plan.after_needs;
+            if (needs & (AS_BOW | AS_NBOW)) {
+                uint32_t al = cls_alnum(p);
+                as.bow_b = al ^ (advance(al, (carry >> CY_A) & 1u) & nrs);
+                carry_out |= top_bit(al) << CY_A;
+                uint32_t nb = next_byte | 0x20u;
+                uint32_t a_next = (next_byte - '0' < 10u) || (nb - 'a' < 26u);
+                as.bow_a = al ^ shift_down(al & nrs, a_next);
+            }
+            if (needs & (AS_BOL_CARET | AS_EOL_DOLLAR | AS_EOL_Z)) {
+                as.nl = cls_eq(p, '\n');
+                as.bolc_b = as.rs | (advance(as.nl, (carry >> CY_NL) & 1u) & nrs);
+                carry_out |= top_bit(as.nl) << CY_NL;
+                as.lb = shift_down(as.rs, rs_next);
+                as.eold_a = as.lb | shift_down(as.nl & nrs, next_byte == '\n');
+            }
+            __syncwarp();
+
+            // ---- marker steps
+            uint32_t E = 0;
+            const uint32_t start = plan.anchored ? as.rs : 0xffffffffu;
+            int end_i = 0;
+            for (int s = 0; s < plan.nsteps; ++s) {
+                const StepD st = plan.steps[s];
+                const uint32_t c = S.cls[st.cls][lane];
+                uint32_t entry = 0;
+                for (int j = 0; j < st.npreds; ++j) {
+                    const PredD pr = st.preds[j];
+                    uint32_t t = pr.src == SRC_START ? start : S.slot[pr.src][lane];
+                    entry |= apply_before(t, pr.mask, as);
+                }
+                uint32_t P = entry & c;
+                if (st.self_loop) P = spread(P, apply_before(c & nrs, st.self_mask, as), (carry >> s) & 1u);
+                while (end_i < plan.nends && plan.ends[end_i].src == s) E |= apply_after(P, plan.ends[end_i++].mask, as);
+                S.slot[s][lane] = advance(P, (carry >> s) & 1u) & nrs;
+                carry_out |= top_bit(P) << s;
+            }
+
+            // ---- sticky per-row OR of matches (and of dirty bytes when there are any)
+            uint32_t F = spread(E, nrs, (carry >> CY_F) & 1u);
+            carry_out |= top_bit(F) << CY_F;
+            S.f[lane] = F;
+            const bool any_dirty = __any_sync(FULL, dirty_bits != 0) || ((carry >> CY_D) & 1u);
+            if (any_dirty) {
+                uint32_t D = spread(dirty_bits, nrs, (carry >> CY_D) & 1u);
+                carry_out |= top_bit(D) << CY_D;
+                S.d[lane] = D;
+            }
+            __syncwarp();
+
+            // ---- finalise the rows whose last byte lies in this window
+            for (;;) {
+                int j = kfin + (int)lane;
+                int o = j <= rb ? __ldg(A.offsets + j) : 0x7fffffff;
+                bool in = o <= we;
+                bool hit = false, dirty = false;
+                if (in) {
+                    int o_prev = __ldg(A.offsets + j - 1);
+                    if (o > o_prev) {  // non-empty row j-1, last byte o-1 >= ws
+                        int b = o - 1 - ws;
+                        hit = (S.f[b >> 5] >> (b & 31)) & 1u;
+                        dirty = any_dirty && ((S.d[b >> 5] >> (b & 31)) & 1u);
+                        if (!dirty) A.out[j - 1] = hit;
+                    }
+                }
+                unsigned dm = __ballot_sync(FULL, dirty);
+                if (dm) {
+                    unsigned basei = 0;
+                    if (lane == 0) basei = atomicAdd(A.dirty_count, __popc(dm));
+                    basei = __shfl_sync(FULL, basei, 0);
+                    if (dirty) A.dirty_rows[basei + __popc(dm & ((1u << lane) - 1))] = j - 1;
+                }
+                my_matches += __popc(__ballot_sync(FULL, hit && !dirty));
+                unsigned m = __ballot_sync(FULL, in);
+                kfin += __popc(m);
+                if (m != FULL) break;
+            }
+            __syncwarp();
+            carry = carry_out;
+            cur_lo = nxt_lo;
+            cur_hi = nxt_hi;
+        }
+    }
+    if (lane == 0 && my_matches) atomicAdd(A.total, my_matches);
+}
+
+const PlanDev& device_plan(const Plan& plan);
+
+bool run(const Plan& plan, const custr_column* col, uint8_t* out, unsigned long long* total, int32_t** dirty_rows,
+         unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count)
+{
+    const int32_t n = col->n;
+    if (((uintptr_t)col->chars & 15) != 0) return false;  // vector loads need a 16-byte aligned base
+    CUSTR_CUDA(cudaMemsetAsync(out, 0, (size_t)n, g_stream));
+    keep_rows = dev_alloc(sizeof(int32_t) * (size_t)(n ? n : 1));
+    keep_count = dev_alloc(sizeof(unsigned int));
+    CUSTR_CUDA(cudaMemsetAsync(keep_count->ptr, 0, sizeof(unsigned int), g_stream));
+    *dirty_rows = (int32_t*)keep_rows->ptr;
+    *dirty_count = (unsigned int*)keep_count->ptr;
+    if (col->nbytes == 0) return true;
+    Args a;
+    a.chars = col->chars;
+    a.offsets = col->offsets;
+    a.n = n;
+    a.first = col->first_off;
+    a.end = col->first_off + (int32_t)col->nbytes;
+    a.nitems = (int)((col->nbytes + ITEM_BYTES - 1) / ITEM_BYTES);
+    a.out = out;
+    a.total = total;
+    a.dirty_rows = *dirty_rows;
+    a.dirty_count = *dirty_count;
+    int blocks = (a.nitems + WARPS - 1) / WARPS;
+    int cap = num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    LAUNCH(k_bitstream, blocks, THREADS, 0, device_plan(plan), a);
+    return true;
+}
+
+}  // namespace bits
+}  // namespace custr

@@ -1,4 +1,5 @@
-// Bit-parallel ("bitstream") regex tier: see regex_bits.cu.
+// Bit-parallel ("bitstream") regex tier: model in regex_bits_plan.h, lowering in regex_bits_lower.cpp, device
+// executor in regex_bits.cu.
 #pragma once
 #include "common.cuh"
 #include "regex_prog.h"
@@ -8,14 +9,23 @@
 namespace custr {
 namespace bits {
 
-struct Plan;  // lowered program (host description + device image)
+struct Plan;  // lowered program
 
 // Try to lower a compiled pattern to a bitstream plan for a boolean search (anchored = `match`, else
 // `contains_re`).  Returns null when the pattern is outside the provably-equivalent subset.
 std::shared_ptr<Plan> lower(const rx::Program& prog, bool anchored, const uint8_t* unicode_flags);
 std::string describe(const Plan& plan);
-// out[i] = 1 if row i matches; *total += number of matching rows.  Enqueued on g_stream.
-void run(const Plan& plan, const custr_column* col, uint8_t* out, unsigned long long* total);
+
+// Device run.  out[i] = 1 for matching rows that are pure ASCII; *total += their number.  Rows with a non-ASCII or NUL
+// byte are NOT decided: their indices are appended to *dirty_rows (count in *dirty_count, both device memory owned by the
+// returned buffers) for the exact Pike-VM kernel.  Returns false (nothing launched) if the column layout is not
+// supported (unaligned chars base).  Enqueued on g_stream.
+bool run(const Plan& plan, const custr_column* col, uint8_t* out, unsigned long long* total, int32_t** dirty_rows,
+         unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count);
+
+// Plain host executor of a plan (tests/sim only): out[i] for every row, dirty[i] = row needs the exact path.
+void reference_execute(const Plan& plan, const char* chars, const int32_t* offsets, const uint8_t* validity, int32_t n,
+                       uint8_t* out, uint8_t* dirty);
 
 }  // namespace bits
 }  // namespace custr

@@ -47,6 +47,10 @@ long long custr_launch_count(void);
 const char* custr_last_regex_tier(void);
 /* force a tier for A/B testing: 0 = auto, 1 = exact Pike VM only */
 void custr_set_regex_tier(int tier);
+/* when on, regex calls bracket their dominant kernel(s) with CUDA events on the launch stream;
+ * custr_last_kernel_ms() returns that device time for the last call on this thread (-1 if none) */
+void custr_set_profiling(int on);
+float custr_last_kernel_ms(void);
 
 /* ---- column create / export  (NVStrings::create_from_offsets NVStrings.cu:109-119, create_from_array :74-86,
  *      create_offsets :402-482, to_host :266-346, set_null_bitarray :493-544, byte_count/len attrs.cu:32,72) ---- */

@@ -80,6 +80,30 @@ int sim_count(const char* chars, const int32_t* off, const uint8_t* validity, in
     return total;
 }
 
+// bitstream tier on the host: plan reference executor for ASCII rows + exact VM for the rows it flags dirty.
+// returns -1 when the pattern is not eligible for the bitstream tier.
+int sim_bits_bool(const char* chars, const int32_t* off, const uint8_t* validity, int n, const char* pattern, int anchored, uint8_t* out)
+{
+    Prog p(pattern);
+    std::shared_ptr<bits::Plan> plan = bits::lower(p.prog, anchored != 0, k_flags);
+    if (!plan) return -1;
+    std::vector<uint8_t> dirty(n ? n : 1);
+    bits::reference_execute(*plan, chars, off, validity, n, out, dirty.data());
+    ColView col{chars, off, validity, 0, n};
+    L* lists = new L;
+    lists->init();
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        if (dirty[i]) {
+            int len = off[i + 1] - off[i], mb, me;
+            out[i] = col.valid(i) ? (uint8_t)rxdev::vm_find<1024>(p.P, (const uint8_t*)chars + off[i], len, 0, anchored ? 1 : len, mb, me, *lists) : 0;
+        }
+        total += out[i];
+    }
+    delete lists;
+    return total;
+}
+
 // out_off[n+1] always written; out_chars written when non-null (second call)
 long sim_replace_re(const char* chars, const int32_t* off, const uint8_t* validity, int n, const char* pattern, const char* repl,
                     int maxrepl, int32_t* out_off, char* out_chars)

@@ -46,6 +46,17 @@ def bool_search(chars, offsets, validity, pattern, anchored):
     return out[:n].astype(bool), rc
 
 
+def bits_bool(chars, offsets, validity, pattern, anchored):
+    """bitstream tier simulated on the host; returns (None, -1) when the pattern is not eligible"""
+    chars, offsets, validity = _cols(chars, offsets, validity)
+    n = len(offsets) - 1
+    out = np.zeros(max(n, 1), np.uint8)
+    rc = lib().sim_bits_bool(_p(chars), _p(offsets), _p(validity), n, pattern.encode() if isinstance(pattern, str) else pattern, int(anchored), _p(out))
+    if rc < 0:
+        return None, -1
+    return out[:n].astype(bool), rc
+
+
 def count(chars, offsets, validity, pattern):
     chars, offsets, validity = _cols(chars, offsets, validity)
     n = len(offsets) - 1
