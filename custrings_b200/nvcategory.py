@@ -50,18 +50,19 @@ def gather_keys_host(local_keys, group=None):
     return merged
 
 
-def gather_keys_device(keys, group=None):
-    """All-gather an nvstrings of keys across ranks with tensor collectives (NCCL on GPUs): sizes first, then the
-    max-padded (offsets, chars, validity) payloads.  Returns an nvstrings holding every rank's keys."""
+def exchange_key_arrays(chars, offsets, valid, group=None, device=None):
+    """All-gather one (chars uint8[], offsets int32[k+1], valid bool[k]) key column per rank with tensor collectives
+    (NCCL over NVLink on GPUs, gloo in the CPU tests): sizes first, then max-padded payloads.  Pure host/torch logic,
+    no custr calls.  Returns the rank-ordered concatenation (chars, offsets, valid)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
-        return keys
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    chars, offsets, validity = keys.to_arrays()
+        return chars, offsets, valid
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
     n = len(offsets) - 1
-    meta = torch.tensor([n, int(offsets[-1])], dtype=torch.int64, device=dev)
+    meta = torch.tensor([n, int(offsets[-1]) - int(offsets[0])], dtype=torch.int64, device=device)
     metas = [torch.zeros_like(meta) for _ in range(world)]
     dist.all_gather(metas, meta, group=group)
     metas = [m.cpu().tolist() for m in metas]
@@ -69,32 +70,36 @@ def gather_keys_device(keys, group=None):
     max_b = max(m[1] for m in metas)
     lens = np.zeros(max_n + 1, np.int32)
     lens[:n] = np.diff(offsets)
-    valid = np.zeros(max_n + 1, np.int32)
-    valid[:n] = np.unpackbits(validity, bitorder="little")[:n] if n else 0
+    vflags = np.zeros(max_n + 1, np.int32)
+    vflags[:n] = valid
     payload = np.zeros(max_b + 1, np.uint8)
-    payload[: len(chars)] = chars
-    t_len = torch.from_numpy(lens).to(dev)
-    t_val = torch.from_numpy(valid).to(dev)
-    t_chr = torch.from_numpy(payload).to(dev)
+    payload[: metas[dist.get_rank(group)][1]] = chars[int(offsets[0]): int(offsets[-1])]
+    t_len, t_val, t_chr = (torch.from_numpy(x).to(device) for x in (lens, vflags, payload))
     g_len = [torch.zeros_like(t_len) for _ in range(world)]
     g_val = [torch.zeros_like(t_val) for _ in range(world)]
     g_chr = [torch.zeros_like(t_chr) for _ in range(world)]
     dist.all_gather(g_len, t_len, group=group)
     dist.all_gather(g_val, t_val, group=group)
     dist.all_gather(g_chr, t_chr, group=group)
-    all_lens, all_valid, all_chars = [], [], []
-    for r in range(world):
-        k, b = metas[r]
-        all_lens.append(g_len[r][:k].cpu().numpy())
-        all_valid.append(g_val[r][:k].cpu().numpy().astype(bool))
-        all_chars.append(g_chr[r][:b].cpu().numpy())
-    lens = np.concatenate(all_lens)
-    valid = np.concatenate(all_valid)
-    chars = np.concatenate(all_chars)
-    offs = np.zeros(len(lens) + 1, np.int32)
-    np.cumsum(lens, out=offs[1:])
+    all_lens = np.concatenate([g_len[r][: metas[r][0]].cpu().numpy() for r in range(world)])
+    all_valid = np.concatenate([g_val[r][: metas[r][0]].cpu().numpy().astype(bool) for r in range(world)])
+    all_chars = np.concatenate([g_chr[r][: metas[r][1]].cpu().numpy() for r in range(world)])
+    offs = np.zeros(len(all_lens) + 1, np.int32)
+    np.cumsum(all_lens, out=offs[1:])
+    return all_chars, offs, all_valid
+
+
+def gather_keys_device(keys, group=None):
+    """All-gather an nvstrings of keys across ranks; returns an nvstrings holding every rank's keys in rank order."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return keys
+    chars, offsets, validity = keys.to_arrays()
+    n = len(offsets) - 1
+    valid = np.unpackbits(validity, bitorder="little")[:n].astype(bool) if n else np.zeros(0, bool)
+    chars, offs, valid = exchange_key_arrays(chars, offsets, valid, group)
     nulls = int((~valid).sum())
-    return _nvs.from_offsets(chars if chars.size else np.zeros(1, np.uint8), offs, len(lens), np.packbits(valid, bitorder="little"), nulls)
+    return _nvs.from_offsets(chars if chars.size else np.zeros(1, np.uint8), offs, len(offs) - 1, np.packbits(valid, bitorder="little"), nulls)
 
 
 def from_strings_sharded(strs, group=None):
