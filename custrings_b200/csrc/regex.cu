@@ -290,7 +290,8 @@ static int bool_search(const custr_column* col, const char* pattern, uint8_t* re
             unsigned int* dirty_count = nullptr;
             BufPtr keep_rows, keep_count;
             g_timer.start();
-            if (cap && bits::run(*plan, col, out.dev, total.get(), &dirty_rows, &dirty_count, keep_rows, keep_count)) {
+            if (cap && bits::run(*plan, col, (const uint8_t*)c->dev_image->ptr, device_unicode_flags(), out.dev, total.get(), &dirty_rows,
+                                 &dirty_count, keep_rows, keep_count)) {
                 // rows with non-ASCII / NUL bytes: exact VM over the work list (usually a few % of the rows)
                 int grid = vm_grid(n < 1 << 20 ? n : 1 << 20);
                 DISPATCH_CAP(cap, k_vm_bool_rows, grid, smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
@@ -347,7 +348,11 @@ extern "C" {
 const char* custr_last_regex_tier(void) { return g_last_tier; }
 void custr_set_profiling(int on) { g_profile = on; }
 float custr_last_kernel_ms(void) { return g_last_kernel_ms; }
-void custr_set_regex_tier(int tier) { g_forced_tier = tier; }
+void custr_set_regex_tier(int tier)
+{
+    g_forced_tier = tier == 1 ? 1 : 0;
+    bits::g_force_generic = tier == 2;  // 2: bitstream tier, generic DAG interpreter even for chain-shaped plans
+}
 
 int custr_regex_describe(const char* pattern, char* buf, size_t buflen)
 {

@@ -16,14 +16,19 @@
 //   * rows holding a byte >= 0x80 or a NUL are appended to a work list and decided by the exact Pike-VM kernel.
 #include "regex_bits.h"
 #include "regex_bits_plan.h"
+#include "regex_vm.cuh"
 
 namespace custr {
 namespace bits {
 
 struct Plan {
     PlanDev dev;
+    bool is_chain = false;
+    ChainDev chain;
     std::string text;
 };
+
+bool g_force_generic = false;  // A/B switch: run chain-shaped plans on the generic interpreter kernel
 
 constexpr int WARPS = 8;
 constexpr int THREADS = WARPS * 32;
@@ -44,6 +49,8 @@ struct Args {
     unsigned long long* total;
     int32_t* dirty_rows;
     unsigned int* dirty_count;
+    const uint8_t* prog_img;  // compiled program image (exact class tests for non-ASCII characters)
+    const uint8_t* uflags;
 };
 
 struct WarpSmem {
@@ -99,11 +106,14 @@ __device__ __forceinline__ void transpose_planes(const uint4& lo, const uint4& h
     t2 = __byte_perm(b2, b3, 0x5140); t3 = __byte_perm(b2, b3, 0x7362);
     p[4] = __byte_perm(t0, t2, 0x5410); p[5] = __byte_perm(t0, t2, 0x7632);
     p[6] = __byte_perm(t1, t3, 0x5410); p[7] = __byte_perm(t1, t3, 0x7632);
-#define DELTA_SWAP(A, B, S, M)                               \
-    {                                                        \
-        uint32_t na = ((A) & (M)) | (((B) << (S)) & ~(M));   \
-        uint32_t nb = (((A) >> (S)) & (M)) | ((B) & ~(M));   \
-        (A) = na; (B) = nb;                                  \
+    // one delta swap = 2 shifts + 2 bit-selects: (a & m) | (x & ~m) is a single LOP3 (LUT 0xE2) — ptxas does not
+    // find it on its own when m and ~m are both immediates
+#define DELTA_SWAP(A, B, S, M)                                                                              \
+    {                                                                                                       \
+        uint32_t na, nb, bs = (B) << (S), as_ = (A) >> (S);                                                 \
+        asm("lop3.b32 %0, %1, %2, %3, 0xE2;" : "=r"(na) : "r"(A), "r"(M), "r"(bs));                         \
+        asm("lop3.b32 %0, %1, %2, %3, 0xE2;" : "=r"(nb) : "r"(as_), "r"(M), "r"(B));                        \
+        (A) = na; (B) = nb;                                                                                 \
     }
     DELTA_SWAP(p[0], p[4], 4, 0x0F0F0F0Fu) DELTA_SWAP(p[1], p[5], 4, 0x0F0F0F0Fu)
     DELTA_SWAP(p[2], p[6], 4, 0x0F0F0F0Fu) DELTA_SWAP(p[3], p[7], 4, 0x0F0F0F0Fu)
@@ -176,6 +186,7 @@ struct Assertions {  // zero-width assertion streams of the current window
 };
 __device__ __forceinline__ uint32_t apply_before(uint32_t t, uint32_t m, const Assertions& a)
 {
+    if (m == AS_BOW) return t & a.bow_b;  // common single-assertion cases first
     if (m & AS_BOW) t &= a.bow_b;
     if (m & AS_NBOW) t &= ~a.bow_b;
     if (m & AS_BOL_CARET) t &= a.bolc_b;
@@ -186,6 +197,7 @@ __device__ __forceinline__ uint32_t apply_before(uint32_t t, uint32_t m, const A
 }
 __device__ __forceinline__ uint32_t apply_after(uint32_t t, uint32_t m, const Assertions& a)
 {
+    if (m == AS_BOW) return t & a.bow_a;
     if (m & AS_BOW) t &= a.bow_a;
     if (m & AS_NBOW) t &= ~a.bow_a;
     if (m & AS_BOL_CARET) t &= a.nl;
@@ -388,10 +400,13 @@ k_bitstream(const __grid_constant__ PlanDev plan, const Args A)
     if (lane == 0 && my_matches) atomicAdd(A.total, my_matches);
 }
 
+
+#include "regex_chain.cuh"
+
 const PlanDev& device_plan(const Plan& plan);
 
-bool run(const Plan& plan, const custr_column* col, uint8_t* out, unsigned long long* total, int32_t** dirty_rows,
-         unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count)
+bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, const uint8_t* uflags, uint8_t* out,
+         unsigned long long* total, int32_t** dirty_rows, unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count)
 {
     const int32_t n = col->n;
     if (((uintptr_t)col->chars & 15) != 0) return false;  // vector loads need a 16-byte aligned base
@@ -413,9 +428,15 @@ bool run(const Plan& plan, const custr_column* col, uint8_t* out, unsigned long 
     a.total = total;
     a.dirty_rows = *dirty_rows;
     a.dirty_count = *dirty_count;
+    a.prog_img = prog_img;
+    a.uflags = uflags;
     int blocks = (a.nitems + WARPS - 1) / WARPS;
     int cap = num_sms() * 8;
     if (blocks > cap) blocks = cap;
+    if (plan.is_chain && !g_force_generic) {
+        launch_chain(plan.chain, a, blocks);
+        return true;
+    }
     LAUNCH(k_bitstream, blocks, THREADS, 0, device_plan(plan), a);
     return true;
 }

@@ -19,6 +19,8 @@ namespace bits {
 
 struct Plan {
     PlanDev dev;
+    bool is_chain = false;
+    ChainDev chain;
     std::string text;
 };
 
@@ -151,8 +153,8 @@ struct Lowering {
     {
         switch (in.op) {
         case rx::OP_CHAR:
-            if (in.arg == 0 || in.arg >= 128) return false;
-            bm.set(in.arg);
+            if (in.arg == 0) return false;
+            if (in.arg < 128) bm.set(in.arg);  // a multi-byte literal has an empty ASCII set (decided by decoding)
             return true;
         case rx::OP_ANY: for (unsigned c = 0; c < 128; ++c) if (c != '\n') bm.set(c); return true;
         case rx::OP_ANYNL: for (unsigned c = 0; c < 128; ++c) bm.set(c); return true;
@@ -220,20 +222,31 @@ std::shared_ptr<Plan> lower(const rx::Program& prog, bool anchored, const uint8_
     memset(&P, 0, sizeof(P));
     P.anchored = anchored ? 1 : 0;
     P.nsteps = (uint8_t)order.size();
-    std::map<Bitmap128, int> class_ids;
+    std::map<std::pair<Bitmap128, std::pair<uint32_t, uint32_t>>, int> class_ids;
     for (size_t k = 0; k < order.size(); ++k) {
         const rx::Inst& in = prog.insts[order[k]];
         Bitmap128 bm;
         if (!L.class_bitmap(in, bm)) return nullptr;
         bm.w[0] &= ~1u;  // NUL is decided by the exact path
-        auto it = class_ids.find(bm);
+        uint32_t na_kind = NA_NEVER, na_arg = 0;
+        switch (in.op) {
+        case rx::OP_CHAR: if (in.arg >= 128) { na_kind = NA_CHAR_EQ; na_arg = in.arg; } break;
+        case rx::OP_ANY: case rx::OP_ANYNL: na_kind = NA_ALWAYS; break;
+        case rx::OP_CLASS: na_kind = NA_CLASS; na_arg = in.arg; break;
+        case rx::OP_NCLASS: na_kind = NA_NCLASS; na_arg = in.arg; break;
+        default: break;
+        }
+        auto key = std::make_pair(bm, std::make_pair(na_kind, na_arg));
+        auto it = class_ids.find(key);
         if (it == class_ids.end()) {
             if (class_ids.size() >= (size_t)MAX_CLASSES) return nullptr;
             ClassD cd{};
             if (!decompose(bm, cd)) return nullptr;
+            cd.na_kind = na_kind;
+            cd.na_arg = na_arg;
             int id = (int)class_ids.size();
             P.classes[id] = cd;
-            it = class_ids.emplace(bm, id).first;
+            it = class_ids.emplace(key, id).first;
         }
         P.steps[k].cls = (uint8_t)it->second;
     }
@@ -264,6 +277,39 @@ std::shared_ptr<Plan> lower(const rx::Program& prog, bool anchored, const uint8_
         }
     }
     if (P.nends == 0) return nullptr;
+    // ---- linear chain?  (step s fed only by s-1, END only from the last step, unguarded self loops)
+    {
+        bool chain = P.nsteps <= CHAIN_MAX_STEPS && P.nclasses <= CHAIN_MAX_CLASSES && P.nends == 1 && P.ends[0].src == P.nsteps - 1;
+        for (int s2 = 0; chain && s2 < P.nsteps; ++s2) {
+            const StepD& st = P.steps[s2];
+            chain = st.npreds == 1 && st.preds[0].src == (s2 == 0 ? SRC_START : s2 - 1) && (!st.self_loop || st.self_mask == 0) &&
+                    (s2 == 0 || st.preds[0].mask == 0);  // assertions only in front of the chain and before END
+        }
+        if (chain) {
+            ChainDev& C = plan->chain;
+            memset(&C, 0, sizeof(C));
+            C.nsteps = P.nsteps;
+            C.nclasses = P.nclasses;
+            C.anchored = P.anchored;
+            C.end_mask = P.ends[0].mask;
+            C.needs = P.before_needs | P.after_needs;
+            for (int s2 = 0; s2 < P.nsteps; ++s2)
+                C.steps[s2] = ChainStepD{P.steps[s2].cls, P.steps[s2].preds[0].mask, P.steps[s2].self_loop};
+            for (int k = 0; k < P.nclasses; ++k) {
+                ChainClassD& cc = C.classes[k];
+                const ClassD& src = P.classes[k];
+                cc.negate = src.negate;
+                cc.na_kind = src.na_kind;
+                cc.na_arg = src.na_arg;
+                for (int a2 = 0; a2 < src.natoms; ++a2) {
+                    if (src.atoms[a2].kind >= AK_WORD) cc.builtins |= 1u << src.atoms[a2].kind;
+                    else cc.atoms[cc.natoms++] = src.atoms[a2];
+                }
+                C.builtin_union |= cc.builtins;
+            }
+            plan->is_chain = true;
+        }
+    }
     plan->text = describe(*plan);
     return plan;
 }
@@ -273,7 +319,7 @@ std::string describe(const Plan& plan)
     const PlanDev& P = plan.dev;
     static const char* an[] = {"EQ", "RANGE", "WORD", "ALNUM", "DIGIT", "SPACE", "LOWER", "UPPER", "ANY"};
     std::ostringstream o;
-    o << (P.anchored ? "anchored " : "") << "classes=" << (int)P.nclasses << " steps=" << (int)P.nsteps << " ends=" << (int)P.nends << " {";
+    o << (plan.is_chain ? "chain " : "dag ") << (P.anchored ? "anchored " : "") << "classes=" << (int)P.nclasses << " steps=" << (int)P.nsteps << " ends=" << (int)P.nends << " {";
     for (int k = 0; k < P.nclasses; ++k) {
         o << " C" << k << "=" << (P.classes[k].negate ? "!" : "") << "(";
         for (int a = 0; a < P.classes[k].natoms; ++a) {
@@ -302,6 +348,7 @@ std::string describe(const Plan& plan)
 }
 
 const PlanDev& device_plan(const Plan& plan) { return plan.dev; }
+const ChainDev* device_chain(const Plan& plan) { return plan.is_chain ? &plan.chain : nullptr; }
 
 // ---- plain host executor (tests/sim only) ------------------------------------------------------------------------
 void reference_execute(const Plan& plan, const char* chars, const int32_t* offsets, const uint8_t* validity, int32_t n,

@@ -29,8 +29,10 @@ constexpr int MAX_PREDS = 6;
 constexpr int MAX_ENDS = 8;
 constexpr int SRC_START = 255;
 
+// how a class treats a NON-ASCII character (decided by decoding it, only where such bytes occur)
+enum NaKind : uint32_t { NA_NEVER = 0, NA_ALWAYS, NA_CHAR_EQ, NA_CLASS, NA_NCLASS };
 struct AtomD { uint8_t kind, lo, hi, pad; };
-struct ClassD { uint8_t natoms, negate, pad0, pad1; AtomD atoms[MAX_ATOMS]; };
+struct ClassD { uint8_t natoms, negate, pad0, pad1; AtomD atoms[MAX_ATOMS]; uint32_t na_kind, na_arg; };
 struct PredD { uint8_t src, mask; };                       // src = step index or SRC_START
 struct StepD { uint8_t cls, npreds, self_loop, self_mask; PredD preds[MAX_PREDS]; };
 struct EndD { uint8_t src, mask; };
@@ -41,6 +43,25 @@ struct PlanDev {
     ClassD classes[MAX_CLASSES];
     StepD steps[MAX_STEPS];
     EndD ends[MAX_ENDS];
+};
+
+// Linear-chain specialisation (regex_bits.cu k_chain): step s is fed only by step s-1 (step 0 by START), END hangs
+// off the last step.  Covers literals, class sequences, x+, x*, x{n,m}-free tails, leading/trailing assertions.
+constexpr int CHAIN_MAX_STEPS = 8;
+constexpr int CHAIN_MAX_CLASSES = 4;
+struct ChainStepD { uint32_t cls, before, loop; };
+struct ChainClassD {
+    uint32_t builtins;   // OR of (1 << AtomKind) for the builtin atoms (AK_WORD .. AK_ANY)
+    uint32_t natoms;     // remaining EQ / RANGE atoms
+    AtomD atoms[MAX_ATOMS];
+    uint32_t negate, na_kind, na_arg;
+};
+struct ChainDev {
+    uint32_t nsteps, nclasses, anchored, end_mask;
+    uint32_t needs;           // union of all assertion bits
+    uint32_t builtin_union;   // union of ChainClassD::builtins (which builtin streams to compute per window)
+    ChainStepD steps[CHAIN_MAX_STEPS];
+    ChainClassD classes[CHAIN_MAX_CLASSES];
 };
 
 // ASCII membership of one byte in an atom / class (shared by host reference executor and lowering checks)

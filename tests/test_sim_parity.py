@@ -72,7 +72,7 @@ def test_bitstream_lowering_equals_reference(data):
 def test_headline_pattern_is_bitstream_eligible():
     from tests import simlib
     d = simlib.describe(r"\b\w{4,}\b")
-    assert "bitstream: classes=1 steps=4" in d and "WORD" in d
+    assert "bitstream: chain classes=1 steps=4" in d and "WORD" in d
     assert "not eligible" in simlib.describe(r"a*")       # nullable -> exact VM
     assert "not eligible" in simlib.describe(r"(ab)+c")   # loop over two instructions -> exact VM
 

@@ -17,8 +17,11 @@ ap.add_argument("--bytes", type=int, default=1 << 30)
 ap.add_argument("--calls", type=int, default=4)
 ap.add_argument("--pattern", default=r"\b\w{4,}\b")
 ap.add_argument("--tier", type=int, default=0)
+ap.add_argument("--ascii", action="store_true", help="replace every non-ASCII byte by a letter")
 a = ap.parse_args()
 chars, offsets, validity, nulls = c2_corpus(a.rows, a.bytes)
+if a.ascii:
+    chars[chars >= 0x80] = 101
 col = nvstrings.from_offsets(chars, offsets, a.rows, validity, nulls)
 res = torch.empty(a.rows, dtype=torch.uint8, device="cuda")
 L = lib()
