@@ -14,7 +14,7 @@ NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nv
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
 
-SOURCES = ["column.cu", "regex.cu", "regex_bits.cu", "regex_bits_lower.cpp", "regex_compile.cpp", "find.cu", "split.cu", "category.cu"]
+SOURCES = ["column.cu", "regex.cu", "regex_bits.cu", "regex_bits_lower.cpp", "regex_compile.cpp", "find.cu", "split.cu", "category.cu", "classes.cpp"]
 
 
 def _stale(out, deps):

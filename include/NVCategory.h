@@ -1,0 +1,32 @@
+/*
+ * NVCategory — key-build subset of the reference's cpp/include/NVCategory.h:48-351 on libcustr.so's C-ABI.
+ * keys = distinct strings sorted by unsigned-byte order (null first), values = int32 key index per row.
+ */
+#pragma once
+#include <vector>
+#include "NVStrings.h"
+
+struct custr_category;
+
+class NVCategory {
+    custr_category* cat_;
+    explicit NVCategory(custr_category* c) : cat_(c) {}
+    ~NVCategory();
+    NVCategory(const NVCategory&) = delete;
+
+public:
+    static NVCategory* create_from_array(const char** strs, unsigned int count);                        // :71
+    static NVCategory* create_from_offsets(const char* strs, unsigned int count, const int* offsets,
+                                           const unsigned char* nullbitmask = 0, int nulls = 0, bool devmem = true);  // :101
+    static NVCategory* create_from_strings(NVStrings& strs);                                             // :107
+    static NVCategory* create_from_strings(std::vector<NVStrings*>& strs);                               // :114
+    static void destroy(NVCategory* inst);                                                               // :138
+
+    unsigned int size();          // :148
+    unsigned int keys_size();     // :152
+    bool has_nulls();             // :156
+    NVStrings* get_keys();        // :197
+    int get_values(int* results, bool devmem = true);  // :225
+    const int* values_cptr();     // :232
+    NVStrings* to_strings();      // :326
+};

@@ -1,0 +1,67 @@
+/*
+ * NVStrings — C++ class surface of the hot path, drop-in for the reference's cpp/include/NVStrings.h:48-1205
+ * (same method names, argument meaning, return values and exception types), implemented on libcustr.so's C-ABI
+ * (include/custr.h).  Instances are immutable; factories return new-ed objects released with NVStrings::destroy;
+ * result arrays are caller allocated (device memory when devmem == true).  Only the methods of SURVEY.md §8 are
+ * declared; everything else of the reference class is out of scope.
+ */
+#pragma once
+#include <cstddef>
+#include <utility>
+#include <vector>
+
+struct custr_column;
+
+class NVStrings {
+    custr_column* col_;
+    explicit NVStrings(custr_column* c) : col_(c) {}
+    ~NVStrings();
+    NVStrings(const NVStrings&) = delete;
+    NVStrings& operator=(const NVStrings&) = delete;
+    friend class NVCategory;
+    friend class NVText;
+
+public:
+    // reference NVStrings.h:86,116 / NVStrings.cu:74-119
+    static NVStrings* create_from_array(const char** strs, unsigned int count);
+    static NVStrings* create_from_offsets(const char* strs, int count, const int* offsets, const unsigned char* nullbitmask = 0,
+                                          int nulls = 0, bool devmem = true);
+    static void destroy(NVStrings* inst);  // :156
+
+    unsigned int size() const;                                                                           // :167
+    int create_offsets(char* strs, int* offsets, unsigned char* nullbitmask = 0, bool devmem = true);   // :207
+    unsigned int set_null_bitarray(unsigned char* bitarray, bool emptyIsNull = false, bool devmem = true);  // :225
+    int to_host(char** list, int start, int end);                                                       // :251
+    unsigned int len(int* lengths, bool devmem = true);                                                 // :345
+    size_t byte_count(int* lengths, bool devmem = true);                                                // :354
+    int hash(unsigned int* results, bool devmem = true);                                                // :1031
+
+    // regex: count.cu:59-250, replace.cu:110-189, replace_multi.cu:110-197
+    int contains_re(const char* pattern, bool* results, bool devmem = true);                            // :963
+    int match(const char* pattern, bool* results, bool devmem = true);                                  // :972
+    int count_re(const char* pattern, int* results, bool devmem = true);                                // :981
+    NVStrings* replace_re(const char* pattern, const char* repl, int maxrepl = -1);                     // :766
+    NVStrings* replace_re(std::vector<const char*>& patterns, NVStrings& repls);                        // :779
+
+    // literal: find.cu:75-387, modify.cu:109-299
+    unsigned int find(const char* str, int start, int end, int* results, bool devmem = true);           // :861
+    unsigned int rfind(const char* str, int start, int end, int* results, bool devmem = true);          // :873
+    unsigned int find_multiple(NVStrings& strs, int* results, bool devmem = true);                      // :898
+    int contains(const char* str, bool* results, bool devmem = true);                                   // :907
+    unsigned int startswith(const char* str, bool* results, bool devmem = true);                        // :925
+    unsigned int endswith(const char* str, bool* results, bool devmem = true);                          // :934
+    NVStrings* replace(const char* str, const char* repl, int maxrepl = -1);                            // :714
+    NVStrings* replace(NVStrings& strs, NVStrings& repls);                                              // :726
+
+    // split: split.cu:125-956.  split_record returns one NVStrings per row (nullptr for null rows); all of them are
+    // views over ONE flat token column instead of the reference's N allocations.
+    int split_record(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results);           // :464
+    int split_record(int maxsplit, std::vector<NVStrings*>& results);                                   // :484
+    unsigned int split(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results);          // :504
+    unsigned int split(int maxsplit, std::vector<NVStrings*>& results);                                 // :524
+
+    NVStrings* gather(const int* pos, unsigned int count, bool devmem = true);                          // :270
+    NVStrings* sublist(unsigned int start, unsigned int end, int step = 0);                             // :261
+
+    custr_column* column() const { return col_; }  // escape hatch to the C-ABI handle
+};
