@@ -29,6 +29,7 @@ struct Plan {
 };
 
 bool g_force_generic = false;  // A/B switch: run chain-shaped plans on the generic interpreter kernel
+bool g_chain32 = false;        // A/B switch: 32-bit-stream chain kernel instead of the 64-bit one
 
 constexpr int WARPS = 8;
 constexpr int THREADS = WARPS * 32;
@@ -124,41 +125,48 @@ __device__ __forceinline__ void transpose_planes(const uint4& lo, const uint4& h
 #undef DELTA_SWAP
 }
 
-// ---- character classes as boolean formulas over the planes (ASCII, plane 7 ignored) ---------------------------------
-__device__ __forceinline__ uint32_t cls_digit(const uint32_t (&p)[8])
+// ---- character classes as boolean formulas over the planes (ASCII, plane 7 ignored); T = uint32_t or uint64_t streams
+template <typename T>
+__device__ __forceinline__ T cls_digit(const T (&p)[8])
 {
     return ~p[6] & p[5] & p[4] & (~p[3] | (~p[2] & ~p[1]));
 }
-__device__ __forceinline__ uint32_t cls_letter5(const uint32_t (&p)[8])  // low five bits in 1..26
+template <typename T>
+__device__ __forceinline__ T cls_letter5(const T (&p)[8])  // low five bits in 1..26
 {
-    uint32_t nz = p[4] | p[3] | p[2] | p[1] | p[0];
-    uint32_t gt26 = p[4] & p[3] & (p[2] | (p[1] & p[0]));
+    T nz = p[4] | p[3] | p[2] | p[1] | p[0];
+    T gt26 = p[4] & p[3] & (p[2] | (p[1] & p[0]));
     return nz & ~gt26;
 }
-__device__ __forceinline__ uint32_t cls_alnum(const uint32_t (&p)[8]) { return (p[6] & cls_letter5(p)) | cls_digit(p); }
-__device__ __forceinline__ uint32_t cls_underscore(const uint32_t (&p)[8])
+template <typename T>
+__device__ __forceinline__ T cls_alnum(const T (&p)[8]) { return (p[6] & cls_letter5(p)) | cls_digit(p); }
+template <typename T>
+__device__ __forceinline__ T cls_underscore(const T (&p)[8])
 {
     return p[6] & ~p[5] & p[4] & p[3] & p[2] & p[1] & p[0];
 }
-__device__ __forceinline__ uint32_t cls_space(const uint32_t (&p)[8])
+template <typename T>
+__device__ __forceinline__ T cls_space(const T (&p)[8])
 {
-    uint32_t hi0 = ~p[6] & ~p[5];
-    uint32_t c9_13 = hi0 & ~p[4] & p[3] & ((~p[2] & (p[1] | p[0])) | (p[2] & ~p[1]));
-    uint32_t c28_31 = hi0 & p[4] & p[3] & p[2];
-    uint32_t c32 = ~p[6] & p[5] & ~(p[4] | p[3] | p[2] | p[1] | p[0]);
+    T hi0 = ~p[6] & ~p[5];
+    T c9_13 = hi0 & ~p[4] & p[3] & ((~p[2] & (p[1] | p[0])) | (p[2] & ~p[1]));
+    T c28_31 = hi0 & p[4] & p[3] & p[2];
+    T c32 = ~p[6] & p[5] & ~(p[4] | p[3] | p[2] | p[1] | p[0]);
     return c9_13 | c28_31 | c32;
 }
-__device__ __forceinline__ uint32_t cls_eq(const uint32_t (&p)[8], uint32_t c)
+template <typename T>
+__device__ __forceinline__ T cls_eq(const T (&p)[8], uint32_t c)
 {
-    uint32_t t = 0xffffffffu;
+    T t = ~T(0);
 #pragma unroll
     for (int b = 0; b < 7; ++b) t &= ((c >> b) & 1u) ? p[b] : ~p[b];
     return t;
 }
 // bytes >= c (7-bit compare, MSB first)
-__device__ __forceinline__ uint32_t cls_ge(const uint32_t (&p)[8], uint32_t c)
+template <typename T>
+__device__ __forceinline__ T cls_ge(const T (&p)[8], uint32_t c)
 {
-    uint32_t gt = 0, eq = 0xffffffffu;
+    T gt = 0, eq = ~T(0);
 #pragma unroll
     for (int b = 6; b >= 0; --b) {
         if ((c >> b) & 1u) eq &= p[b];
@@ -166,18 +174,19 @@ __device__ __forceinline__ uint32_t cls_ge(const uint32_t (&p)[8], uint32_t c)
     }
     return gt | eq;
 }
-__device__ __forceinline__ uint32_t cls_atom(const uint32_t (&p)[8], const AtomD a)
+template <typename T>
+__device__ __forceinline__ T cls_atom(const T (&p)[8], const AtomD a)
 {
     switch (a.kind) {
     case AK_EQ: return cls_eq(p, a.lo);
-    case AK_RANGE: return cls_ge(p, a.lo) & ~(a.hi >= 127 ? 0u : cls_ge(p, a.hi + 1u));
+    case AK_RANGE: return cls_ge(p, a.lo) & ~(a.hi >= 127 ? T(0) : cls_ge(p, a.hi + 1u));
     case AK_WORD: return cls_alnum(p) | cls_underscore(p);
     case AK_ALNUM: return cls_alnum(p);
     case AK_DIGIT: return cls_digit(p);
     case AK_SPACE: return cls_space(p);
     case AK_LOWER: return p[6] & p[5] & cls_letter5(p);
     case AK_UPPER: return p[6] & ~p[5] & cls_letter5(p);
-    default: return 0xffffffffu;
+    default: return ~T(0);
     }
 }
 
@@ -402,6 +411,7 @@ k_bitstream(const __grid_constant__ PlanDev plan, const Args A)
 
 
 #include "regex_chain.cuh"
+#include "regex_chain64.cuh"
 
 const PlanDev& device_plan(const Plan& plan);
 
@@ -434,7 +444,8 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     int cap = num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (plan.is_chain && !g_force_generic) {
-        launch_chain(plan.chain, a, blocks);
+        if (g_chain32) launch_chain(plan.chain, a, blocks);   // 1024-byte windows, 32-bit streams (A/B)
+        else launch_chain64(plan.chain, a, blocks);           // 2048-byte windows, 64-bit streams, cp.async ring
         return true;
     }
     LAUNCH(k_bitstream, blocks, THREADS, 0, device_plan(plan), a);

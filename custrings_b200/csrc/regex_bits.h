@@ -23,6 +23,7 @@ std::string describe(const Plan& plan);
 bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, const uint8_t* uflags, uint8_t* out,
          unsigned long long* total, int32_t** dirty_rows, unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count);
 extern bool g_force_generic;
+extern bool g_chain32;
 
 // Plain host executor of a plan (tests/sim only): out[i] for every row, dirty[i] = row needs the exact path.
 void reference_execute(const Plan& plan, const char* chars, const int32_t* offsets, const uint8_t* validity, int32_t n,

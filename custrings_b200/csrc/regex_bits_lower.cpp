@@ -301,6 +301,14 @@ std::shared_ptr<Plan> lower(const rx::Program& prog, bool anchored, const uint8_
                 cc.negate = src.negate;
                 cc.na_kind = src.na_kind;
                 cc.na_arg = src.na_arg;
+                if ((src.na_kind == NA_CLASS || src.na_kind == NA_NCLASS) && src.na_arg < prog.classes.size() &&
+                    prog.classes[src.na_arg].ranges.size() <= 8) {
+                    const rx::Class& rc = prog.classes[src.na_arg];
+                    cc.na_inline = 1;
+                    cc.na_builtins = (uint32_t)rc.builtins;
+                    cc.na_nranges = (uint32_t)rc.ranges.size();
+                    for (size_t r = 0; r < rc.ranges.size(); ++r) cc.na_ranges[r] = rc.ranges[r];
+                }
                 for (int a2 = 0; a2 < src.natoms; ++a2) {
                     if (src.atoms[a2].kind >= AK_WORD) cc.builtins |= 1u << src.atoms[a2].kind;
                     else cc.atoms[cc.natoms++] = src.atoms[a2];

@@ -55,6 +55,10 @@ struct ChainClassD {
     uint32_t natoms;     // remaining EQ / RANGE atoms
     AtomD atoms[MAX_ATOMS];
     uint32_t negate, na_kind, na_arg;
+    // exact definition of the source class for non-ASCII characters, kept in the kernel parameter block so the rare
+    // decode path does not chase the program image through global memory (na_inline == 0: use the image)
+    uint32_t na_inline, na_builtins, na_nranges;
+    uint32_t na_ranges[8];
 };
 struct ChainDev {
     uint32_t nsteps, nclasses, anchored, end_mask;

@@ -47,13 +47,31 @@ __device__ __forceinline__ uint32_t sel_class(const uint32_t (&c)[NCLS], uint32_
     return v;
 }
 
-__device__ __forceinline__ bool na_char_matches(const ChainClassD& cd, const rxdev::DevProg& P, uint32_t ch)
+// exact class test of a NON-ASCII character (reference regexec.inl:127-155) from the inlined class definition
+__device__ __forceinline__ bool na_class_inline(const ChainClassD& cd, const uint8_t* __restrict__ uflags, uint32_t ch)
+{
+    for (uint32_t i = 0; i < cd.na_nranges; i += 2)
+        if (ch >= cd.na_ranges[i] && ch <= cd.na_ranges[i + 1]) return true;
+    const uint32_t b = cd.na_builtins;
+    if (!b) return false;
+    const uint32_t cp = packed_to_cp(ch);
+    if (cp > 0xFFFFu) return false;
+    const uint32_t f = __ldg(uflags + cp);
+    const bool alnum = (f & 15u) != 0, space = (f & 16u) != 0, digit = (f & 4u) != 0;
+    return ((b & rx::CB_W) && alnum) || ((b & rx::CB_S) && space) || ((b & rx::CB_D) && digit) || ((b & rx::CB_NW) && !alnum) ||
+           ((b & rx::CB_NS) && !space) || ((b & rx::CB_ND) && !digit);
+}
+__device__ __forceinline__ bool na_char_matches(const ChainClassD& cd, const Args& A, uint32_t ch)
 {
     switch (cd.na_kind) {
     case NA_ALWAYS: return true;
     case NA_CHAR_EQ: return ch == cd.na_arg;
-    case NA_CLASS: return rxdev::class_match(P, (int)cd.na_arg, ch);
-    case NA_NCLASS: return !rxdev::class_match(P, (int)cd.na_arg, ch);
+    case NA_CLASS:
+        return cd.na_inline ? na_class_inline(cd, A.uflags, ch)
+                            : rxdev::class_match(rxdev::bind_program(A.prog_img, A.uflags), (int)cd.na_arg, ch);
+    case NA_NCLASS:
+        return !(cd.na_inline ? na_class_inline(cd, A.uflags, ch)
+                              : rxdev::class_match(rxdev::bind_program(A.prog_img, A.uflags), (int)cd.na_arg, ch));
     default: return false;
     }
 }
@@ -63,7 +81,6 @@ template <int NCLS>
 __device__ __noinline__ void classify_non_ascii(const ChainDev& cd, const Args& A, int lane_base, uint32_t na, uint32_t (&c)[NCLS],
                                                 uint32_t& al)
 {
-    rxdev::DevProg P = rxdev::bind_program(A.prog_img, A.uflags);
     const uint8_t* base = (const uint8_t*)A.chars;
     while (na) {
         int b = __ffs(na) - 1;
@@ -79,7 +96,7 @@ __device__ __noinline__ void classify_non_ascii(const ChainDev& cd, const Args& 
         na &= ~bits;
 #pragma unroll
         for (int k = 0; k < NCLS; ++k)
-            if (k < (int)cd.nclasses) c[k] = na_char_matches(cd.classes[k], P, ch) ? (c[k] | bits) : (c[k] & ~bits);
+            if (k < (int)cd.nclasses) c[k] = na_char_matches(cd.classes[k], A, ch) ? (c[k] | bits) : (c[k] & ~bits);
         al = is_alnum_packed(ch, A.uflags) ? (al | bits) : (al & ~bits);
     }
 }

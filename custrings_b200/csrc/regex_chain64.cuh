@@ -1,0 +1,468 @@
+// Linear-chain bitstream kernel, 64-bit streams — included by regex_bits.cu inside namespace custr::bits.
+//
+// Same model as regex_chain.cuh (k_chain), twice the work per warp iteration: a WINDOW is 2048 bytes, lane L owns the 64
+// bytes [64L, 64L+64) = one 64-bit word of every stream.  Everything that costs a fixed number of instructions per window
+// — the offsets pass (ROWSTART scatter + row finalisation), shuffles of advance / look-ahead, the two ballots and the
+// scalar carry solve of each `spread`, flag tests, loop overhead — is paid once per 2048 bytes instead of once per 1024.
+// Char tiles are staged global -> shared with cp.async (16-byte LDGSTS, zero-filled past the end of the buffer) into a
+// two-stage per-warp ring: the copy of window k+1 is in flight while window k is evaluated, and it costs no registers.
+// Each lane reads back only the 64 bytes it copied itself (bank-conflict-free swizzle), so cp.async.wait_group is the only
+// synchronisation the ring needs.
+#pragma once
+
+constexpr int WIN64 = 2048;
+constexpr int RING_STAGES = 2;
+using u64 = unsigned long long;
+
+__device__ __forceinline__ uint32_t lo32(u64 x) { return (uint32_t)x; }
+__device__ __forceinline__ uint32_t hi32(u64 x) { return (uint32_t)(x >> 32); }
+__device__ __forceinline__ u64 mk64(uint32_t lo, uint32_t hi) { return ((u64)hi << 32) | lo; }
+
+// move every bit one position up; bit 0 of lane 0 comes from the previous window (top word kept in last_hi)
+__device__ __forceinline__ u64 adv64(u64 x, uint32_t last_hi, const LaneCtx& L)
+{
+    uint32_t v = L.is31 ? last_hi : hi32(x);
+    uint32_t up = __shfl_sync(FULL, v, L.src);
+    return mk64(__funnelshift_l(up, lo32(x), 1), __funnelshift_l(lo32(x), hi32(x), 1));
+}
+__device__ __forceinline__ u64 shift_down64(u64 x, uint32_t next_bit, const LaneCtx& L)
+{
+    uint32_t dn = __shfl_down_sync(FULL, lo32(x), 1);
+    if (L.is31) dn = next_bit;
+    return mk64(__funnelshift_r(lo32(x), hi32(x), 1), __funnelshift_r(hi32(x), dn, 1));
+}
+// R[p] = Q[p] | (R[p-1] & K[p]) over the 2048 positions of the window; R[-1] = top bit of last_hi
+__device__ __forceinline__ u64 spread64(u64 q, u64 k, uint32_t last_hi, const LaneCtx& L)
+{
+    u64 s = adv64(q, last_hi, L) & k;
+    u64 sum = s + k;
+    uint32_t g = __ballot_sync(FULL, sum < s);
+    uint32_t p = __ballot_sync(FULL, sum == ~0ull);
+    uint32_t g1 = g << 1, p1 = p << 1;
+    uint32_t s2 = (g1 << 1) & p1;
+    uint32_t c = g1 | ((((s2 + p1) ^ p1) | s2) & p1);
+    sum += (c >> L.lane) & 1u;
+    return q | (((sum ^ k) | s) & k);
+}
+
+struct Assertions64 {
+    u64 rs, bow_b, bolc_b, nl, bow_a, lb, eold_a;
+};
+__device__ __forceinline__ u64 apply_before64_generic(u64 t, uint32_t m, const Assertions64& a)
+{
+    if (m & AS_BOW) t &= a.bow_b;
+    if (m & AS_NBOW) t &= ~a.bow_b;
+    if (m & AS_BOL_CARET) t &= a.bolc_b;
+    if (m & AS_BOL_A) t &= a.rs;
+    if (m & AS_EOL_DOLLAR) t &= a.nl;
+    if (m & AS_EOL_Z) t = 0;
+    return t;
+}
+__device__ __forceinline__ u64 apply_before64(u64 t, uint32_t m, const Assertions64& a)
+{
+    if (m == AS_BOW) return t & a.bow_b;  // the common single assertion inline, everything else out of line (code size)
+    return apply_before64_generic(t, m, a);
+}
+__device__ __forceinline__ u64 apply_after64_generic(u64 t, uint32_t m, const Assertions64& a)
+{
+    if (m & AS_BOW) t &= a.bow_a;
+    if (m & AS_NBOW) t &= ~a.bow_a;
+    if (m & AS_BOL_CARET) t &= a.nl;
+    if (m & AS_BOL_A) t = 0;
+    if (m & AS_EOL_DOLLAR) t &= a.eold_a;
+    if (m & AS_EOL_Z) t &= a.lb;
+    return t;
+}
+__device__ __forceinline__ u64 apply_after64(u64 t, uint32_t m, const Assertions64& a)
+{
+    if (m == AS_BOW) return t & a.bow_a;
+    return apply_after64_generic(t, m, a);
+}
+// EQ / RANGE atoms and multi-builtin classes: rare, kept out of the hot instruction stream
+__device__ __forceinline__ u64 class_generic64(const ChainClassD& cc, const u64 (&p)[8], u64 letter5, u64 digit, u64 alnum, u64 word, u64 space)
+{
+    const uint32_t f = cc.builtins;
+    u64 v = 0;
+    if (f & (1u << AK_WORD)) v |= word;
+    if (f & (1u << AK_ALNUM)) v |= alnum;
+    if (f & (1u << AK_DIGIT)) v |= digit;
+    if (f & (1u << AK_SPACE)) v |= space;
+    if (f & (1u << AK_LOWER)) v |= p[6] & p[5] & letter5;
+    if (f & (1u << AK_UPPER)) v |= p[6] & ~p[5] & letter5;
+    if (f & (1u << AK_ANY)) v = ~0ull;
+    for (uint32_t a = 0; a < cc.natoms; ++a) v |= cls_atom(p, cc.atoms[a]);
+    return v;
+}
+
+template <int NCLS>
+__device__ __forceinline__ u64 sel_class64(const u64 (&c)[NCLS], uint32_t k)
+{
+    if (NCLS == 1) return c[0];
+    if (NCLS == 2) return k ? c[1] : c[0];
+    u64 v = c[0];
+#pragma unroll
+    for (int i = 1; i < NCLS; ++i)
+        if (k == (uint32_t)i) v = c[i];
+    return v;
+}
+
+__device__ __forceinline__ int ring_chunk_offset(uint32_t lane, int k);
+
+// Non-ASCII bytes of this lane: decode each character once and give ALL its bytes (inside the lane) its class bits.
+// Bytes are taken from the lane's own staged copy in shared memory; only characters that straddle a lane boundary touch
+// global memory.
+template <int NCLS>
+__device__ __noinline__ void classify_non_ascii64(const ChainDev& cd, const Args& A, const char* slot, int lane_base, u64 na,
+                                                  u64 (&c)[NCLS], u64& al)
+{
+    const uint8_t* base = (const uint8_t*)A.chars;
+    const uint32_t lane = lane_id();
+    auto byte_at = [&](int pos) -> uint32_t {
+        const int rel = pos - lane_base;
+        if ((unsigned)rel < 64u) return (uint8_t)slot[ring_chunk_offset(lane, rel >> 4) + (rel & 15)];
+        return pos < A.end ? base[pos] : 0u;
+    };
+    while (na) {
+        const int b = __ffsll((long long)na) - 1;
+        int q = lane_base + b;
+        while (q > A.first && (byte_at(q) & 0xC0u) == 0x80u) --q;  // only the leading continuation run has to walk back
+        uint32_t ch = byte_at(q);
+        const int w = utf8_width((uint8_t)ch);
+        for (int k = 1; k < w; ++k) ch = (ch << 8) | byte_at(q + k);
+        int lo = q - lane_base, hi = lo + w;  // bytes of the character, lane-relative
+        if (lo < 0) lo = 0;
+        if (hi > 64) hi = 64;
+        if (hi <= b) hi = b + 1;  // malformed input: always make progress
+        const u64 bits = (hi >= 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
+        na &= ~bits;
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k)
+            if (k < (int)cd.nclasses) c[k] = na_char_matches(cd.classes[k], A, ch) ? (c[k] | bits) : (c[k] & ~bits);
+        al = is_alnum_packed(ch, A.uflags) ? (al | bits) : (al & ~bits);
+    }
+}
+
+template <int NS>
+struct ChainState64 {  // top words of the previous window's streams (only their top bit is ever used)
+    uint32_t last[NS];
+    uint32_t last_al, last_nl, last_f, last_d;
+};
+
+// One code path for ASCII and UTF-8 windows (the UTF-8 extras sit behind the warp-uniform `utf8` flag): duplicating the
+// chain for the two cases doubled the hot instruction footprint past the instruction cache.
+template <int NS, int NCLS>
+__device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[NCLS], u64 al, u64 nl, u64 rs, bool utf8, u64 cont,
+                                            uint32_t rs_next, uint32_t next_is_cont, uint32_t a_next, uint32_t nl_next,
+                                            ChainState64<NS>& st, const LaneCtx& L)
+{
+    const u64 nrs = ~rs;
+    u64 fin = ~0ull;       // last byte of a character
+    uint32_t cont0 = 0u;   // window starts inside a character
+    if (utf8) {
+        fin = ~shift_down64(cont, next_is_cont, L);
+        cont0 = __shfl_sync(FULL, lo32(cont), 0) & 1u;
+    }
+    Assertions64 as;
+    as.rs = rs;
+    as.nl = nl;
+    as.bow_b = as.bow_a = as.bolc_b = as.lb = as.eold_a = 0;
+    if (cd.needs & (AS_BOW | AS_NBOW)) {
+        as.bow_b = al ^ (adv64(al, st.last_al, L) & nrs);
+        as.bow_a = al ^ shift_down64(al & nrs, a_next, L);
+        st.last_al = hi32(al);
+    }
+    if (cd.needs & (AS_BOL_CARET | AS_EOL_DOLLAR | AS_EOL_Z)) {
+        as.bolc_b = rs | (adv64(nl, st.last_nl, L) & nrs);
+        as.lb = shift_down64(rs, rs_next, L);
+        as.eold_a = as.lb | shift_down64(nl & nrs, nl_next, L);
+        st.last_nl = hi32(nl);
+    }
+    u64 P = 0;
+    uint32_t old_prev = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        u64 t;
+        if (s == 0) {
+            t = cd.anchored ? rs : ~0ull;
+            const uint32_t before = cd.steps[0].before;
+            if (before) t = apply_before64(t, before, as);
+        } else {
+            // the marker of step s-1 moves to the next position; the carry (previous window's stream) is dropped when
+            // this window starts inside a character: that marker was not on a final byte
+            t = adv64(P, cont0 ? 0u : old_prev, L) & nrs;
+        }
+        const u64 ck = sel_class64<NCLS>(c, cd.steps[s].cls);
+        t &= ck & ~cont;
+        const uint32_t old = st.last[s];
+        u64 Z = t;
+        if (cd.steps[s].loop) Z = spread64(t, ck & nrs, old, L);
+        else if (utf8) {  // move the marker from the lead byte to the last byte of its character (<= 3 continuation bytes)
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) Z |= adv64(Z, old, L) & cont;
+        }
+        st.last[s] = hi32(Z);
+        old_prev = old;
+        P = Z & fin;
+    }
+    return cd.end_mask ? apply_after64(P, cd.end_mask, as) : P;
+}
+
+// lane L keeps its 4 x 16-byte chunks at a per-lane rotation so that the 8 lanes of an LDS.128 phase hit 8 distinct
+// 16-byte bank groups
+__device__ __forceinline__ int ring_chunk_offset(uint32_t lane, int k) { return 64 * (int)lane + 16 * ((k + (int)(lane >> 1)) & 3); }
+
+__device__ __forceinline__ void ring_issue(char* slot, const char* __restrict__ chars, int ws, int end, uint32_t lane)
+{
+    if (ws + WIN64 <= end) {  // whole window inside the buffer: plain 16-byte copies
+        const char* src = chars + ws + 64 * (int)lane;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot) + 64u * lane;
+        const uint32_t rot = lane >> 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * ((k + rot) & 3u)), "l"(src + 16 * k) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int pos = ws + 64 * (int)lane + 16 * k;
+        int bytes = end - pos;
+        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+        const char* src = chars + (bytes > 0 ? pos : 0);  // never form an out-of-range address; size 0 = pure zero fill
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + ring_chunk_offset(lane, k));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int NS, int NCLS>
+__global__ void __launch_bounds__(THREADS, 3)
+k_chain64(const __grid_constant__ ChainDev cd, const Args A)
+{
+    __shared__ __align__(16) char sm_ring[WARPS][RING_STAGES][WIN64];
+    __shared__ uint32_t sm_rs[WARPS][64], sm_f[WARPS][64], sm_d[WARPS][64];
+    const int warp = threadIdx.x >> 5;
+    uint32_t* S_rs = sm_rs[warp];
+    uint32_t* S_f = sm_f[warp];
+    uint32_t* S_d = sm_d[warp];
+    LaneCtx L;
+    L.lane = lane_id();
+    L.src = (L.lane + 31) & 31;
+    L.is31 = L.lane == 31;
+    const uint32_t lane = L.lane;
+    const int warps_total = gridDim.x * WARPS;
+    unsigned long long my_matches = 0;
+    const uint32_t bneed = cd.builtin_union | ((cd.needs & (AS_BOW | AS_NBOW)) ? (1u << AK_ALNUM) : 0u);
+    const bool need_nl = (cd.needs & (AS_BOL_CARET | AS_EOL_DOLLAR | AS_EOL_Z)) != 0;
+
+    for (int item = blockIdx.x * WARPS + warp; item < A.nitems; item += warps_total) {
+        const int lo_byte = A.first + item * ITEM_BYTES;
+        const int ra = item == 0 ? 0 : warp_lower_bound(A.offsets, A.n, lo_byte);
+        const int rb = item == A.nitems - 1 ? A.n : warp_lower_bound(A.offsets, A.n, lo_byte + ITEM_BYTES);
+        if (ra >= rb) continue;
+        const int byte_a = __ldg(A.offsets + ra), byte_b = __ldg(A.offsets + rb);
+        if (byte_a >= byte_b) continue;  // only empty rows: results stay 0 (pre-cleared)
+        ChainState64<NS> st;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) st.last[s] = 0;
+        st.last_al = st.last_nl = st.last_f = st.last_d = 0;
+        uint32_t d_live = 0;
+        int ws = byte_a & ~(WIN64 - 1);
+        int kcur = ra + 1;       // next offsets index to consume; offsets[j] >= ws for every j >= kcur
+        int prev_o = byte_a;     // offsets[kcur - 1]
+        int pend = byte_a - ws;  // window-relative position of a row start already known (-1: none)
+        int o_nxt = (kcur + (int)lane <= rb) ? __ldg(A.offsets + kcur + (int)lane) : 0x7fffffff;
+        int stage = 0;
+        __syncwarp();  // the previous item's reads of the ring are done
+        ring_issue(sm_ring[warp][0], A.chars, ws, A.end, lane);
+
+        for (; ws < byte_b; ws += WIN64, stage ^= 1) {
+            const int we = ws + WIN64;
+            const bool more = we < byte_b;
+            if (more) ring_issue(sm_ring[warp][stage ^ 1], A.chars, we, A.end, lane);  // next window in flight
+
+            // ---- one pass over the offsets that fall into (ws, we]: ROWSTART bits now, row results after evaluation
+            S_rs[2 * lane] = (lane == 0 && pend == 0) ? 1u : 0u;
+            S_rs[2 * lane + 1] = 0u;
+            __syncwarp();
+            if (pend > 0 && lane == 0) atomicOr(&S_rs[pend >> 5], 1u << (pend & 31));  // first window of the item
+            const int j = kcur + (int)lane;
+            const int o = o_nxt;
+            const bool inw = o <= we;
+            if (inw && o < we) atomicOr(&S_rs[(o - ws) >> 5], 1u << ((o - ws) & 31));
+            const unsigned m_in = __ballot_sync(FULL, inw);
+            bool at_we = __any_sync(FULL, inw && o == we);
+            int consumed = __popc(m_in);
+            if (m_in == FULL) {  // more than 32 rows end in this window (short / empty rows): generic loop
+                for (;;) {
+                    int j2 = kcur + consumed + (int)lane;
+                    int o2 = j2 <= rb ? __ldg(A.offsets + j2) : 0x7fffffff;
+                    bool in2 = o2 <= we;
+                    if (in2 && o2 < we) atomicOr(&S_rs[(o2 - ws) >> 5], 1u << ((o2 - ws) & 31));
+                    unsigned m2 = __ballot_sync(FULL, in2);
+                    at_we = at_we || __any_sync(FULL, in2 && o2 == we);
+                    consumed += __popc(m2);
+                    if (m2 != FULL) break;
+                }
+            }
+            {   // first offsets chunk of the NEXT window: issued now, consumed one iteration later
+                const int jn = kcur + consumed + (int)lane;
+                o_nxt = jn <= rb ? __ldg(A.offsets + jn) : 0x7fffffff;
+            }
+            __syncwarp();
+            const u64 rs = mk64(S_rs[2 * lane], S_rs[2 * lane + 1]);
+            const uint32_t rs_next = at_we || we >= A.end;
+            const uint32_t next_byte = (!rs_next && we < A.end) ? (uint8_t)A.chars[we] : 0;
+
+            // ---- this window's bytes: wait for its cp.async group, read back my own 64 bytes, transpose to bit planes
+            if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const char* slot = sm_ring[warp][stage];
+            u64 p[8];
+            {
+                uint32_t pl[8], ph[8];
+                const uint4 v0 = *(const uint4*)(slot + ring_chunk_offset(lane, 0));
+                const uint4 v1 = *(const uint4*)(slot + ring_chunk_offset(lane, 1));
+                transpose_planes(v0, v1, pl);
+                const uint4 v2 = *(const uint4*)(slot + ring_chunk_offset(lane, 2));
+                const uint4 v3 = *(const uint4*)(slot + ring_chunk_offset(lane, 3));
+                transpose_planes(v2, v3, ph);
+#pragma unroll
+                for (int b = 0; b < 8; ++b) p[b] = mk64(pl[b], ph[b]);
+            }
+            const u64 na = p[7];
+            const u64 zero = ~(p[0] | p[1] | p[2] | p[3] | p[4] | p[5] | p[6] | p[7]);
+            const u64 letter5 = cls_letter5(p), digit = cls_digit(p);
+            const u64 alnum = (p[6] & letter5) | digit, word = alnum | cls_underscore(p);
+            u64 space = 0;
+            if (bneed & (1u << AK_SPACE)) space = cls_space(p);
+            u64 c[NCLS];
+#pragma unroll
+            for (int k = 0; k < NCLS; ++k) {
+                u64 v = 0;
+                if (k < (int)cd.nclasses) {
+                    const uint32_t f = cd.classes[k].builtins;
+                    if (cd.classes[k].natoms == 0 && f == (1u << AK_WORD)) v = word;          // single builtin: inline
+                    else if (cd.classes[k].natoms == 0 && f == (1u << AK_DIGIT)) v = digit;
+                    else if (cd.classes[k].natoms == 0 && f == (1u << AK_ALNUM)) v = alnum;
+                    else if (cd.classes[k].natoms == 0 && f == (1u << AK_SPACE)) v = space;
+                    else v = class_generic64(cd.classes[k], p, letter5, digit, alnum, word, space);
+                    if (cd.classes[k].negate) v = ~v;
+                }
+                c[k] = v;
+            }
+            u64 al = alnum;
+            const u64 nl = need_nl ? (cls_eq(p, '\n') & ~na) : 0ull;
+            uint32_t a_next = 0;
+            const uint32_t nl_next = next_byte == '\n';
+            if (cd.needs & (AS_BOW | AS_NBOW)) {
+                if (next_byte < 0x80u) a_next = (next_byte - '0' < 10u) || ((next_byte | 0x20u) - 'a' < 26u);
+                else if ((next_byte & 0xC0u) != 0x80u) {
+                    int w;
+                    a_next = is_alnum_packed(utf8_packed((const uint8_t*)A.chars + we, (const uint8_t*)A.chars + A.end, w), A.uflags);
+                }
+            }
+            const bool utf8 = __any_sync(FULL, na != 0);
+            u64 cont = 0;
+            if (utf8) {
+                classify_non_ascii64<NCLS>(cd, A, slot, ws + 64 * (int)lane, na, c, al);
+                cont = p[7] & ~p[6];
+            }
+            const u64 E = chain_eval64<NS, NCLS>(cd, c, al, nl, rs, utf8, cont, rs_next, (next_byte & 0xC0u) == 0x80u, a_next, nl_next, st, L);
+
+            // ---- sticky per-row OR of the match bits; NUL bytes make a row "dirty" (decided by the exact VM)
+            const u64 nrs = ~rs;
+            const u64 F = spread64(E, nrs, st.last_f, L);
+            st.last_f = hi32(F);
+            S_f[2 * lane] = lo32(F);
+            S_f[2 * lane + 1] = hi32(F);
+            const bool any_dirty = __any_sync(FULL, zero != 0) || d_live;
+            if (any_dirty) {
+                const u64 D = spread64(zero, nrs, st.last_d, L);
+                st.last_d = hi32(D);
+                S_d[2 * lane] = lo32(D);
+                S_d[2 * lane + 1] = hi32(D);
+                d_live = __shfl_sync(FULL, hi32(D), 31) >> 31;
+            }
+            __syncwarp();
+
+            // ---- finalise the rows whose last byte lies in this window (first chunk from registers)
+            {
+                int o_prev = __shfl_up_sync(FULL, o, 1);
+                if (lane == 0) o_prev = prev_o;
+                bool hit = false, dirty = false;
+                if (inw && o > o_prev) {  // non-empty row j-1, last byte o-1 >= ws
+                    const int b = o - 1 - ws;
+                    hit = (S_f[b >> 5] >> (b & 31)) & 1u;
+                    dirty = any_dirty && ((S_d[b >> 5] >> (b & 31)) & 1u);
+                    if (!dirty) A.out[j - 1] = hit;
+                }
+                if (any_dirty) {
+                    const unsigned dm = __ballot_sync(FULL, dirty);
+                    if (dm) {
+                        unsigned basei = 0;
+                        if (lane == 0) basei = atomicAdd(A.dirty_count, __popc(dm));
+                        basei = __shfl_sync(FULL, basei, 0);
+                        if (dirty) A.dirty_rows[basei + __popc(dm & ((1u << lane) - 1))] = j - 1;
+                    }
+                }
+                my_matches += __popc(__ballot_sync(FULL, hit && !dirty));
+            }
+            if (m_in == FULL) {  // remaining chunks: reload
+                for (int k2 = kcur + 32; k2 < kcur + consumed; k2 += 32) {
+                    const int j2 = k2 + (int)lane;
+                    bool hit = false, dirty = false;
+                    if (j2 < kcur + consumed) {
+                        const int o2 = __ldg(A.offsets + j2), o2p = __ldg(A.offsets + j2 - 1);
+                        if (o2 > o2p) {
+                            const int b = o2 - 1 - ws;
+                            hit = (S_f[b >> 5] >> (b & 31)) & 1u;
+                            dirty = any_dirty && ((S_d[b >> 5] >> (b & 31)) & 1u);
+                            if (!dirty) A.out[j2 - 1] = hit;
+                        }
+                    }
+                    const unsigned dm = __ballot_sync(FULL, dirty);
+                    if (dm) {
+                        unsigned basei = 0;
+                        if (lane == 0) basei = atomicAdd(A.dirty_count, __popc(dm));
+                        basei = __shfl_sync(FULL, basei, 0);
+                        if (dirty) A.dirty_rows[basei + __popc(dm & ((1u << lane) - 1))] = j2 - 1;
+                    }
+                    my_matches += __popc(__ballot_sync(FULL, hit && !dirty));
+                }
+            }
+            if (consumed) {
+                prev_o = m_in == FULL ? __ldg(A.offsets + kcur + consumed - 1) : __shfl_sync(FULL, o, consumed - 1);
+                kcur += consumed;
+            }
+            pend = at_we ? 0 : -1;
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && my_matches) atomicAdd(A.total, my_matches);
+}
+
+template <int NS>
+static void launch_chain64_ns(const ChainDev& cd, const Args& a, int blocks)
+{
+    auto k1 = k_chain64<NS, 1>;
+    auto k2 = k_chain64<NS, 2>;
+    auto k4 = k_chain64<NS, 4>;
+    if (cd.nclasses <= 1) LAUNCH(k1, blocks, THREADS, 0, cd, a);
+    else if (cd.nclasses == 2) LAUNCH(k2, blocks, THREADS, 0, cd, a);
+    else LAUNCH(k4, blocks, THREADS, 0, cd, a);
+}
+
+static void launch_chain64(const ChainDev& cd, const Args& a, int blocks)
+{
+    switch (cd.nsteps) {
+    case 1: launch_chain64_ns<1>(cd, a, blocks); break;
+    case 2: launch_chain64_ns<2>(cd, a, blocks); break;
+    case 3: launch_chain64_ns<3>(cd, a, blocks); break;
+    case 4: launch_chain64_ns<4>(cd, a, blocks); break;
+    case 5: launch_chain64_ns<5>(cd, a, blocks); break;
+    case 6: launch_chain64_ns<6>(cd, a, blocks); break;
+    case 7: launch_chain64_ns<7>(cd, a, blocks); break;
+    default: launch_chain64_ns<8>(cd, a, blocks); break;
+    }
+}

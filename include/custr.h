@@ -45,7 +45,8 @@ int  custr_sync(void);
 long long custr_launch_count(void);
 /* name of the regex execution tier used by the last regex call on this thread ("bitstream", "pikevm") */
 const char* custr_last_regex_tier(void);
-/* force a tier for A/B testing: 0 = auto, 1 = exact Pike VM only */
+/* force a tier for A/B testing: 0 = auto, 1 = exact Pike VM only, 2 = bitstream generic interpreter kernel,
+ * 3 = bitstream 32-bit-stream chain kernel */
 void custr_set_regex_tier(int tier);
 /* when on, regex calls bracket their dominant kernel(s) with CUDA events on the launch stream;
  * custr_last_kernel_ms() returns that device time for the last call on this thread (-1 if none) */
