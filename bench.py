@@ -200,13 +200,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled from the warm-up on, through the device-resident timed region and the
+    # end-to-end region (a single nvidia-smi query takes longer than the 20-step timed region itself)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         matches = step()
     tier = L.custr_last_regex_tier().decode()
 
     # ---- device-resident timed region
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = L.custr_launch_count()
     L.custr_set_profiling(1)
     kernel_ms = []
@@ -221,8 +223,6 @@ def main():
     elapsed_ms = ev0.elapsed_time(ev1)
     L.custr_set_profiling(0)
     launches = L.custr_launch_count() - launches0
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
 
     # ---- end-to-end through the public API from host buffers
     def e2e_step():
@@ -240,6 +240,8 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_matches = int(h_res.sum().item())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
 
     times = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -253,6 +255,14 @@ def main():
         k_ms = float(np.mean(kernel_ms))
         alg = algorithmic_bytes(n, int(offsets[-1]))
         achieved = alg / (k_ms / 1e3) / 1e9
+        traffic = None
+        try:  # dram read+write of the dominant kernel from the committed ncu --set full capture (same workload)
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tj = json.load(f)
+            if tier == "bitstream" and args.rows == 10_000_000 and args.bytes == 1 << 30:
+                traffic = tj["traffic"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "strings/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -264,9 +274,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "strings/s", "h2d_bytes_per_step": int(chars.nbytes + offsets.nbytes + validity.nbytes),
                     "d2h_bytes_per_step": int(n), "steps": args.e2e_steps, "matches_rank0": e2e_matches},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel_ms": k_ms, "algorithmic_bytes": alg, "peak_source": peak_src,
-                         "kernel": "bits::k_bitstream" if tier == "bitstream" else "k_vm_bool"},
+                         "kernel": "bits::k_chain64<4,1> (+ memset, + k_vm_bool_rows for rows holding NUL)" if tier == "bitstream" else "k_vm_bool<32>"},
             "clocks": sampler.summary(),
         }
         if world == 1:
