@@ -1,0 +1,144 @@
+"""Full-size checks (BASELINE.json configs) through size-independent properties, where the oracle would take minutes:
+tier agreement, count/contains consistency, replace idempotence, tokenize/split agreement, dictionary round trip."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+PAT = r"\b\w{4,}\b"
+
+
+@pytest.fixture(scope="module")
+def c2():
+    import torch
+    from custrings_b200 import nvstrings
+    from custrings_b200.workloads import c2_corpus
+    n, nbytes = 10_000_000, 1 << 30
+    chars, offsets, validity, nulls = c2_corpus(n, nbytes)
+    col = nvstrings.from_offsets(chars, offsets, n, validity, nulls)
+    return n, chars, offsets, validity, nulls, col
+
+
+def _bool(col, pat, tier, anchored=False):
+    import torch
+    from custrings_b200._lib import lib
+    out = torch.zeros(col.size(), dtype=torch.uint8, device="cuda")
+    lib().custr_set_regex_tier(tier)
+    try:
+        fn = lib().custr_match if anchored else lib().custr_contains_re
+        cnt = fn(col.m_cptr, pat.encode(), out.data_ptr(), 1)
+        used = lib().custr_last_regex_tier().decode()
+    finally:
+        lib().custr_set_regex_tier(0)
+    return out, cnt, used
+
+
+def test_c2_tiers_agree_full_size(c2, oracle):
+    import torch
+    n, chars, offsets, validity, nulls, col = c2
+    fast, cnt_fast, used = _bool(col, PAT, 0)
+    assert used == "bitstream"
+    exact, cnt_exact, used1 = _bool(col, PAT, 1)
+    assert used1 == "pikevm"
+    assert cnt_fast == cnt_exact == int(fast.sum().item())
+    assert torch.equal(fast, exact)
+    for tier in (2, 3):
+        other, cnt, _ = _bool(col, PAT, tier)
+        assert cnt == cnt_exact and torch.equal(other, exact)
+    # oracle on a prefix of the same column
+    from custrings_b200.workloads import slice_rows
+    m = 200_000
+    c, o, v, nn = slice_rows(chars, offsets, validity, 0, m)
+    want, wcnt = oracle.RefStrings.from_arrays(c, o, v, nn).contains_re(PAT)
+    assert np.array_equal(fast[:m].cpu().numpy().astype(bool), want)
+    # null rows are false
+    valid = np.unpackbits(validity, bitorder="little")[:n].astype(bool)
+    assert not fast.cpu().numpy()[~valid].any()
+
+
+def test_c2_more_patterns_tiers_agree(c2):
+    import torch
+    n, chars, offsets, validity, nulls, col = c2
+    sub = col[0:2_000_000]
+    for pat, anchored in ((r"\d+", False), (r"[a-f]{3}\b", False), (r"é", False), (r"\w+ \w+", True), (r"^\w{8}", False), (r"z\w*$", False),
+                          (r"\bq\w+|\bz\w+", False)):
+        a, ca, _ = _bool(sub, pat, 0, anchored)
+        b, cb, _ = _bool(sub, pat, 1, anchored)
+        assert ca == cb and torch.equal(a, b), pat
+
+
+def test_c2_count_and_replace_properties(c2):
+    import torch
+    from custrings_b200._lib import lib
+    n, chars, offsets, validity, nulls, col = c2
+    sub = col[0:1_000_000]
+    m = sub.size()
+    hit, cnt, _ = _bool(sub, PAT, 0)
+    counts = torch.zeros(m, dtype=torch.int32, device="cuda")
+    nz = lib().custr_count_re(sub.m_cptr, PAT.encode(), counts.data_ptr(), 1)
+    assert nz == cnt and torch.equal(counts > 0, hit.bool())
+    replaced = sub.replace(PAT, "#")
+    again, cnt2, _ = _bool(replaced, PAT, 0)
+    assert cnt2 == 0 and not again.any()
+    # byte accounting: every match shrinks the row by (len(match) - 1) >= 3 bytes
+    assert replaced.byte_count() <= sub.byte_count() - 3 * int(counts.sum().item())
+    assert replaced.size() == m and replaced.null_count() == sub.null_count()
+
+
+def test_c2_tokenize_split_agree(c2):
+    from custrings_b200 import nvtext
+    import torch
+    n, chars, offsets, validity, nulls, col = c2
+    sub = col[0:1_000_000]
+    tc = torch.zeros(sub.size(), dtype=torch.int32, device="cuda")
+    nvtext.token_count(sub, None, devptr=tc.data_ptr())
+    tokens = nvtext.tokenize(sub)
+    assert tokens.size() == int(tc.sum().item())
+    flat, row_off = sub.split_record_flat(None)
+    # whitespace split_record: one "" token for valid rows without tokens, else the same tokens as tokenize
+    valid = np.unpackbits(sub.to_arrays()[2], bitorder="little")[: sub.size()].astype(bool)
+    per_row = np.diff(row_off)
+    tcn = tc.cpu().numpy()
+    assert np.array_equal(per_row[valid], np.maximum(tcn[valid], 1)) and (per_row[~valid] == 0).all()
+    assert tokens.byte_count() == flat.byte_count()
+
+
+def test_c4_category_roundtrip_large():
+    import torch
+    from custrings_b200 import nvstrings, nvcategory
+    rng = np.random.Generator(np.random.PCG64(11))
+    k, n = 1000, 5_000_000
+    lens = rng.integers(8, 25, size=k)
+    alphabet = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz0123456789", np.uint8)
+    keys = [alphabet[rng.integers(0, 36, size=l)].tobytes() for l in lens]
+    keys = list(dict.fromkeys(keys))
+    pick = rng.integers(0, len(keys), size=n)
+    klen = np.array([len(x) for x in keys])
+    koff = np.zeros(len(keys) + 1, np.int64)
+    np.cumsum(klen, out=koff[1:])
+    kchars = np.frombuffer(b"".join(keys), np.uint8)
+    row_len = klen[pick]
+    offsets = np.zeros(n + 1, np.int64)
+    np.cumsum(row_len, out=offsets[1:])
+    idx = np.repeat(koff[pick] - offsets[:-1], row_len) + np.arange(offsets[-1])
+    chars = kchars[idx]
+    col = nvstrings.from_offsets(chars, offsets.astype(np.int32), n)
+    cat = nvcategory.from_strings(col)
+    got_keys = [x.encode() for x in cat.keys().to_host()]
+    assert got_keys == sorted(keys)
+    rank = {key: i for i, key in enumerate(got_keys)}
+    want = np.array([rank[x] for x in keys], np.int32)[pick]
+    vals = torch.zeros(n, dtype=torch.int32, device="cuda")
+    cat.values(devptr=vals.data_ptr())
+    assert np.array_equal(vals.cpu().numpy(), want)
+
+
+def test_c1_split_csv_shape(oracle):
+    from custrings_b200 import nvstrings
+    rng = np.random.Generator(np.random.PCG64(3))
+    rows = ["%d,%s,%d.%02d,%s,,x" % (i, "ab" * int(rng.integers(0, 4)), rng.integers(0, 99), rng.integers(0, 99), "é" if i % 7 == 0 else "q")
+            for i in range(985)]
+    cols = nvstrings.to_device(rows).split(",")
+    want = oracle.RefStrings.from_list(rows).split(",")
+    assert len(cols) == len(want) == 6
+    for a, b in zip(cols, want):
+        assert oracle.unpack(*a.to_arrays()) == b.to_list()
