@@ -50,6 +50,7 @@ struct Args {
     unsigned long long* total;
     int32_t* dirty_rows;
     unsigned int* dirty_count;
+    unsigned int* item_counter;  // dynamic work distribution (k_chain64)
     const uint8_t* prog_img;  // compiled program image (exact class tests for non-ASCII characters)
     const uint8_t* uflags;
 };
@@ -422,8 +423,8 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     if (((uintptr_t)col->chars & 15) != 0) return false;  // vector loads need a 16-byte aligned base
     CUSTR_CUDA(cudaMemsetAsync(out, 0, (size_t)n, g_stream));
     keep_rows = dev_alloc(sizeof(int32_t) * (size_t)(n ? n : 1));
-    keep_count = dev_alloc(sizeof(unsigned int));
-    CUSTR_CUDA(cudaMemsetAsync(keep_count->ptr, 0, sizeof(unsigned int), g_stream));
+    keep_count = dev_alloc(2 * sizeof(unsigned int));  // [0] dirty-row count, [1] work-item counter
+    CUSTR_CUDA(cudaMemsetAsync(keep_count->ptr, 0, 2 * sizeof(unsigned int), g_stream));
     *dirty_rows = (int32_t*)keep_rows->ptr;
     *dirty_count = (unsigned int*)keep_count->ptr;
     if (col->nbytes == 0) return true;
@@ -438,6 +439,7 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     a.total = total;
     a.dirty_rows = *dirty_rows;
     a.dirty_count = *dirty_count;
+    a.item_counter = (unsigned int*)keep_count->ptr + 1;
     a.prog_img = prog_img;
     a.uflags = uflags;
     int blocks = (a.nitems + WARPS - 1) / WARPS;
@@ -445,7 +447,10 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     if (blocks > cap) blocks = cap;
     if (plan.is_chain && !g_force_generic) {
         if (g_chain32) launch_chain(plan.chain, a, blocks);   // 1024-byte windows, 32-bit streams (A/B)
-        else launch_chain64(plan.chain, a, blocks);           // 2048-byte windows, 64-bit streams, cp.async ring
+        else {  // 2048-byte windows, 64-bit streams, cp.async ring; grid = resident set (3 CTAs per SM), dynamic items
+            int resident = num_sms() * 3;
+            launch_chain64(plan.chain, a, blocks < resident ? blocks : resident);
+        }
         return true;
     }
     LAUNCH(k_bitstream, blocks, THREADS, 0, device_plan(plan), a);

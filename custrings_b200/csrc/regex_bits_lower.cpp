@@ -314,7 +314,24 @@ std::shared_ptr<Plan> lower(const rx::Program& prog, bool anchored, const uint8_
                     else cc.atoms[cc.natoms++] = src.atoms[a2];
                 }
                 C.builtin_union |= cc.builtins;
+                // exact 2-byte-character bitmap (covers Latin-1 .. Arabic): decided once here instead of per character
+                const rx::Inst& src_inst = prog.insts[order[0]];
+                (void)src_inst;
+                for (uint32_t cp = 0x80; cp < 0x800; ++cp) {
+                    const uint32_t packed = ((0xC0u | (cp >> 6)) << 8) | (0x80u | (cp & 0x3Fu));
+                    bool in = false;
+                    switch (src.na_kind) {
+                    case NA_ALWAYS: in = true; break;
+                    case NA_CHAR_EQ: in = packed == src.na_arg; break;
+                    case NA_CLASS: in = rx::class_matches(prog.classes[src.na_arg], packed, uflags); break;
+                    case NA_NCLASS: in = !rx::class_matches(prog.classes[src.na_arg], packed, uflags); break;
+                    default: break;
+                    }
+                    if (in) cc.na2[cp >> 5] |= 1u << (cp & 31);
+                }
             }
+            for (uint32_t cp = 0x80; cp < 0x800; ++cp)
+                if ((uflags[cp] & 15) != 0) C.na2_alnum[cp >> 5] |= 1u << (cp & 31);
             plan->is_chain = true;
         }
     }

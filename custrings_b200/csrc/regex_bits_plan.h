@@ -59,11 +59,13 @@ struct ChainClassD {
     // decode path does not chase the program image through global memory (na_inline == 0: use the image)
     uint32_t na_inline, na_builtins, na_nranges;
     uint32_t na_ranges[8];
+    uint32_t na2[64];    // membership bitmap of the 2-byte characters U+0080..U+07FF (bit = code point), exact
 };
 struct ChainDev {
     uint32_t nsteps, nclasses, anchored, end_mask;
     uint32_t needs;           // union of all assertion bits
     uint32_t builtin_union;   // union of ChainClassD::builtins (which builtin streams to compute per window)
+    uint32_t na2_alnum[64];   // \\b-alphanumeric bitmap of U+0080..U+07FF
     ChainStepD steps[CHAIN_MAX_STEPS];
     ChainClassD classes[CHAIN_MAX_CLASSES];
 };

@@ -135,6 +135,14 @@ __device__ __noinline__ void classify_non_ascii64(const ChainDev& cd, const Args
         if (hi <= b) hi = b + 1;  // malformed input: always make progress
         const u64 bits = (hi >= 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
         na &= ~bits;
+        if (w == 2) {  // U+0080..U+07FF: exact bitmaps in the kernel parameter block, no memory traffic
+            const uint32_t cp = ((ch >> 2) & 0x7C0u) | (ch & 0x3Fu);
+#pragma unroll
+            for (int k = 0; k < NCLS; ++k)
+                if (k < (int)cd.nclasses) c[k] = ((cd.classes[k].na2[cp >> 5] >> (cp & 31)) & 1u) ? (c[k] | bits) : (c[k] & ~bits);
+            al = ((cd.na2_alnum[cp >> 5] >> (cp & 31)) & 1u) ? (al | bits) : (al & ~bits);
+            continue;
+        }
 #pragma unroll
         for (int k = 0; k < NCLS; ++k)
             if (k < (int)cd.nclasses) c[k] = na_char_matches(cd.classes[k], A, ch) ? (c[k] | bits) : (c[k] & ~bits);
@@ -255,7 +263,14 @@ k_chain64(const __grid_constant__ ChainDev cd, const Args A)
     const uint32_t bneed = cd.builtin_union | ((cd.needs & (AS_BOW | AS_NBOW)) ? (1u << AK_ALNUM) : 0u);
     const bool need_nl = (cd.needs & (AS_BOL_CARET | AS_EOL_DOLLAR | AS_EOL_Z)) != 0;
 
-    for (int item = blockIdx.x * WARPS + warp; item < A.nitems; item += warps_total) {
+    // work items are handed out dynamically (one atomicAdd per 32 KiB item): the grid is exactly the resident set, so
+    // there is no partial last wave and the tail is a single item
+    (void)warps_total;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(A.item_counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= A.nitems) break;
         const int lo_byte = A.first + item * ITEM_BYTES;
         const int ra = item == 0 ? 0 : warp_lower_bound(A.offsets, A.n, lo_byte);
         const int rb = item == A.nitems - 1 ? A.n : warp_lower_bound(A.offsets, A.n, lo_byte + ITEM_BYTES);
