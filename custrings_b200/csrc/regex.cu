@@ -92,6 +92,26 @@ static CompiledPtr get_compiled(const char* pattern)
     return c;
 }
 
+// A program that is nothing but CHAR, CHAR, ..., END (e.g. the README day-of-week chain: replace("Sun","0") with the
+// default regex=True) matches exactly like the literal: same leftmost, non-overlapping spans.  Returns its UTF-8 bytes.
+static bool pure_literal(const rx::Program& p, std::string& lit)
+{
+    if (p.malformed || p.ngroups != 0 || p.insts.empty()) return false;
+    lit.clear();
+    int id = p.start_inst;
+    for (size_t guard = 0; guard <= p.insts.size(); ++guard) {
+        const rx::Inst& in = p.insts[id];
+        if (in.op == rx::OP_END) return !lit.empty();
+        if (in.op != rx::OP_CHAR || in.arg == 0) return false;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            unsigned b = (in.arg >> shift) & 0xFFu;
+            if (b || shift == 0) { if (b) lit.push_back((char)b); }
+        }
+        id = in.next;
+    }
+    return false;
+}
+
 static int cap_tier(int ninsts)
 {
     if (ninsts <= 32) return 32;
@@ -414,6 +434,13 @@ custr_column* custr_replace_re(const custr_column* col, const char* pattern, con
             int32_t n = col->n;
             if (n == 0) return custr_create_from_offsets(nullptr, 0, nullptr, nullptr, 0, 0);
             CompiledPtr c = get_compiled(pattern);
+            std::string lit;
+            if (g_forced_tier != 1 && pure_literal(c->prog, lit)) {  // literal pattern: the find-based kernel is exact
+                custr_column* r = custr_replace(col, lit.c_str(), repl, maxrepl);
+                if (!r) throw ArgError{CUSTR_ERR_INVALID};
+                g_last_tier = "literal";
+                return r;
+            }
             int cap = check_cap(*c, "replace_re");
             int repl_len = (int)strlen(repl);
             BufPtr d_repl = upload(repl, repl_len ? repl_len : 1);

@@ -118,3 +118,31 @@ def test_category(oracle):
     rng.shuffle(uniq)
     c4 = nvcategory.to_device(uniq)
     assert c4.keys().to_host() == sorted(uniq) and [sorted(uniq)[v] for v in c4.values()] == uniq
+
+
+def test_c3_readme_day_of_week_chain(oracle):
+    """BASELINE config 3 / reference README.md:29-31: split(',')[4] then 7 x replace(day, index) with regex=True"""
+    from custrings_b200 import nvstrings
+    from custrings_b200._lib import lib
+    rng = random.Random(7)
+    days = ["Sun", "Mon", "Tues", "Wed", "Thur", "Fri", "Sat"]
+    rows = ["%.2f,%.2f,%s,%s,%s,%s,%d" % (rng.random() * 50, rng.random() * 10, rng.choice(["Female", "Male"]), rng.choice(["Yes", "No"]),
+                                          rng.choice(days), rng.choice(["Lunch", "Dinner"]), rng.randint(1, 6)) for _ in range(3000)]
+    rows[17] = None
+    dev = nvstrings.to_device(rows).split(",")[4]
+    ref = oracle.RefStrings.from_list(rows).split(",")[4]
+    for i, d in enumerate(days):
+        dev = dev.replace(d, str(i))
+        assert lib().custr_last_regex_tier() == b"literal"
+        ref = ref.replace_re(d, str(i))
+    assert oracle.unpack(*dev.to_arrays()) == ref.to_list()
+    # the exact VM gives the same answer for the same chain
+    lib().custr_set_regex_tier(1)
+    try:
+        dev2 = nvstrings.to_device(rows).split(",")[4]
+        for i, d in enumerate(days):
+            dev2 = dev2.replace(d, str(i))
+        assert lib().custr_last_regex_tier() == b"pikevm"
+    finally:
+        lib().custr_set_regex_tier(0)
+    assert dev2.to_host() == dev.to_host()
