@@ -1,0 +1,92 @@
+"""Edge cases of the column layout against the bitstream kernels (windowing, row bookkeeping, views): every result
+is compared with the exact Pike-VM tier and, where cheap, with the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+PATS = [r"\b\w{4,}\b", r"\d+", r"^a", r"z$", r"é+x", r"\bq", r"[a-c]{2}\s", r"ab|cd", r"x\b", r"^$"]
+
+
+def _both(col, pat, anchored=False):
+    from custrings_b200._lib import lib
+    out = {}
+    for tier in (0, 1, 2, 3):
+        lib().custr_set_regex_tier(tier)
+        try:
+            out[tier] = col.match(pat) if anchored else col.contains(pat)
+        finally:
+            lib().custr_set_regex_tier(0)
+    return out
+
+
+def _check(strs, oracle=None):
+    from custrings_b200 import nvstrings
+    col = nvstrings.to_device(strs)
+    for pat in PATS:
+        for anchored in (False, True):
+            r = _both(col, pat, anchored)
+            assert r[0] == r[1] == r[2] == r[3], (pat, anchored)
+            if oracle is not None:
+                ref = oracle.RefStrings.from_list(strs)
+                want = (ref.match(pat) if anchored else ref.contains_re(pat))[0].tolist()
+                assert [False if x is None else x for x in r[0]] == want, (pat, anchored)
+    return col
+
+
+def test_degenerate_columns(oracle):
+    _check([""], oracle)
+    _check([None], oracle)
+    _check(["", "", None, ""] * 100, oracle)
+    _check(["abcd"], oracle)
+    _check(["a"] * 5000, oracle)                       # > 32 rows per window: multi-chunk row bookkeeping
+    _check(["", "abcd", ""] * 3000, oracle)
+    _check([None, "word", "", "zz z", "é"] * 2000, oracle)
+
+
+def test_long_rows_cross_many_windows(oracle):
+    big = "ab " * 300_000 + "abcd"                      # ~900 KB row, the only match at the very end
+    rows = ["x", big, "", "q" * 5000 + " éx", "12 " * 20000, None, "tail abcd"]
+    col = _check(rows, oracle)
+    assert col.contains(r"\b\w{4,}\b") == [False, True, False, True, False, None, True]
+
+
+def test_window_boundary_alignment(oracle):
+    # rows whose ends / multi-byte characters land exactly on 1024 / 2048 byte window boundaries
+    rows = []
+    for total in (1023, 1024, 1025, 2047, 2048, 2049, 4096):
+        rows.append("a" * (total - 5) + " bcde")
+    rows.append("a" * 2047 + "é" + "bcd")              # 2-byte char straddling a 2048-byte boundary
+    rows.append("x" * 1022 + "日本語" + "y" * 10)        # 3-byte chars across a 1024-byte boundary
+    rows.append("w" * 4095)
+    rows += ["ab", "", None, "é" * 700, "abc é" * 500]
+    _check(rows, oracle)
+
+
+def test_row_slice_views_and_gather():
+    from custrings_b200 import nvstrings
+    import random
+    rng = random.Random(5)
+    strs = ["".join(rng.choice("ab cdé1_\n") for _ in range(rng.choice([0, 1, 3, 9, 40, 200]))) for _ in range(5000)]
+    strs[10] = None
+    col = nvstrings.to_device(strs)
+    for lo, hi in ((0, 5000), (1, 4999), (7, 3001), (2500, 2501), (4999, 5000), (100, 100)):
+        view = col[lo:hi]
+        for pat in PATS[:6]:
+            r = _both(view, pat)
+            assert r[0] == r[1] == r[3], (lo, hi, pat)
+            assert r[0] == _both(nvstrings.to_device(strs[lo:hi]), pat)[1] if hi > lo else r[0] == []
+
+
+def test_adopted_device_buffers():
+    import torch
+    from custrings_b200 import nvstrings
+    strs = ["alpha beta", "", "xy", "gamma1234 z", "é", "a_b1 c"] * 1000
+    enc = [s.encode() for s in strs]
+    offsets = np.zeros(len(enc) + 1, np.int32)
+    np.cumsum([len(e) for e in enc], out=offsets[1:])
+    chars = torch.from_numpy(np.frombuffer(b"".join(enc), np.uint8).copy()).cuda()
+    offs = torch.from_numpy(offsets).cuda()
+    col = nvstrings.from_device_view(chars, offs, len(strs))
+    want = nvstrings.to_device(strs).contains(r"\b\w{4,}\b")
+    assert col.contains(r"\b\w{4,}\b") == want
+    assert col.to_host() == strs
