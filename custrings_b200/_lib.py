@@ -46,6 +46,9 @@ _SIGNATURES = {
     "custr_replace_re": (vp, [vp, cp, cp, ci]),
     "custr_replace_re_multi": (vp, [vp, vp, ci, vp]),
     "custr_regex_describe": (ci, [cp, vp, C.c_size_t]),
+    "custr_findall": (ci, [vp, cp, vp, ci]),
+    "custr_findall_record": (ci, [vp, cp, vp, vp, ci]),
+    "custr_extract": (ci, [vp, cp, vp, ci]),
     "custr_find": (ci, [vp, cp, ci, ci, vp, ci]),
     "custr_rfind": (ci, [vp, cp, ci, ci, vp, ci]),
     "custr_contains": (ci, [vp, cp, vp, ci]),

@@ -103,6 +103,44 @@ NVStrings* NVStrings::replace_re(std::vector<const char*>& patterns, NVStrings& 
     return new NVStrings(checked(custr_replace_re_multi(col_, patterns.data(), (int)patterns.size(), repls.col_)));
 }
 
+static int collect_columns(int (*fn)(const custr_column*, const char*, custr_column**, int32_t), const custr_column* col,
+                           const char* pattern, std::vector<NVStrings*>& results, NVStrings* (*wrap)(custr_column*))
+{
+    int cap = 64;
+    for (;;) {
+        std::vector<custr_column*> out((size_t)cap, nullptr);
+        int cols = checked(fn(col, pattern, out.data(), cap));
+        if (cols <= cap) {
+            for (int c = 0; c < cols; ++c) results.push_back(wrap(out[c]));
+            return cols;
+        }
+        for (int c = 0; c < cap; ++c) custr_column_free(out[c]);
+        cap = cols;
+    }
+}
+int NVStrings::findall(const char* pattern, std::vector<NVStrings*>& results)
+{
+    if (!pattern) return -1;
+    return collect_columns(custr_findall, col_, pattern, results, [](custr_column* c) { return new NVStrings(c); });
+}
+int NVStrings::extract(const char* pattern, std::vector<NVStrings*>& results)
+{
+    if (!pattern) return -1;
+    return collect_columns(custr_extract, col_, pattern, results, [](custr_column* c) { return new NVStrings(c); });
+}
+int NVStrings::findall_record(const char* pattern, std::vector<NVStrings*>& results)
+{
+    if (!pattern) return -1;
+    unsigned n = size();
+    custr_column* tokens = nullptr;
+    std::vector<int> row_off(n + 1, 0);
+    int total = checked(custr_findall_record(col_, pattern, &tokens, row_off.data(), 0));
+    checked(tokens);
+    for (unsigned i = 0; i < n; ++i) results.push_back(new NVStrings(checked(custr_slice_rows(tokens, row_off[i], row_off[i + 1]))));
+    custr_column_free(tokens);
+    return total;
+}
+
 unsigned int NVStrings::find(const char* str, int start, int end, int* results, bool devmem)
 {
     return (unsigned)checked(custr_find(col_, str, start, end, results, devmem));

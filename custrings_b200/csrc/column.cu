@@ -258,6 +258,32 @@ custr_column* make_column(BufPtr chars, BufPtr offsets, BufPtr validity, int32_t
     return c;
 }
 
+std::vector<custr_column*> assemble_columns(int32_t n, int ncols, int32_t* lens, const uint8_t* valid,
+                                            void (*copy)(const ColumnOut* d_outs, void* ctx), void* ctx)
+{
+    std::vector<BufPtr> offs(ncols), chars(ncols);
+    std::vector<int64_t> totals(ncols);
+    std::vector<ColumnOut> outs(ncols);
+    for (int c = 0; c < ncols; ++c) {
+        CUSTR_CUDA(cudaMemsetAsync(lens + (size_t)c * (n + 1) + n, 0, sizeof(int32_t), g_stream));
+        offs[c] = dev_alloc(sizeof(int32_t) * (size_t)(n + 1));
+        totals[c] = scan_lengths_to_offsets(lens + (size_t)c * (n + 1), (int32_t*)offs[c]->ptr, n);
+        chars[c] = dev_alloc((size_t)totals[c]);
+        outs[c] = ColumnOut{(char*)chars[c]->ptr, (const int32_t*)offs[c]->ptr};
+    }
+    BufPtr d_outs = upload(outs.data(), sizeof(ColumnOut) * (size_t)ncols);
+    copy((const ColumnOut*)d_outs->ptr, ctx);
+    std::vector<custr_column*> result;
+    for (int c = 0; c < ncols; ++c) {
+        BufPtr bits = dev_alloc((n + 7) / 8);
+        pack_bits(valid + (size_t)c * n, (uint8_t*)bits->ptr, n);
+        int32_t nulls = count_zero_bits((const uint8_t*)bits->ptr, 0, n);
+        result.push_back(make_column(chars[c], offs[c], bits, n, nulls, totals[c]));
+    }
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    return result;
+}
+
 custr_column* all_null_column(int32_t n)
 {
     BufPtr off = dev_alloc(sizeof(int32_t) * (size_t)(n + 1));

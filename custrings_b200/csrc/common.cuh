@@ -136,6 +136,13 @@ struct ResultBuf {  // device staging for a caller result array that may live on
 // upload a small host blob
 BufPtr upload(const void* host, size_t bytes);
 
+// Column-major result assembly shared by the "one output column per token / match / group" operations:
+// lens[c*(n+1)+row] and valid[c*n+row] are filled by the caller's length pass; `copy` must launch the kernel that writes
+// the bytes of (row, c) at outs[c].chars + outs[c].offsets[row].  Returns the ncols new columns.
+struct ColumnOut { char* chars; const int32_t* offsets; };
+std::vector<custr_column*> assemble_columns(int32_t n, int ncols, int32_t* lens, const uint8_t* valid,
+                                            void (*copy)(const ColumnOut* d_outs, void* ctx), void* ctx);
+
 // generic guard for the extern "C" layer
 template <typename F, typename R>
 R guarded(F&& f, R on_arg, R on_cuda)

@@ -253,6 +253,94 @@ k_vm_replace_multi(ColView col, MultiProgs progs, const uint8_t* __restrict__ uf
     }
 }
 
+
+// ---- findall / extract (capture-span callers, reference findall.cu:36-98, extract.cu:36-68) ---------------------------
+// walks the non-overlapping matches of a row exactly like count_re does and calls f(k, begin, end)
+template <int CAP, typename F>
+__device__ __forceinline__ int walk_matches(const rxdev::DevProg& P, const uint8_t* s, int n, rxdev::Lists<CAP>& L, int limit, F f)
+{
+    int k = 0, begin = 0;
+    while (begin <= n && k < limit) {
+        int mb = 0, me = 0;
+        if (!rxdev::vm_find<CAP>(P, s, n, begin, n, mb, me, L)) break;
+        f(k, mb, me);
+        ++k;
+        if (me > mb) begin = me;
+        else begin = mb + (mb < n ? utf8_width(s[mb]) : 1);
+    }
+    return k;
+}
+
+// pass 0: column-major lengths; pass 1: column-major copy; pass 2: row-major lengths; pass 3: row-major copy
+template <int CAP>
+__global__ void __launch_bounds__(VM_THREADS)
+k_vm_findall(ColView col, const uint8_t* __restrict__ img, int img_bytes, const uint8_t* __restrict__ uflags, int pass,
+             const int32_t* __restrict__ counts_or_rowoff, int ncols, int32_t* __restrict__ lens, uint8_t* __restrict__ valid,
+             const ColumnOut* __restrict__ outs, const int32_t* __restrict__ tok_off, char* __restrict__ flat_out)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    rxdev::DevProg P = rxdev::bind_program(stage_program(img, img_bytes, smem), uflags);
+    rxdev::Lists<CAP> L;
+    L.init();
+    const size_t n = col.n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < col.n; i += gridDim.x * blockDim.x) {
+        const uint8_t* s = (const uint8_t*)col.chars + col.offsets[i];
+        const int len = col.offsets[i + 1] - col.offsets[i];
+        if (pass < 2) {
+            const int cnt = counts_or_rowoff[i];
+            if (pass == 0) {
+                for (int k = 0; k < ncols; ++k) { lens[(size_t)k * (n + 1) + i] = 0; valid[(size_t)k * n + i] = k < cnt; }
+                if (cnt > 0) walk_matches<CAP>(P, s, len, L, cnt, [&](int k, int b, int e) { lens[(size_t)k * (n + 1) + i] = e - b; });
+            } else if (cnt > 0)
+                walk_matches<CAP>(P, s, len, L, cnt, [&](int k, int b, int e) {
+                    char* o = outs[k].chars + outs[k].offsets[i];
+                    for (int j = b; j < e; ++j) *o++ = (char)s[j];
+                });
+        } else {
+            const int first = counts_or_rowoff[i], cnt = counts_or_rowoff[i + 1] - first;
+            if (cnt <= 0) continue;
+            if (pass == 2) walk_matches<CAP>(P, s, len, L, cnt, [&](int k, int b, int e) { lens[first + k] = e - b; });
+            else
+                walk_matches<CAP>(P, s, len, L, cnt, [&](int k, int b, int e) {
+                    char* o = flat_out + tok_off[first + k];
+                    for (int j = b; j < e; ++j) *o++ = (char)s[j];
+                });
+        }
+    }
+}
+
+// extract: first match of the row, then one anchored re-run per capture group (reference extract.cu:50-58)
+template <int CAP>
+__global__ void __launch_bounds__(VM_THREADS)
+k_vm_extract(ColView col, const uint8_t* __restrict__ img, int img_bytes, const uint8_t* __restrict__ uflags, int pass, int ngroups,
+             int32_t* __restrict__ lens, uint8_t* __restrict__ valid, const ColumnOut* __restrict__ outs)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    rxdev::DevProg P = rxdev::bind_program(stage_program(img, img_bytes, smem), uflags);
+    rxdev::Lists<CAP> L;
+    rxdev::Lists<CAP, true> LG;
+    L.init();
+    LG.init();
+    const size_t n = col.n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < col.n; i += gridDim.x * blockDim.x) {
+        const uint8_t* s = (const uint8_t*)col.chars + col.offsets[i];
+        const int len = col.offsets[i + 1] - col.offsets[i];
+        int mb = 0, me = 0;
+        const bool hit = col.valid(i) && rxdev::vm_find<CAP>(P, s, len, 0, len, mb, me, L);
+        for (int g = 0; g < ngroups; ++g) {
+            int gb = -1, ge = -1;
+            bool ok = hit && rxdev::vm_find<CAP, true>(P, s, len, mb, mb + 1, gb, ge, LG, g + 1) && ge > gb && gb >= 0;
+            if (pass == 0) {
+                lens[(size_t)g * (n + 1) + i] = ok ? ge - gb : 0;
+                valid[(size_t)g * n + i] = ok;
+            } else if (ok) {
+                char* o = outs[g].chars + outs[g].offsets[i];
+                for (int j = gb; j < ge; ++j) *o++ = (char)s[j];
+            }
+        }
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------------------
 static inline int vm_grid(int n)
 {
@@ -359,6 +447,37 @@ static BufPtr copy_validity(const custr_column* col)
     return v;
 }
 
+
+struct FindallCtx { const custr_column* col; Compiled* c; int cap; const int32_t* counts; int ncols; };
+static void findall_copy(const ColumnOut* d_outs, void* vctx)
+{
+    FindallCtx* x = (FindallCtx*)vctx;
+    DISPATCH_CAP(x->cap, k_vm_findall, vm_grid(x->col->n), smem_for(*x->c), view_of(x->col), (const uint8_t*)x->c->dev_image->ptr,
+                 (int)x->c->image.size(), device_unicode_flags(), 1, x->counts, x->ncols, (int32_t*)nullptr, (uint8_t*)nullptr, d_outs,
+                 (const int32_t*)nullptr, (char*)nullptr);
+}
+struct ExtractCtx { const custr_column* col; Compiled* c; int cap; int ngroups; };
+static void extract_copy(const ColumnOut* d_outs, void* vctx)
+{
+    ExtractCtx* x = (ExtractCtx*)vctx;
+    DISPATCH_CAP(x->cap, k_vm_extract, vm_grid(x->col->n), smem_for(*x->c), view_of(x->col), (const uint8_t*)x->c->dev_image->ptr,
+                 (int)x->c->image.size(), device_unicode_flags(), 1, x->ngroups, (int32_t*)nullptr, (uint8_t*)nullptr, d_outs);
+}
+
+static int max_count(const int32_t* d, int n)
+{
+    Scratch<int32_t> out(1);
+    size_t tmp_bytes = 0;
+    cub::DeviceReduce::Max(nullptr, tmp_bytes, d, out.get(), n, g_stream);
+    BufPtr tmp = dev_alloc(tmp_bytes);
+    CUSTR_CUDA(cub::DeviceReduce::Max(tmp->ptr, tmp_bytes, d, out.get(), n, g_stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    int32_t h = 0;
+    CUSTR_CUDA(cudaMemcpyAsync(&h, out.get(), 4, cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    return h;
+}
+
 }  // namespace custr
 
 using namespace custr;
@@ -420,6 +539,103 @@ int custr_count_re(const custr_column* col, const char* pattern, int32_t* result
             int matches = (int)read_counter(total.get());
             out.finish();
             return matches;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
+
+int custr_findall(const custr_column* col, const char* pattern, custr_column** out, int32_t cap)
+{
+    return guarded(
+        [&]() -> int {
+            if (!col || !pattern) return fail(CUSTR_ERR_ARG, "findall: null argument");
+            int32_t n = col->n;
+            if (n == 0) return 0;
+            CompiledPtr c = get_compiled(pattern);
+            int vcap = check_cap(*c, "findall");
+            Scratch<int32_t> counts((size_t)n + 1);
+            Scratch<unsigned long long> total(1);
+            CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
+            DISPATCH_CAP(vcap, k_vm_count, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr, (int)c->image.size(),
+                         device_unicode_flags(), counts.get(), total.get());
+            int ncols = max_count(counts.get(), n);
+            if (ncols == 0) {  // no match anywhere: one all-null column (findall.cu:131-132)
+                if (cap > 0) out[0] = all_null_column(n);
+                return 1;
+            }
+            Scratch<int32_t> lens((size_t)ncols * (n + 1));
+            Scratch<uint8_t> valid((size_t)ncols * n);
+            DISPATCH_CAP(vcap, k_vm_findall, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
+                         (int)c->image.size(), device_unicode_flags(), 0, (const int32_t*)counts.get(), ncols, lens.get(), valid.get(),
+                         (const ColumnOut*)nullptr, (const int32_t*)nullptr, (char*)nullptr);
+            FindallCtx ctx{col, c.get(), vcap, counts.get(), ncols};
+            std::vector<custr_column*> cols = assemble_columns(n, ncols, lens.get(), valid.get(), findall_copy, &ctx);
+            for (int k = 0; k < ncols; ++k) { if (k < cap) out[k] = cols[k]; else custr_column_free(cols[k]); }
+            g_last_tier = "pikevm";
+            return ncols;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
+int custr_findall_record(const custr_column* col, const char* pattern, custr_column** tokens, int32_t* row_offsets, int devmem)
+{
+    return guarded(
+        [&]() -> int {
+            if (!col || !pattern || !tokens) return fail(CUSTR_ERR_ARG, "findall_record: null argument");
+            int32_t n = col->n;
+            CompiledPtr c = get_compiled(pattern);
+            int vcap = check_cap(*c, "findall_record");
+            Scratch<int32_t> counts((size_t)n + 1);
+            CUSTR_CUDA(cudaMemsetAsync(counts.get() + n, 0, 4, g_stream));
+            Scratch<unsigned long long> total(1);
+            CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
+            if (n) DISPATCH_CAP(vcap, k_vm_count, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
+                                (int)c->image.size(), device_unicode_flags(), counts.get(), total.get());
+            Scratch<int32_t> row_off((size_t)n + 1);
+            int64_t ntok = scan_lengths_to_offsets(counts.get(), row_off.get(), n);
+            Scratch<int32_t> tlens((size_t)ntok + 1);
+            CUSTR_CUDA(cudaMemsetAsync(tlens.get() + ntok, 0, 4, g_stream));
+            if (ntok) DISPATCH_CAP(vcap, k_vm_findall, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
+                                   (int)c->image.size(), device_unicode_flags(), 2, (const int32_t*)row_off.get(), 0, tlens.get(),
+                                   (uint8_t*)nullptr, (const ColumnOut*)nullptr, (const int32_t*)nullptr, (char*)nullptr);
+            BufPtr tok_off = dev_alloc(sizeof(int32_t) * (size_t)(ntok + 1));
+            int64_t bytes = scan_lengths_to_offsets(tlens.get(), (int32_t*)tok_off->ptr, (int32_t)ntok);
+            BufPtr chars = dev_alloc((size_t)bytes);
+            if (ntok) DISPATCH_CAP(vcap, k_vm_findall, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
+                                   (int)c->image.size(), device_unicode_flags(), 3, (const int32_t*)row_off.get(), 0, (int32_t*)nullptr,
+                                   (uint8_t*)nullptr, (const ColumnOut*)nullptr, (const int32_t*)tok_off->ptr, (char*)chars->ptr);
+            if (row_offsets) {
+                cudaMemcpyKind kind = devmem ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+                CUSTR_CUDA(cudaMemcpyAsync(row_offsets, row_off.get(), sizeof(int32_t) * (size_t)(n + 1), kind, g_stream));
+            }
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            *tokens = make_column(chars, tok_off, nullptr, (int32_t)ntok, 0, bytes);
+            g_last_tier = "pikevm";
+            return (int)ntok;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
+int custr_extract(const custr_column* col, const char* pattern, custr_column** out, int32_t cap)
+{
+    return guarded(
+        [&]() -> int {
+            if (!col || !pattern) return fail(CUSTR_ERR_ARG, "extract: null argument");
+            int32_t n = col->n;
+            if (n == 0) return 0;
+            CompiledPtr c = get_compiled(pattern);
+            int vcap = check_cap(*c, "extract");
+            int groups = c->prog.ngroups;
+            if (groups == 0) return 0;
+            Scratch<int32_t> lens((size_t)groups * (n + 1));
+            Scratch<uint8_t> valid((size_t)groups * n);
+            DISPATCH_CAP(vcap, k_vm_extract, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
+                         (int)c->image.size(), device_unicode_flags(), 0, groups, lens.get(), valid.get(), (const ColumnOut*)nullptr);
+            ExtractCtx ctx{col, c.get(), vcap, groups};
+            std::vector<custr_column*> cols = assemble_columns(n, groups, lens.get(), valid.get(), extract_copy, &ctx);
+            for (int k = 0; k < groups; ++k) { if (k < cap) out[k] = cols[k]; else custr_column_free(cols[k]); }
+            g_last_tier = "pikevm";
+            return groups;
         },
         (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
 }

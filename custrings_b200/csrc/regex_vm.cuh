@@ -59,10 +59,12 @@ CUSTR_HD bool class_match(const DevProg& P, int cls, uint32_t c)
     return false;
 }
 
-template <int CAP>
+// GROUPS: threads also carry the end of the tracked capture group (reference Relist ranges are int2, regexec.inl:26-108)
+template <int CAP, bool GROUPS = false>
 struct Lists {
     uint16_t id[2][CAP];
     int32_t beg[2][CAP];
+    int32_t endp[2][GROUPS ? CAP : 1];
     uint32_t mask[2][(CAP + 31) / 32];
     int size[2];
 
@@ -82,13 +84,14 @@ struct Lists {
         }
         size[k] = 0;
     }
-    CUSTR_HD void activate(int k, int inst, int b)
+    CUSTR_HD void activate(int k, int inst, int b, int e = -1)
     {
         uint32_t bit = 1u << (inst & 31);
         if (mask[k][inst >> 5] & bit) return;
         mask[k][inst >> 5] |= bit;
         id[k][size[k]] = (uint16_t)inst;
         beg[k][size[k]] = b;
+        if (GROUPS) endp[k][size[k]] = e;
         ++size[k];
     }
 };
@@ -96,9 +99,11 @@ struct Lists {
 // Search row bytes s[0..n) starting at byte offset `begin`; new threads are seeded at offset `off` only while
 // off < seed_limit (n for an unanchored search; begin+1 for "match only here": reference `end = begin+1`).
 // On success mbeg/mend are the byte offsets of the winning match.
-template <int CAP>
+// GROUPS / gid: track capture group `gid` (>= 1) instead of the whole match: threads are seeded with (-1,-1), LBRA / RBRA
+// of that group record the position, END reports the group's span (reference regexec.inl:296-307,422-425 with groupId).
+template <int CAP, bool GROUPS = false>
 __host__ __device__ int vm_find(const DevProg& P, const uint8_t* __restrict__ s, int n, int begin, int seed_limit, int& mbeg,
-                       int& mend, Lists<CAP>& L)
+                       int& mend, Lists<CAP, GROUPS>& L, int gid = 0)
 {
     int match = 0;
     int off = begin;
@@ -122,7 +127,7 @@ __host__ __device__ int vm_find(const DevProg& P, const uint8_t* __restrict__ s,
                 return match;
         }
         if (off < seed_limit && !match)
-            for (int i = 0; i < nstarts; ++i) L.activate(cur, P.starts[i], off);
+            for (int i = 0; i < nstarts; ++i) L.activate(cur, P.starts[i], GROUPS ? -1 : off, -1);
 
         int w = 1;
         c = off < n ? utf8_packed(s + off, s + n, w) : 0;
@@ -136,14 +141,20 @@ __host__ __device__ int vm_find(const DevProg& P, const uint8_t* __restrict__ s,
             expanded = false;
             for (int i = 0; i < L.size[cur]; ++i) {
                 const int id = L.id[cur][i];
-                const int b = L.beg[cur][i];
+                int b = L.beg[cur][i];
+                int e = GROUPS ? L.endp[cur][i] : -1;
                 const rx::Inst in = P.insts[id];
                 int go = -1;
                 switch (in.op) {
                 case rx::OP_CHAR: case rx::OP_ANY: case rx::OP_ANYNL: case rx::OP_CLASS: case rx::OP_NCLASS: case rx::OP_END:
                     go = id;
                     break;
-                case rx::OP_LBRA: case rx::OP_RBRA:
+                case rx::OP_LBRA:
+                    if (GROUPS && (int)in.arg == gid) b = off;
+                    go = in.next; expanded = true;
+                    break;
+                case rx::OP_RBRA:
+                    if (GROUPS && (int)in.arg == gid) e = off;
                     go = in.next; expanded = true;
                     break;
                 case rx::OP_BOL:
@@ -159,12 +170,12 @@ __host__ __device__ int vm_find(const DevProg& P, const uint8_t* __restrict__ s,
                     break;
                 }
                 case rx::OP_SPLIT:
-                    L.activate(nxt, in.other, b);
+                    L.activate(nxt, in.other, b, e);
                     go = in.next; expanded = true;
                     break;
                 default: break;  // OP_BAD: thread dies
                 }
-                if (go >= 0) L.activate(nxt, go, b);
+                if (go >= 0) L.activate(nxt, go, b, e);
             }
             cur = nxt;
         } while (expanded && ++rounds <= ninsts + 1);
@@ -186,12 +197,12 @@ __host__ __device__ int vm_find(const DevProg& P, const uint8_t* __restrict__ s,
                 case rx::OP_END:
                     match = 1;
                     mbeg = L.beg[cur][i];
-                    mend = off;
+                    mend = GROUPS ? L.endp[cur][i] : off;
                     i = L.size[cur];  // cut every lower-priority thread
                     break;
                 default: break;
                 }
-                if (take) L.activate(nxt, in.next, L.beg[cur][i]);
+                if (take) L.activate(nxt, in.next, L.beg[cur][i], GROUPS ? L.endp[cur][i] : -1);
             }
             cur = nxt;
         }

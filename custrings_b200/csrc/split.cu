@@ -88,8 +88,6 @@ k_split_lengths(ColView col, SplitParams P, const int32_t* __restrict__ counts, 
     }
 }
 
-struct ColumnOut { char* chars; const int32_t* offsets; };
-
 __global__ void __launch_bounds__(SPLIT_THREADS)
 k_split_copy(ColView col, SplitParams P, const int32_t* __restrict__ counts, const ColumnOut* __restrict__ outs)
 {

@@ -281,6 +281,46 @@ class nvstrings:
             h = lib().custr_replace_multi(self.m_cptr, pats.m_cptr, repls.m_cptr)
         return nvstrings(check_handle(h, "replace_multi"))
 
+    def findall(self, pat):
+        """All non-overlapping matches, column-major: result[c] holds the c-th match of every row (None where a row has
+        fewer).  reference nvstrings.py:1921 -> findall.cu:99"""
+        return self._columns(lib().custr_findall, pat, "findall")
+
+    def findall_record(self, pat):
+        """One nvstrings of matches per row (None for null rows).  reference nvstrings.py:1891 -> findall_record.cu:97"""
+        rows = self.size()
+        row_off = np.zeros(rows + 1, np.int32)
+        tok = C.c_void_p()
+        check_rc(lib().custr_findall_record(self.m_cptr, _enc(pat), C.byref(tok), as_ptr(row_off), 0), "findall_record")
+        tokens = nvstrings(check_handle(tok.value, "findall_record"))
+        # the reference returns an EMPTY instance (not None) for rows without matches, null rows included
+        return [nvstrings(check_handle(lib().custr_slice_rows(tokens.m_cptr, int(row_off[i]), int(row_off[i + 1])), "findall_record"))
+                for i in range(rows)]
+
+    def extract(self, pat):
+        """One nvstrings per capture group of the first match.  reference nvstrings.py:2127 -> extract.cu:69"""
+        return self._columns(lib().custr_extract, pat, "extract")
+
+    def extract_record(self, pat):
+        """Per row: an nvstrings with one entry per capture group (None for null rows).  reference nvstrings.py:2097"""
+        cols = [c.to_host() for c in self.extract(pat)]
+        hit = self.contains(pat)
+        # reference extract_record.cu: a matching row gets "" for a group without a span, a non-matching row all-null
+        return [to_device([(c[i] if c[i] is not None else ("" if hit[i] else None)) for c in cols]) for i in range(self.size())]
+
+    def _columns(self, fn, pat, what):
+        if pat is None:
+            raise ValueError(what + ": pat is None")
+        cap = 64
+        while True:
+            out = (C.c_void_p * cap)()
+            cols = check_rc(fn(self.m_cptr, _enc(pat), out, cap), what)
+            got = [nvstrings(out[i]) for i in range(min(max(cols, 0), cap))]
+            if cols <= cap:
+                return got
+            del got
+            cap = cols
+
     # ------------------------------------------------------------------ literal find
     def find(self, sub, start=0, end=None, devptr=0):
         """Character position of the first `sub` in [start,end), -1 if absent.  reference nvstrings.py:1796"""

@@ -43,6 +43,11 @@ public:
     NVStrings* replace_re(const char* pattern, const char* repl, int maxrepl = -1);                     // :766
     NVStrings* replace_re(std::vector<const char*>& patterns, NVStrings& repls);                        // :779
 
+    // capture-span callers ("next" rows): findall.cu:99, findall_record.cu:97, extract.cu:69
+    int findall(const char* pattern, std::vector<NVStrings*>& results);          // :943  column c = c-th match of each row
+    int findall_record(const char* pattern, std::vector<NVStrings*>& results);   // :952  one (possibly empty) instance per row
+    int extract(const char* pattern, std::vector<NVStrings*>& results);          // :682  one column per capture group
+
     // literal: find.cu:75-387, modify.cu:109-299
     unsigned int find(const char* str, int start, int end, int* results, bool devmem = true);           // :861
     unsigned int rfind(const char* str, int start, int end, int* results, bool devmem = true);          // :873

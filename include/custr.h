@@ -90,6 +90,13 @@ int custr_count_re(const custr_column* col, const char* pattern, int32_t* result
 custr_column* custr_replace_re(const custr_column* col, const char* pattern, const char* repl, int32_t maxrepl);
 custr_column* custr_replace_re_multi(const custr_column* col, const char* const* patterns, int32_t npatterns,
                                      const custr_column* repls);
+/* Capture-span callers ("next" rows of the scope table): NVStrings::findall findall.cu:99-170 (column c = c-th match of each
+ * row, null where a row has fewer), findall_record findall_record.cu:97 (flat: all matches in row order + row offsets),
+ * extract extract.cu:69-150 (one column per capture group of the FIRST match; null when the row does not match or the group
+ * is empty).  Column-major variants write up to `cap` columns and return the number of columns. */
+int custr_findall(const custr_column* col, const char* pattern, custr_column** out, int32_t cap);
+int custr_findall_record(const custr_column* col, const char* pattern, custr_column** tokens, int32_t* row_offsets, int devmem);
+int custr_extract(const custr_column* col, const char* pattern, custr_column** out, int32_t cap);
 /* Debug/inspection: compile a pattern and print its instruction listing into buf (host). Returns #instructions. */
 int custr_regex_describe(const char* pattern, char* buf, size_t buflen);
 

@@ -52,6 +52,8 @@ def lib():
         L.ref_split.argtypes = [vp, cp, ci, ci, vp, ci]
         L.ref_split_record.argtypes = [vp, cp, ci, ci, vp]
         L.ref_partition.argtypes = [vp, cp, ci, vp]
+        L.ref_regex_columns.argtypes = [vp, cp, ci, vp, ci]
+        L.ref_regex_records.argtypes = [vp, cp, ci, vp]
         L.ref_tokenize.argtypes = [vp, cp]
         L.ref_tokenize_multi.argtypes = [vp, vp]
         L.ref_token_count.argtypes = [vp, cp, vp]
@@ -216,6 +218,28 @@ class RefStrings:
         out = (C.c_void_p * max(n, 1))()
         rc = lib().ref_partition(self.h, _b(delim), int(right), out)
         return [RefStrings(out[i]) if out[i] else None for i in range(n)], rc
+
+    def _regex_columns(self, pat, kind):
+        cap = 256
+        out = (C.c_void_p * cap)()
+        n = lib().ref_regex_columns(self.h, _b(pat), kind, out, cap)
+        if n == -100:
+            raise ValueError(lib().ref_last_error().decode())
+        return [RefStrings(out[i]) for i in range(min(n, cap))]
+
+    def findall(self, pat): return self._regex_columns(pat, 0)
+    def extract(self, pat): return self._regex_columns(pat, 1)
+
+    def _regex_records(self, pat, kind):
+        n = self.size()
+        out = (C.c_void_p * max(n, 1))()
+        rc = lib().ref_regex_records(self.h, _b(pat), kind, out)
+        if rc == -100:
+            raise ValueError(lib().ref_last_error().decode())
+        return [RefStrings(out[i]) if out[i] else None for i in range(n)]
+
+    def findall_record(self, pat): return self._regex_records(pat, 0)
+    def extract_record(self, pat): return self._regex_records(pat, 1)
 
     def tokenize(self, delim=None):
         return RefStrings(lib().ref_tokenize(self.h, _b(delim)))

@@ -125,6 +125,29 @@ int ref_partition(void* h, const char* delim, int right, void** out)
     return rc;
 }
 
+// column-major regex results: findall (kind 0) / extract (kind 1); writes up to cap handles, returns #columns
+int ref_regex_columns(void* h, const char* pat, int kind, void** out, int cap)
+{
+    NVStrings* s = (NVStrings*)h;
+    std::vector<NVStrings*> res;
+    int rc;
+    GUARD(rc = kind == 0 ? s->findall(pat, res) : s->extract(pat, res), -100);
+    int n = (int)res.size();
+    for (int i = 0; i < n; ++i) { if (i < cap) out[i] = res[i]; else NVStrings::destroy(res[i]); }
+    (void)rc;
+    return n;
+}
+// row-major: findall_record (kind 0) / extract_record (kind 1); out holds size() handles
+int ref_regex_records(void* h, const char* pat, int kind, void** out)
+{
+    NVStrings* s = (NVStrings*)h;
+    std::vector<NVStrings*> res;
+    int rc;
+    GUARD(rc = kind == 0 ? s->findall_record(pat, res) : s->extract_record(pat, res), -100);
+    for (size_t i = 0; i < res.size(); ++i) out[i] = res[i];
+    return rc;
+}
+
 void* ref_tokenize(void* h, const char* delim) { GUARD(return NVText::tokenize(*(NVStrings*)h, delim), nullptr); }
 void* ref_tokenize_multi(void* h, void* delims) { GUARD(return NVText::tokenize(*(NVStrings*)h, *(NVStrings*)delims), nullptr); }
 int ref_token_count(void* h, const char* delim, unsigned* out) { GUARD(return (int)NVText::token_count(*(NVStrings*)h, delim, out, false), -100); }

@@ -77,3 +77,27 @@ def test_roundtrip_and_attrs(cols, oracle):
     sub = dev[3:20]
     assert sub.to_host() == strs[3:20]
     assert dev.gather([5, 0, 14, 2]).to_host() == [strs[5], strs[0], strs[14], strs[2]]
+
+
+def test_findall_extract_capture_spans(cols, oracle):
+    """'next' rows of the scope table: findall / findall_record / extract / extract_record vs the oracle"""
+    strs, dev, ref = cols
+
+    def lst(c):
+        return oracle.unpack(*c.to_arrays())
+
+    for p in [r"\w\d", r"\d+", r"[a-z]+", "é", r"\b\w{4,}\b", r"a*", r"q", r"(\w+) (\w+)", r"l+|o"] + corpus.random_patterns(31, 25):
+        want = [c.to_list() for c in ref.findall(p)]
+        got = [lst(c) for c in dev.findall(p)]
+        assert got == want, ("findall", p)
+        wr = [r.to_list() for r in ref.findall_record(p)]
+        gr = [lst(r) for r in dev.findall_record(p)]
+        assert gr == wr, ("findall_record", p)
+    for p in [r"(\w+) (\w+)", r"(\w)(\d)?", r"(x*)(y)", r"(a)|(x)", r"(\d+):(\d+)", r"([a-z])([a-z])([a-z])", r"(é)", r"\b(\w{4,})\b", r"(a(b)?)+"]:
+        want = [c.to_list() for c in ref.extract(p)]
+        got = [lst(c) for c in dev.extract(p)]
+        assert got == want, ("extract", p)
+        wr = [r.to_list() for r in ref.extract_record(p)]
+        gr = [lst(r) for r in dev.extract_record(p)]
+        assert gr == wr, ("extract_record", p)
+    assert dev.extract(r"\d+") == []  # no capture groups -> no columns (extract.cu:96-100)
