@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "regex_vm.cuh"
 #include "regex_bits.h"
+#include "chain_spans.cuh"
 #include <cub/cub.cuh>
 #include <list>
 #include <map>
@@ -110,6 +111,18 @@ static bool pure_literal(const rx::Program& p, std::string& lit)
         id = in.next;
     }
     return false;
+}
+
+static int cap_tier(int ninsts);
+static const bits::ChainDev* span_plan(Compiled& c)
+{
+    if (g_forced_tier == 1) return nullptr;
+    if (!c.plans_built) {
+        c.plan_contains = bits::lower(c.prog, false, host_unicode_flags());
+        c.plan_match = bits::lower(c.prog, true, host_unicode_flags());
+        c.plans_built = true;
+    }
+    return c.plan_contains ? bits::span_chain(*c.plan_contains) : nullptr;
 }
 
 static int cap_tier(int ninsts)
@@ -253,6 +266,44 @@ k_vm_replace_multi(ColView col, MultiProgs progs, const uint8_t* __restrict__ uf
     }
 }
 
+
+
+// ---- span fast path for last-loop chains (chain_spans.cuh): thread-per-row scalar scan, no NFA lists -------------------
+__global__ void __launch_bounds__(256)
+k_chain_count(ColView col, const __grid_constant__ bits::ChainDev cd, const uint8_t* __restrict__ uflags, int32_t* __restrict__ out,
+              unsigned long long* __restrict__ total, int* __restrict__ nul_seen)
+{
+    for (int base = blockIdx.x * blockDim.x; base < col.n; base += gridDim.x * blockDim.x) {
+        int i = base + threadIdx.x;
+        int found = 0;
+        if (i < col.n) {
+            if (col.valid(i)) {
+                const uint8_t* s = (const uint8_t*)col.chars + col.offsets[i];
+                const int n = col.offsets[i + 1] - col.offsets[i];
+                if (spans::has_nul(s, n)) *nul_seen = 1;
+                else found = spans::row_count(cd, s, n, uflags);
+            }
+            out[i] = found;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, found != 0);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(total, (unsigned long long)__popc(m));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_chain_replace(ColView col, const __grid_constant__ bits::ChainDev cd, const uint8_t* __restrict__ uflags, const char* __restrict__ repl,
+                int repl_len, int maxrepl, int32_t* __restrict__ out_len, const int32_t* __restrict__ out_off, char* __restrict__ out_chars,
+                int* __restrict__ nul_seen)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < col.n; i += gridDim.x * blockDim.x) {
+        if (!col.valid(i)) { if (!out_chars) out_len[i] = 0; continue; }
+        const uint8_t* s = (const uint8_t*)col.chars + col.offsets[i];
+        int n = col.offsets[i + 1] - col.offsets[i];
+        if (!out_chars && spans::has_nul(s, n)) { *nul_seen = 1; out_len[i] = 0; continue; }
+        int total = spans::row_replace(cd, s, n, uflags, repl, repl_len, maxrepl, out_chars ? out_chars + out_off[i] : nullptr);
+        if (!out_chars) out_len[i] = total;
+    }
+}
 
 // ---- findall / extract (capture-span callers, reference findall.cu:36-98, extract.cu:36-68) ---------------------------
 // walks the non-overlapping matches of a row exactly like count_re does and calls f(k, begin, end)
@@ -533,6 +584,21 @@ int custr_count_re(const custr_column* col, const char* pattern, int32_t* result
             ResultBuf<int32_t> out(results, n, devmem);
             Scratch<unsigned long long> total(1);
             CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
+            if (const bits::ChainDev* cd = span_plan(*c)) {  // last-loop chain: scalar leftmost-longest scan is exact
+                Scratch<int> nul_seen(1);
+                CUSTR_CUDA(cudaMemsetAsync(nul_seen.get(), 0, sizeof(int), g_stream));
+                LAUNCH(k_chain_count, vm_grid(n) * 2, 256, 0, view_of(col), *cd, device_unicode_flags(), out.dev, total.get(), nul_seen.get());
+                int matches = (int)read_counter(total.get());
+                int h_nul = 0;
+                CUSTR_CUDA(cudaMemcpyAsync(&h_nul, nul_seen.get(), sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+                CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+                if (!h_nul) {
+                    g_last_tier = "chainspan";
+                    out.finish();
+                    return matches;
+                }
+                CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));  // a row holds a NUL byte: redo with the exact VM
+            }
             DISPATCH_CAP(cap, k_vm_count, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
                          (int)c->image.size(), device_unicode_flags(), out.dev, total.get());
             g_last_tier = "pikevm";
@@ -662,6 +728,27 @@ custr_column* custr_replace_re(const custr_column* col, const char* pattern, con
             BufPtr d_repl = upload(repl, repl_len ? repl_len : 1);
             Scratch<int32_t> lens((size_t)n + 1);
             CUSTR_CUDA(cudaMemsetAsync(lens.get() + n, 0, sizeof(int32_t), g_stream));
+            const bits::ChainDev* cd = span_plan(*c);
+            Scratch<int> nul_seen(1);
+            int h_nul = 0;
+            if (cd) {  // last-loop chain: scalar leftmost-longest scan is exact (rows holding NUL: whole call goes to the VM)
+                CUSTR_CUDA(cudaMemsetAsync(nul_seen.get(), 0, sizeof(int), g_stream));
+                LAUNCH(k_chain_replace, vm_grid(n) * 2, 256, 0, view_of(col), *cd, device_unicode_flags(), (const char*)d_repl->ptr, repl_len,
+                       maxrepl, lens.get(), (const int32_t*)nullptr, (char*)nullptr, nul_seen.get());
+                CUSTR_CUDA(cudaMemcpyAsync(&h_nul, nul_seen.get(), sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+                CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            }
+            if (cd && !h_nul) {
+                BufPtr off2;
+                int64_t total2 = 0;
+                finish_replace(col, lens, off2, total2);
+                BufPtr chars2 = dev_alloc((size_t)total2);
+                LAUNCH(k_chain_replace, vm_grid(n) * 2, 256, 0, view_of(col), *cd, device_unicode_flags(), (const char*)d_repl->ptr, repl_len,
+                       maxrepl, (int32_t*)nullptr, (const int32_t*)off2->ptr, (char*)chars2->ptr, nul_seen.get());
+                g_last_tier = "chainspan";
+                CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+                return make_column(chars2, off2, copy_validity(col), n, col->nulls, total2);
+            }
             DISPATCH_CAP(cap, k_vm_replace, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
                          (int)c->image.size(), device_unicode_flags(), (const char*)d_repl->ptr, repl_len, maxrepl, lens.get(),
                          (const int32_t*)nullptr, (char*)nullptr);

@@ -24,6 +24,7 @@ namespace bits {
 struct Plan {
     PlanDev dev;
     bool is_chain = false;
+    bool span_ok = false;
     ChainDev chain;
     std::string text;
 };

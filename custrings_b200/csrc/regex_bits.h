@@ -25,6 +25,12 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
 extern bool g_force_generic;
 extern bool g_chain32;
 
+// Non-null when the plan is a linear chain whose only loop is its last step: for those patterns the match SPAN the Pike VM
+// reports (leftmost start, then thread priority) is "leftmost start, longest end that satisfies the trailing assertion",
+// which chain_spans.cuh computes with a scalar per-row scan (count_re / replace_re / findall fast path).
+struct ChainDev;
+const ChainDev* span_chain(const Plan& plan);
+
 // Plain host executor of a plan (tests/sim only): out[i] for every row, dirty[i] = row needs the exact path.
 void reference_execute(const Plan& plan, const char* chars, const int32_t* offsets, const uint8_t* validity, int32_t n,
                        uint8_t* out, uint8_t* dirty);

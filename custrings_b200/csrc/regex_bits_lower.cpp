@@ -20,6 +20,7 @@ namespace bits {
 struct Plan {
     PlanDev dev;
     bool is_chain = false;
+    bool span_ok = false;  // chain whose only loop is a GREEDY loop on the last step (see span_chain)
     ChainDev chain;
     std::string text;
 };
@@ -317,6 +318,8 @@ std::shared_ptr<Plan> lower(const rx::Program& prog, bool anchored, const uint8_
                 // exact 2-byte-character bitmap (covers Latin-1 .. Arabic): decided once here instead of per character
                 const rx::Inst& src_inst = prog.insts[order[0]];
                 (void)src_inst;
+                for (uint32_t ch = 1; ch < 128; ++ch)
+                    if (class_has(src, ch)) cc.ascii[ch >> 5] |= 1u << (ch & 31);
                 for (uint32_t cp = 0x80; cp < 0x800; ++cp) {
                     const uint32_t packed = ((0xC0u | (cp >> 6)) << 8) | (0x80u | (cp & 0x3Fu));
                     bool in = false;
@@ -333,6 +336,16 @@ std::shared_ptr<Plan> lower(const rx::Program& prog, bool anchored, const uint8_
             for (uint32_t cp = 0x80; cp < 0x800; ++cp)
                 if ((uflags[cp] & 15) != 0) C.na2_alnum[cp >> 5] |= 1u << (cp & 31);
             plan->is_chain = true;
+            // span fast path: no loop before the last step, and the last step's loop (if any) must be greedy, i.e. the
+            // SPLIT that follows the instruction tries the loop body first (regcomp PLUS, not PLUS_LAZY)
+            bool span_ok = true;
+            for (int s2 = 0; s2 + 1 < P.nsteps; ++s2) span_ok = span_ok && !P.steps[s2].self_loop;
+            if (span_ok && P.steps[P.nsteps - 1].self_loop) {
+                const int last = order[P.nsteps - 1];
+                const rx::Inst& nx = prog.insts[prog.insts[last].next];
+                span_ok = nx.op == rx::OP_SPLIT && nx.other == last;
+            }
+            plan->span_ok = span_ok;
         }
     }
     plan->text = describe(*plan);
@@ -374,6 +387,9 @@ std::string describe(const Plan& plan)
 
 const PlanDev& device_plan(const Plan& plan) { return plan.dev; }
 const ChainDev* device_chain(const Plan& plan) { return plan.is_chain ? &plan.chain : nullptr; }
+// chain whose only loop (if any) is a greedy loop on its last step: leftmost start + longest admissible end == the Pike
+// VM's span
+const ChainDev* span_chain(const Plan& plan) { return plan.is_chain && plan.span_ok ? &plan.chain : nullptr; }
 
 // ---- plain host executor (tests/sim only) ------------------------------------------------------------------------
 void reference_execute(const Plan& plan, const char* chars, const int32_t* offsets, const uint8_t* validity, int32_t n,

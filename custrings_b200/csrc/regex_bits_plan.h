@@ -60,6 +60,7 @@ struct ChainClassD {
     uint32_t na_inline, na_builtins, na_nranges;
     uint32_t na_ranges[8];
     uint32_t na2[64];    // membership bitmap of the 2-byte characters U+0080..U+07FF (bit = code point), exact
+    uint32_t ascii[4];   // exact ASCII membership bitmap (used by the per-row span matcher, chain_spans.cuh)
 };
 struct ChainDev {
     uint32_t nsteps, nclasses, anchored, end_mask;

@@ -5,6 +5,7 @@
 #include "../../custrings_b200/csrc/regex_vm.cuh"
 #include "../../custrings_b200/csrc/rowops.cuh"
 #include "../../custrings_b200/csrc/regex_bits_core.cuh"
+#include "../../custrings_b200/csrc/chain_spans.cuh"
 #include <vector>
 #include <string>
 
@@ -102,6 +103,46 @@ int sim_bits_bool(const char* chars, const int32_t* off, const uint8_t* validity
     }
     delete lists;
     return total;
+}
+
+// span fast path (chain_spans.cuh) on the host: count_re.  returns -1 when the pattern is not a last-loop chain
+int sim_chain_count(const char* chars, const int32_t* off, const uint8_t* validity, int n, const char* pattern, int32_t* out)
+{
+    Prog p(pattern);
+    std::shared_ptr<bits::Plan> plan = bits::lower(p.prog, false, k_flags);
+    const bits::ChainDev* cd = plan ? bits::span_chain(*plan) : nullptr;
+    if (!cd) return -1;
+    ColView col{chars, off, validity, 0, n};
+    for (int i = 0; i < n; ++i)
+        if (col.valid(i) && spans::has_nul((const uint8_t*)chars + off[i], off[i + 1] - off[i])) return -1;  // product falls back to the VM
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        out[i] = col.valid(i) ? spans::row_count(*cd, (const uint8_t*)chars + off[i], off[i + 1] - off[i], k_flags) : 0;
+        total += out[i] != 0;
+    }
+    return total;
+}
+
+long sim_chain_replace(const char* chars, const int32_t* off, const uint8_t* validity, int n, const char* pattern, const char* repl,
+                       int maxrepl, int32_t* out_off, char* out_chars)
+{
+    Prog p(pattern);
+    std::shared_ptr<bits::Plan> plan = bits::lower(p.prog, false, k_flags);
+    const bits::ChainDev* cd = plan ? bits::span_chain(*plan) : nullptr;
+    if (!cd) return -1;
+    ColView col{chars, off, validity, 0, n};
+    for (int i = 0; i < n; ++i)
+        if (col.valid(i) && spans::has_nul((const uint8_t*)chars + off[i], off[i + 1] - off[i])) return -1;
+    int rl = (int)strlen(repl);
+    long run = 0;
+    for (int i = 0; i < n; ++i) {
+        out_off[i] = (int32_t)run;
+        if (col.valid(i))
+            run += spans::row_replace(*cd, (const uint8_t*)chars + off[i], off[i + 1] - off[i], k_flags, repl, rl, maxrepl,
+                                      out_chars ? out_chars + run : nullptr);
+    }
+    out_off[n] = (int32_t)run;
+    return run;
 }
 
 // out_off[n+1] always written; out_chars written when non-null (second call)

@@ -16,6 +16,7 @@ def lib():
         _lib = C.CDLL(build())
         _lib.sim_replace_re.restype = C.c_long
         _lib.sim_replace_re_multi.restype = C.c_long
+        _lib.sim_chain_replace.restype = C.c_long
     return _lib
 
 
@@ -55,6 +56,29 @@ def bits_bool(chars, offsets, validity, pattern, anchored):
     if rc < 0:
         return None, -1
     return out[:n].astype(bool), rc
+
+
+def chain_count(chars, offsets, validity, pattern):
+    """span fast path; (None, -1) when the pattern is not a last-loop chain"""
+    chars, offsets, validity = _cols(chars, offsets, validity)
+    n = len(offsets) - 1
+    out = np.zeros(max(n, 1), np.int32)
+    rc = lib().sim_chain_count(_p(chars), _p(offsets), _p(validity), n, pattern.encode() if isinstance(pattern, str) else pattern, _p(out))
+    return (None, -1) if rc < 0 else (out[:n], rc)
+
+
+def chain_replace(chars, offsets, validity, pattern, repl, maxrepl=-1):
+    chars, offsets, validity = _cols(chars, offsets, validity)
+    n = len(offsets) - 1
+    pat = pattern.encode() if isinstance(pattern, str) else pattern
+    rp = repl.encode() if isinstance(repl, str) else repl
+    ooff = np.zeros(n + 1, np.int32)
+    total = lib().sim_chain_replace(_p(chars), _p(offsets), _p(validity), n, pat, rp, maxrepl, _p(ooff), None)
+    if total < 0:
+        return None
+    ochars = np.zeros(max(total, 1), np.uint8)
+    lib().sim_chain_replace(_p(chars), _p(offsets), _p(validity), n, pat, rp, maxrepl, _p(ooff), _p(ochars))
+    return ochars[:total], ooff
 
 
 def count(chars, offsets, validity, pattern):

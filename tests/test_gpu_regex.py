@@ -101,3 +101,17 @@ def test_findall_extract_capture_spans(cols, oracle):
         gr = [lst(r) for r in dev.extract_record(p)]
         assert gr == wr, ("extract_record", p)
     assert dev.extract(r"\d+") == []  # no capture groups -> no columns (extract.cu:96-100)
+
+
+def test_rows_with_nul_bytes_fall_back_exactly(oracle):
+    from custrings_b200 import nvstrings
+    from custrings_b200._lib import lib
+    strs = ["a\x00bcd efgh", "abcd\x00", "\x00abcd", "ab\x00", "\x00", "x\x00y\x00z abcd", "plain words here", None]
+    dev, ref = nvstrings.to_device(strs), oracle.RefStrings.from_list(strs)
+    for p in [r"c", r"\w+", r"\b\w{4,}\b", r"a\w+", r"[a-z]+", r"^a", r"d$", r"\W"]:
+        assert [False if x is None else x for x in dev.contains(p)] == ref.contains_re(p)[0].tolist(), p
+        assert [0 if x is None else x for x in dev.count(p)] == ref.count_re(p)[0].tolist(), p
+        assert lib().custr_last_regex_tier() == b"pikevm"
+        assert oracle.unpack(*dev.replace(p, "#").to_arrays()) == ref.replace_re(p, "#").to_list(), p
+    clean = nvstrings.to_device(["abcd efgh", "x1 y22 z333"])
+    assert clean.count(r"\d+") == [0, 3] and lib().custr_last_regex_tier() == b"chainspan"

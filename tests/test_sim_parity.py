@@ -86,3 +86,26 @@ def test_compiler_quirks():
     d = simlib.describe(r"(?:ab){2}")
     assert d.count("CHAR 0x61") == 2 and "LBRA" not in d
     assert simlib.describe(r"(ab){2}").count("LBRA") == 2  # capture groups are duplicated by {n}
+
+
+def test_chain_span_fast_path_equals_reference(data, oracle):
+    """count_re / replace_re through the scalar leftmost-longest chain matcher (chain_spans.cuh) for every eligible
+    pattern (last-loop greedy chains)"""
+    from tests import simlib
+    strs, chars, offsets, validity, ref = data
+    eligible = 0
+    extra = [r"\b\w{4,}\b", r"\d+", r"[a-z]+\b", r"^\w+", r"\w+$", r"é+", r"\s+", r"a\w+", r"\Bb+", r"\d{2}:", r"[^a]+", r".+", r"x\b", r"_+\b"]
+    for p in SAFE_PATTERNS + extra + corpus.random_patterns(24, 200):
+        got, cnt = simlib.chain_count(chars, offsets, validity, p)
+        if got is None:
+            continue
+        eligible += 1
+        want, wcnt = ref.count_re(p)
+        assert np.array_equal(want, got) and wcnt == cnt, p
+        for repl, mx in (("<>", -1), ("", 2)):
+            w = ref.replace_re(p, repl, mx).to_arrays()
+            g = simlib.chain_replace(chars, offsets, validity, p, repl, mx)
+            assert np.array_equal(w[0], g[0]) and np.array_equal(w[1], g[1]), (p, repl, mx)
+    assert eligible > 40
+    assert simlib.chain_count(chars, offsets, validity, r"[^\w]+?")[0] is None   # lazy loop: not eligible
+    assert simlib.chain_count(chars, offsets, validity, r"\d+:\d+")[0] is None   # loop before the last step
