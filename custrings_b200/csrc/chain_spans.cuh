@@ -47,13 +47,11 @@ CUSTR_HD bool class_has_char(const ChainClassD& cc, uint32_t ch, const uint8_t* 
     return in;
 }
 
-// zero-width assertions at byte offset q of row s[0..n) (q == n: end of row)
-CUSTR_HD bool assert_at(uint32_t mask, const uint8_t* s, int n, int q, bool after, const uint8_t* uflags)
+// zero-width assertions between `prev` (character before byte offset q, 0 at the start of the row) and `cur` (character
+// at q, 0 at the end of the row); the same predicate serves in front of the chain and before END (regexec.inl:308-352)
+CUSTR_HD bool assert_chars(uint32_t mask, uint32_t prev, uint32_t cur, int q, int n, const uint8_t* uflags)
 {
     if (!mask) return true;
-    int w;
-    const uint32_t cur = q < n ? utf8_packed(s + q, s + n, w) : 0u;
-    const uint32_t prev = q > 0 ? utf8_packed_before(s + q, s) : 0u;
     if (mask & (bits::AS_BOW | bits::AS_NBOW)) {
         const bool bow = is_alnum_packed(cur, uflags) != is_alnum_packed(prev, uflags);
         if ((mask & bits::AS_BOW) && !bow) return false;
@@ -63,22 +61,25 @@ CUSTR_HD bool assert_at(uint32_t mask, const uint8_t* s, int n, int q, bool afte
     if ((mask & bits::AS_BOL_A) && q != 0) return false;
     if ((mask & bits::AS_EOL_DOLLAR) && !(q >= n || cur == '\n')) return false;
     if ((mask & bits::AS_EOL_Z) && q < n) return false;
-    (void)after;
     return true;
 }
 
 // leftmost-longest search from byte offset `begin` in s[0..n); requires that only the last step may loop (greedy) and
-// that the row holds no NUL byte
+// that the row holds no NUL byte.  Every character is decoded once per visit; the previous character is carried along.
 CUSTR_HD int chain_find(const ChainDev& cd, const uint8_t* __restrict__ s, int n, int begin, const uint8_t* __restrict__ uflags,
                         int& mbeg, int& mend)
 {
     const int ns = (int)cd.nsteps;
     const bool loop_last = cd.steps[ns - 1].loop != 0;
+    const uint32_t before = cd.steps[0].before, after = cd.end_mask;
+    const ChainClassD& first = cd.classes[cd.steps[0].cls];
+    uint32_t prev = (begin > 0 && begin <= n) ? utf8_packed_before(s + begin, s) : 0u;
     for (int pos = begin; pos < n;) {
         int w0;
         const uint32_t c0 = utf8_packed(s + pos, s + n, w0);
-        if (class_has_char(cd.classes[cd.steps[0].cls], c0, uflags) && assert_at(cd.steps[0].before, s, n, pos, false, uflags)) {
+        if (class_has_char(first, c0, uflags) && assert_chars(before, prev, c0, pos, n, uflags)) {
             int q = pos + w0;
+            uint32_t last = c0;  // last consumed character
             bool ok = true;
             for (int st = 1; st < ns; ++st) {
                 if (q >= n) { ok = false; break; }
@@ -86,23 +87,26 @@ CUSTR_HD int chain_find(const ChainDev& cd, const uint8_t* __restrict__ s, int n
                 const uint32_t c = utf8_packed(s + q, s + n, w);
                 if (!class_has_char(cd.classes[cd.steps[st].cls], c, uflags)) { ok = false; break; }
                 q += w;
+                last = c;
             }
             if (ok) {
-                int best = assert_at(cd.end_mask, s, n, q, true, uflags) ? q : -1;
+                int w = 1;
+                uint32_t nxt = q < n ? utf8_packed(s + q, s + n, w) : 0u;
+                int best = assert_chars(after, last, nxt, q, n, uflags) ? q : -1;
                 if (loop_last) {
                     const ChainClassD& lc = cd.classes[cd.steps[ns - 1].cls];
-                    while (q < n) {
-                        int w;
-                        const uint32_t c = utf8_packed(s + q, s + n, w);
-                        if (!class_has_char(lc, c, uflags)) break;
+                    while (q < n && class_has_char(lc, nxt, uflags)) {
                         q += w;
-                        if (assert_at(cd.end_mask, s, n, q, true, uflags)) best = q;
+                        last = nxt;
+                        nxt = q < n ? utf8_packed(s + q, s + n, w) : 0u;
+                        if (assert_chars(after, last, nxt, q, n, uflags)) best = q;
                     }
                 }
                 if (best >= 0) { mbeg = pos; mend = best; return 1; }
             }
         }
         pos += w0;
+        prev = c0;
     }
     return 0;
 }
