@@ -567,6 +567,8 @@ custr_column* custr_slice_rows(const custr_column* col, int32_t first, int32_t l
         [&]() -> custr_column* {
             if (!col || first < 0 || last < first || last > col->n) throw ArgError{fail(CUSTR_ERR_ARG, "slice_rows: bad range")};
             custr_column* v = new custr_column(*col);  // shares the buffers
+            v->item_bounds = nullptr;                  // derived indexes belong to the parent's row range
+            v->item_bounds_count = 0;
             v->n = last - first;
             v->offsets = col->offsets + first;
             v->vbit0 = col->vbit0 + first;

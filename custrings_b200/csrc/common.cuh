@@ -75,6 +75,10 @@ struct custr_column {
     int32_t first_off = 0;              // offsets[0]
     int64_t nbytes = 0;                 // offsets[n] - offsets[0]
     custr::BufPtr chars_buf, offsets_buf, validity_buf;  // owners (shared between views); empty when adopted
+    // derived, pattern-independent index built lazily by the bitstream regex tier and kept with the (immutable) column:
+    // first row of every 32 KiB work item (4 bytes per 32 KiB of chars)
+    mutable custr::BufPtr item_bounds;
+    mutable int32_t item_bounds_count = 0;
 };
 
 struct custr_category {

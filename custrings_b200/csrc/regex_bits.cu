@@ -52,6 +52,7 @@ struct Args {
     int32_t* dirty_rows;
     unsigned int* dirty_count;
     unsigned int* item_counter;  // dynamic work distribution (k_chain64)
+    const int32_t* item_bounds;  // item_bounds[t] = first row whose start offset is >= first + t*ITEM_BYTES (k_chain64)
     const uint8_t* prog_img;  // compiled program image (exact class tests for non-ASCII characters)
     const uint8_t* uflags;
 };
@@ -412,6 +413,25 @@ k_bitstream(const __grid_constant__ PlanDev plan, const Args A)
 }
 
 
+// item_bounds[t] = first row r with offsets[r] >= first + t*ITEM_BYTES, for t = 0..nitems (bounds[nitems] = n): one coalesced
+// pass over the offsets instead of two dependent binary searches at the head of every work item
+__global__ void k_item_bounds(const int32_t* __restrict__ offsets, int n, int first, int nitems, int32_t* __restrict__ bounds)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // row index 0..n (offsets has n+1 entries)
+    if (i > n) return;
+    const long long cur = (long long)offsets[i] - first;
+    const long long prev = i == 0 ? -1 : (long long)offsets[i - 1] - first;
+    // boundaries t with prev < t*ITEM <= cur get row i
+    long long t_lo = prev < 0 ? 0 : prev / ITEM_BYTES + 1;
+    long long t_hi = cur / ITEM_BYTES;
+    if (t_hi > nitems) t_hi = nitems;
+    for (long long t = t_lo; t <= t_hi; ++t) bounds[t] = i;
+    if (i == n) {  // boundaries past the last offset (only bounds[nitems] when the span is not a multiple of the item size)
+        for (long long t = t_hi + 1; t <= nitems; ++t) bounds[t] = n;
+        bounds[nitems] = n;
+    }
+}
+
 #include "regex_chain.cuh"
 #include "regex_chain64.cuh"
 
@@ -420,6 +440,7 @@ const PlanDev& device_plan(const Plan& plan);
 bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, const uint8_t* uflags, uint8_t* out,
          unsigned long long* total, int32_t** dirty_rows, unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count)
 {
+
     const int32_t n = col->n;
     if (((uintptr_t)col->chars & 15) != 0) return false;  // vector loads need a 16-byte aligned base
     CUSTR_CUDA(cudaMemsetAsync(out, 0, (size_t)n, g_stream));
@@ -441,6 +462,7 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     a.dirty_rows = *dirty_rows;
     a.dirty_count = *dirty_count;
     a.item_counter = (unsigned int*)keep_count->ptr + 1;
+    a.item_bounds = nullptr;
     a.prog_img = prog_img;
     a.uflags = uflags;
     int blocks = (a.nitems + WARPS - 1) / WARPS;
@@ -449,6 +471,12 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     if (plan.is_chain && !g_force_generic) {
         if (g_chain32) launch_chain(plan.chain, a, blocks);   // 1024-byte windows, 32-bit streams (A/B)
         else {  // 2048-byte windows, 64-bit streams, cp.async ring; grid = resident set (3 CTAs per SM), dynamic items
+            if (!col->item_bounds || col->item_bounds_count != a.nitems) {  // once per column (it is immutable)
+                col->item_bounds = dev_alloc(sizeof(int32_t) * (size_t)(a.nitems + 2));
+                col->item_bounds_count = a.nitems;
+                LAUNCH(k_item_bounds, (n + 1 + 255) / 256, 256, 0, a.offsets, n, a.first, a.nitems, (int32_t*)col->item_bounds->ptr);
+            }
+            a.item_bounds = (const int32_t*)col->item_bounds->ptr;
             int resident = num_sms() * 3;
             launch_chain64(plan.chain, a, blocks < resident ? blocks : resident);
         }

@@ -272,8 +272,8 @@ k_chain64(const __grid_constant__ ChainDev cd, const Args A)
         item = __shfl_sync(FULL, item, 0);
         if (item >= A.nitems) break;
         const int lo_byte = A.first + item * ITEM_BYTES;
-        const int ra = item == 0 ? 0 : warp_lower_bound(A.offsets, A.n, lo_byte);
-        const int rb = item == A.nitems - 1 ? A.n : warp_lower_bound(A.offsets, A.n, lo_byte + ITEM_BYTES);
+        (void)lo_byte;
+        const int ra = __ldg(A.item_bounds + item), rb = __ldg(A.item_bounds + item + 1);  // precomputed by k_item_bounds
         if (ra >= rb) continue;
         const int byte_a = __ldg(A.offsets + ra), byte_b = __ldg(A.offsets + rb);
         if (byte_a >= byte_b) continue;  // only empty rows: results stay 0 (pre-cleared)
