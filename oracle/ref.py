@@ -54,6 +54,7 @@ def lib():
         L.ref_partition.argtypes = [vp, cp, ci, vp]
         L.ref_regex_columns.argtypes = [vp, cp, ci, vp, ci]
         L.ref_regex_records.argtypes = [vp, cp, ci, vp]
+        L.ref_regex_dump.argtypes = [cp, vp, ci]
         L.ref_tokenize.argtypes = [vp, cp]
         L.ref_tokenize_multi.argtypes = [vp, vp]
         L.ref_token_count.argtypes = [vp, cp, vp]

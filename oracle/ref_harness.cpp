@@ -13,6 +13,9 @@
 #include <NVStrings.h>
 #include <NVCategory.h>
 #include <NVText.h>
+#include "regex/regcomp.h"   // reference's host regex compiler (cpp/src/regex/regcomp.h), for ref_regex_dump
+
+char32_t* to_char32(const char* ca);  // cpp/src/strings/NVStringsImpl.cu:49
 
 static thread_local std::string g_err;
 #define GUARD(expr, fail)                      \
@@ -146,6 +149,40 @@ int ref_regex_records(void* h, const char* pat, int kind, void** out)
     GUARD(rc = kind == 0 ? s->findall_record(pat, res) : s->extract_record(pat, res), -100);
     for (size_t i = 0; i < res.size(); ++i) out[i] = res[i];
     return rc;
+}
+
+// Dump of the reference's compiled program for `pattern` as int32 words:
+//   [ninsts, start_inst, ngroups, nstarts, nclasses, then ninsts x (type, u1, u2), then nstarts start ids,
+//    then per class: builtins, count, count x char]          (regcomp.h:51-103)
+// Returns the number of words written (or needed if cap is too small).
+int ref_regex_dump(const char* pattern, int* out, int cap)
+{
+    const char32_t* p32 = to_char32(pattern);
+    Reprog* prog = Reprog::create_from(p32);
+    delete p32;
+    std::vector<int> w;
+    w.push_back(prog->inst_count());
+    w.push_back(prog->get_start_inst());
+    w.push_back(prog->groups_count());
+    int nstarts = prog->starts_count() - 1;  // last entry is the -1 terminator
+    w.push_back(nstarts);
+    w.push_back(prog->classes_count());
+    for (int i = 0; i < prog->inst_count(); ++i) {
+        Reinst& in = prog->inst_at(i);
+        w.push_back(in.type);
+        w.push_back(in.u1.right_id);
+        w.push_back(in.u2.left_id);
+    }
+    for (int i = 0; i < nstarts; ++i) w.push_back(prog->starts_data()[i]);
+    for (int k = 0; k < prog->classes_count(); ++k) {
+        Reclass& c = prog->class_at(k);
+        w.push_back(c.builtins);
+        w.push_back((int)c.chrs.size());
+        for (char32_t ch : c.chrs) w.push_back((int)ch);
+    }
+    delete prog;
+    for (size_t i = 0; i < w.size() && (int)i < cap; ++i) out[i] = w[i];
+    return (int)w.size();
 }
 
 void* ref_tokenize(void* h, const char* delim) { GUARD(return NVText::tokenize(*(NVStrings*)h, delim), nullptr); }

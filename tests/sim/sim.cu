@@ -191,4 +191,39 @@ long sim_replace_re_multi(const char* chars, const int32_t* off, const uint8_t* 
     return run;
 }
 
+// this repo's compiled program in the reference's vocabulary (instruction type codes of regcomp.h:25-40), same word
+// layout as oracle's ref_regex_dump so the two compilers can be compared graph against graph
+int sim_program_dump(const char* pattern, int* out, int cap)
+{
+    rx::Program prog = rx::compile(pattern);
+    auto type_of = [](int op) {
+        switch (op) {
+            case rx::OP_CHAR: return 0177;  case rx::OP_ANY: return 0300;   case rx::OP_ANYNL: return 0301;
+            case rx::OP_CLASS: return 0305; case rx::OP_NCLASS: return 0306; case rx::OP_END: return 0377;
+            case rx::OP_LBRA: return 0202;  case rx::OP_RBRA: return 0201;  case rx::OP_BOL: return 0303;
+            case rx::OP_EOL: return 0304;   case rx::OP_BOW: return 0307;   case rx::OP_NBOW: return 0310;
+            case rx::OP_SPLIT: return 0204; default: return -op;
+        }
+    };
+    std::vector<int> w;
+    w.push_back((int)prog.insts.size());
+    w.push_back(prog.start_inst);
+    w.push_back(prog.ngroups);
+    w.push_back((int)prog.starts.size());
+    w.push_back((int)prog.classes.size());
+    for (const rx::Inst& in : prog.insts) {
+        w.push_back(type_of(in.op));
+        w.push_back(in.op == rx::OP_SPLIT ? in.other : (int)in.arg);
+        w.push_back(in.next);
+    }
+    for (int s : prog.starts) w.push_back(s);
+    for (const rx::Class& c : prog.classes) {
+        w.push_back(c.builtins);
+        w.push_back((int)c.ranges.size());
+        for (uint32_t r : c.ranges) w.push_back((int)r);
+    }
+    for (size_t i = 0; i < w.size() && (int)i < cap; ++i) out[i] = w[i];
+    return (int)w.size();
+}
+
 }  // extern "C"

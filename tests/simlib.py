@@ -112,3 +112,30 @@ def replace_re_multi(chars, offsets, validity, patterns, rchars, roffsets, rvali
     ochars = np.zeros(max(total, 1), np.uint8)
     lib().sim_replace_re_multi(*args, _p(ooff), _p(ochars))
     return ochars[:total], ooff
+
+
+def available():
+    try:
+        lib()
+        return True
+    except Exception:
+        return False
+
+
+def program_dump(pattern):
+    """this repo's compiled program in the layout of oracle.restate.reference_program"""
+    out = np.zeros(1 << 16, np.int32)
+    n = lib().sim_program_dump(pattern.encode() if isinstance(pattern, str) else pattern, _p(out), len(out))
+    w = out[:n].tolist()
+    ninsts, start, ngroups, nstarts, nclasses = w[:5]
+    p = 5
+    insts = [tuple(w[p + 3 * i: p + 3 * i + 3]) for i in range(ninsts)]
+    p += 3 * ninsts
+    starts = w[p:p + nstarts]
+    p += nstarts
+    classes = []
+    for _ in range(nclasses):
+        builtins, cnt = w[p], w[p + 1]
+        classes.append((builtins, [x & 0xFFFFFFFF for x in w[p + 2:p + 2 + cnt]]))
+        p += 2 + cnt
+    return {"insts": insts, "start": start, "groups": ngroups, "starts": starts, "classes": classes}
