@@ -469,8 +469,11 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     int cap = num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (plan.is_chain && !g_force_generic) {
+#ifndef CUSTR_EXPERIMENT_ONLY_4_1
         if (g_chain32) launch_chain(plan.chain, a, blocks);   // 1024-byte windows, 32-bit streams (A/B)
-        else {  // 2048-byte windows, 64-bit streams, cp.async ring; grid = resident set (3 CTAs per SM), dynamic items
+        else
+#endif
+        {  // 2048-byte windows, 64-bit streams, cp.async ring; grid = resident set (3 CTAs per SM), dynamic items
             if (!col->item_bounds || col->item_bounds_count != a.nitems) {  // once per column (it is immutable)
                 col->item_bounds = dev_alloc(sizeof(int32_t) * (size_t)(a.nitems + 2));
                 col->item_bounds_count = a.nitems;
@@ -482,7 +485,9 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
         }
         return true;
     }
+#ifndef CUSTR_EXPERIMENT_ONLY_4_1
     LAUNCH(k_bitstream, blocks, THREADS, 0, device_plan(plan), a);
+#endif
     return true;
 }
 

@@ -371,6 +371,7 @@ k_chain(const __grid_constant__ ChainDev cd, const Args A)
     if (lane == 0 && my_matches) atomicAdd(A.total, my_matches);
 }
 
+#ifndef CUSTR_EXPERIMENT_ONLY_4_1
 template <int NS>
 static void launch_chain_ns(const ChainDev& cd, const Args& a, int blocks)
 {
@@ -395,3 +396,4 @@ static void launch_chain(const ChainDev& cd, const Args& a, int blocks)
     default: launch_chain_ns<8>(cd, a, blocks); break;
     }
 }
+#endif

@@ -106,20 +106,66 @@ __device__ __forceinline__ u64 sel_class64(const u64 (&c)[NCLS], uint32_t k)
     return v;
 }
 
-__device__ __forceinline__ int ring_chunk_offset(uint32_t lane, int k);
+// Per-warp shared block.  It is addressed through ONE 32-bit shared-window address kept in a register (made opaque to
+// the compiler, which otherwise re-derives it from %tid / the CTA's shared base at every use: ~35 instructions per
+// window) plus immediates, with explicit ld/st.shared.
+struct __align__(64) WarpSm64 {
+    char ring[RING_STAGES][WIN64];
+    uint32_t rs[64], f[64], d[64];
+};
+constexpr uint32_t SM_RS = RING_STAGES * WIN64, SM_F = SM_RS + 256, SM_D = SM_F + 256;
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ u64 lds64(uint32_t a)
+{
+    uint32_t lo, hi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a) : "memory");
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t lo, uint32_t hi)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(lo), "r"(hi) : "memory");
+}
+__device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// bit `b` (0..2047) of a 64-word stream stored at shared address `a`
+__device__ __forceinline__ uint32_t stream_bit(uint32_t a, int b) { return (lds32(a + 4u * (uint32_t)(b >> 5)) >> (b & 31)) & 1u; }
+
+// Lane L keeps its 4 x 16-byte chunks XOR-swizzled: chunk k sits at 64L + 16 * (k ^ ((L >> 1) & 3)), so the 8 lanes of an
+// LDS.128 phase hit 8 distinct 16-byte bank groups and chunk k's address is (chunk 0's address) ^ 16k.
+__device__ __forceinline__ uint32_t ring_lane_offset(uint32_t lane) { return 64u * lane + 16u * ((lane >> 1) & 3u); }
 
 // Non-ASCII bytes of this lane: decode each character once and give ALL its bytes (inside the lane) its class bits.
-// Bytes are taken from the lane's own staged copy in shared memory; only characters that straddle a lane boundary touch
-// global memory.
+// Bytes are taken from the lane's own staged copy in shared memory (`my0` = shared address of the lane's chunk 0); only
+// characters that straddle a lane boundary touch global memory.
 template <int NCLS>
-__device__ __noinline__ void classify_non_ascii64(const ChainDev& cd, const Args& A, const char* slot, int lane_base, u64 na,
-                                                  u64 (&c)[NCLS], u64& al)
+struct NaClasses {
+    u64 c[NCLS];
+    u64 al;
+};
+template <int NCLS>
+__device__ __noinline__ NaClasses<NCLS> classify_non_ascii64(const ChainDev& cd, const Args& A, uint32_t my0, int lane_base, u64 na,
+                                                             NaClasses<NCLS> r)
 {
     const uint8_t* base = (const uint8_t*)A.chars;
-    const uint32_t lane = lane_id();
     auto byte_at = [&](int pos) -> uint32_t {
         const int rel = pos - lane_base;
-        if ((unsigned)rel < 64u) return (uint8_t)slot[ring_chunk_offset(lane, rel >> 4) + (rel & 15)];
+        if ((unsigned)rel < 64u) return lds8((my0 ^ (uint32_t)(rel & 48)) + (uint32_t)(rel & 15));
         return pos < A.end ? base[pos] : 0u;
     };
     while (na) {
@@ -139,15 +185,16 @@ __device__ __noinline__ void classify_non_ascii64(const ChainDev& cd, const Args
             const uint32_t cp = ((ch >> 2) & 0x7C0u) | (ch & 0x3Fu);
 #pragma unroll
             for (int k = 0; k < NCLS; ++k)
-                if (k < (int)cd.nclasses) c[k] = ((cd.classes[k].na2[cp >> 5] >> (cp & 31)) & 1u) ? (c[k] | bits) : (c[k] & ~bits);
-            al = ((cd.na2_alnum[cp >> 5] >> (cp & 31)) & 1u) ? (al | bits) : (al & ~bits);
+                if (k < (int)cd.nclasses) r.c[k] = ((cd.classes[k].na2[cp >> 5] >> (cp & 31)) & 1u) ? (r.c[k] | bits) : (r.c[k] & ~bits);
+            r.al = ((cd.na2_alnum[cp >> 5] >> (cp & 31)) & 1u) ? (r.al | bits) : (r.al & ~bits);
             continue;
         }
 #pragma unroll
         for (int k = 0; k < NCLS; ++k)
-            if (k < (int)cd.nclasses) c[k] = na_char_matches(cd.classes[k], A, ch) ? (c[k] | bits) : (c[k] & ~bits);
-        al = is_alnum_packed(ch, A.uflags) ? (al | bits) : (al & ~bits);
+            if (k < (int)cd.nclasses) r.c[k] = na_char_matches(cd.classes[k], A, ch) ? (r.c[k] | bits) : (r.c[k] & ~bits);
+        r.al = is_alnum_packed(ch, A.uflags) ? (r.al | bits) : (r.al & ~bits);
     }
+    return r;
 }
 
 template <int NS>
@@ -159,7 +206,7 @@ struct ChainState64 {  // top words of the previous window's streams (only their
 // One code path for ASCII and UTF-8 windows (the UTF-8 extras sit behind the warp-uniform `utf8` flag): duplicating the
 // chain for the two cases doubled the hot instruction footprint past the instruction cache.
 template <int NS, int NCLS>
-__device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[NCLS], u64 al, u64 nl, u64 rs, bool utf8, u64 cont,
+__device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[NCLS], u64 al, u64 nl, u64 rs, bool utf8, int rounds, u64 cont,
                                             uint32_t rs_next, uint32_t next_is_cont, uint32_t a_next, uint32_t nl_next,
                                             ChainState64<NS>& st, const LaneCtx& L)
 {
@@ -204,9 +251,10 @@ __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[N
         const uint32_t old = st.last[s];
         u64 Z = t;
         if (cd.steps[s].loop) Z = spread64(t, ck & nrs, old, L);
-        else if (utf8) {  // move the marker from the lead byte to the last byte of its character (<= 3 continuation bytes)
+        else if (utf8) {  // move the marker from the lead byte to the last byte of its character: one round per
+                          // continuation byte of the longest character in the window (`rounds`, warp-uniform)
 #pragma unroll 1
-            for (int r = 0; r < 3; ++r) Z |= adv64(Z, old, L) & cont;
+            for (int r = 0; r < rounds; ++r) Z |= adv64(Z, old, L) & cont;
         }
         st.last[s] = hi32(Z);
         old_prev = old;
@@ -215,19 +263,15 @@ __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[N
     return cd.end_mask ? apply_after64(P, cd.end_mask, as) : P;
 }
 
-// lane L keeps its 4 x 16-byte chunks at a per-lane rotation so that the 8 lanes of an LDS.128 phase hit 8 distinct
-// 16-byte bank groups
-__device__ __forceinline__ int ring_chunk_offset(uint32_t lane, int k) { return 64 * (int)lane + 16 * ((k + (int)(lane >> 1)) & 3); }
-
-__device__ __forceinline__ void ring_issue(char* slot, const char* __restrict__ chars, int ws, int end, uint32_t lane)
+// copy of window [ws, ws + 2048) into a ring stage; `dst0` = shared address of this lane's chunk 0 in that stage,
+// `gsrc` = chars + 64 * lane
+__device__ __forceinline__ void ring_issue(uint32_t dst0, const char* __restrict__ gsrc, const char* __restrict__ chars, int ws, int end, uint32_t lane)
 {
     if (ws + WIN64 <= end) {  // whole window inside the buffer: plain 16-byte copies
-        const char* src = chars + ws + 64 * (int)lane;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot) + 64u * lane;
-        const uint32_t rot = lane >> 1;
+        const char* src = gsrc + ws;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * ((k + rot) & 3u)), "l"(src + 16 * k) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst0 ^ (16u * k)), "l"(src + 16 * k) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
         return;
     }
@@ -237,27 +281,27 @@ __device__ __forceinline__ void ring_issue(char* slot, const char* __restrict__ 
         int bytes = end - pos;
         bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
         const char* src = chars + (bytes > 0 ? pos : 0);  // never form an out-of-range address; size 0 = pure zero fill
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + ring_chunk_offset(lane, k));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 ^ (16u * k)), "l"(src), "r"(bytes) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 template <int NS, int NCLS>
 __global__ void __launch_bounds__(THREADS, 3)
-k_chain64(const __grid_constant__ ChainDev cd, const Args A)
+k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
 {
-    __shared__ __align__(16) char sm_ring[WARPS][RING_STAGES][WIN64];
-    __shared__ uint32_t sm_rs[WARPS][64], sm_f[WARPS][64], sm_d[WARPS][64];
-    const int warp = threadIdx.x >> 5;
-    uint32_t* S_rs = sm_rs[warp];
-    uint32_t* S_f = sm_f[warp];
-    uint32_t* S_d = sm_d[warp];
+    __shared__ WarpSm64 sm[WARPS];
     LaneCtx L;
     L.lane = lane_id();
+    asm volatile("" : "+r"(L.lane));
     L.src = (L.lane + 31) & 31;
     L.is31 = L.lane == 31;
     const uint32_t lane = L.lane;
+    uint32_t wb = (uint32_t)__cvta_generic_to_shared(&sm[threadIdx.x >> 5]);  // this warp's block
+    uint32_t my0 = wb + ring_lane_offset(lane);                                // my chunk 0 in stage 0
+    uint32_t my_w = wb + 8u * lane;                                            // my 64-bit word of a stream (+ SM_RS / SM_F / SM_D)
+    const char* gsrc = A.chars + 64 * (int)lane;
+    asm volatile("" : "+r"(wb), "+r"(my0), "+r"(my_w));  // keep them in registers instead of re-deriving them per use
     const int warps_total = gridDim.x * WARPS;
     unsigned long long my_matches = 0;
     const uint32_t bneed = cd.builtin_union | ((cd.needs & (AS_BOW | AS_NBOW)) ? (1u << AK_ALNUM) : 0u);
@@ -289,22 +333,22 @@ k_chain64(const __grid_constant__ ChainDev cd, const Args A)
         int o_nxt = (kcur + (int)lane <= rb) ? __ldg(A.offsets + kcur + (int)lane) : 0x7fffffff;
         int stage = 0;
         __syncwarp();  // the previous item's reads of the ring are done
-        ring_issue(sm_ring[warp][0], A.chars, ws, A.end, lane);
+        ring_issue(my0, gsrc, A.chars, ws, A.end, lane);
 
         for (; ws < byte_b; ws += WIN64, stage ^= 1) {
             const int we = ws + WIN64;
             const bool more = we < byte_b;
-            if (more) ring_issue(sm_ring[warp][stage ^ 1], A.chars, we, A.end, lane);  // next window in flight
+            const uint32_t cur0 = my0 + (uint32_t)stage * WIN64;
+            if (more) ring_issue(my0 + (uint32_t)(stage ^ 1) * WIN64, gsrc, A.chars, we, A.end, lane);  // next window in flight
 
             // ---- one pass over the offsets that fall into (ws, we]: ROWSTART bits now, row results after evaluation
-            S_rs[2 * lane] = (lane == 0 && pend == 0) ? 1u : 0u;
-            S_rs[2 * lane + 1] = 0u;
+            sts64(my_w + SM_RS, (lane == 0 && pend == 0) ? 1u : 0u, 0u);
             __syncwarp();
-            if (pend > 0 && lane == 0) atomicOr(&S_rs[pend >> 5], 1u << (pend & 31));  // first window of the item
+            if (pend > 0 && lane == 0) reds_or(wb + SM_RS + 4u * (uint32_t)(pend >> 5), 1u << (pend & 31));  // first window of the item
             const int j = kcur + (int)lane;
             const int o = o_nxt;
             const bool inw = o <= we;
-            if (inw && o < we) atomicOr(&S_rs[(o - ws) >> 5], 1u << ((o - ws) & 31));
+            if (inw && o < we) reds_or(wb + SM_RS + 4u * (uint32_t)((o - ws) >> 5), 1u << ((o - ws) & 31));
             const unsigned m_in = __ballot_sync(FULL, inw);
             bool at_we = __any_sync(FULL, inw && o == we);
             int consumed = __popc(m_in);
@@ -313,7 +357,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const Args A)
                     int j2 = kcur + consumed + (int)lane;
                     int o2 = j2 <= rb ? __ldg(A.offsets + j2) : 0x7fffffff;
                     bool in2 = o2 <= we;
-                    if (in2 && o2 < we) atomicOr(&S_rs[(o2 - ws) >> 5], 1u << ((o2 - ws) & 31));
+                    if (in2 && o2 < we) reds_or(wb + SM_RS + 4u * (uint32_t)((o2 - ws) >> 5), 1u << ((o2 - ws) & 31));
                     unsigned m2 = __ballot_sync(FULL, in2);
                     at_we = at_we || __any_sync(FULL, in2 && o2 == we);
                     consumed += __popc(m2);
@@ -325,22 +369,21 @@ k_chain64(const __grid_constant__ ChainDev cd, const Args A)
                 o_nxt = jn <= rb ? __ldg(A.offsets + jn) : 0x7fffffff;
             }
             __syncwarp();
-            const u64 rs = mk64(S_rs[2 * lane], S_rs[2 * lane + 1]);
+            const u64 rs = lds64(my_w + SM_RS);
             const uint32_t rs_next = at_we || we >= A.end;
             const uint32_t next_byte = (!rs_next && we < A.end) ? (uint8_t)A.chars[we] : 0;
 
             // ---- this window's bytes: wait for its cp.async group, read back my own 64 bytes, transpose to bit planes
             if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            const char* slot = sm_ring[warp][stage];
             u64 p[8];
             {
                 uint32_t pl[8], ph[8];
-                const uint4 v0 = *(const uint4*)(slot + ring_chunk_offset(lane, 0));
-                const uint4 v1 = *(const uint4*)(slot + ring_chunk_offset(lane, 1));
+                const uint4 v0 = lds128(cur0);
+                const uint4 v1 = lds128(cur0 ^ 16u);
                 transpose_planes(v0, v1, pl);
-                const uint4 v2 = *(const uint4*)(slot + ring_chunk_offset(lane, 2));
-                const uint4 v3 = *(const uint4*)(slot + ring_chunk_offset(lane, 3));
+                const uint4 v2 = lds128(cur0 ^ 32u);
+                const uint4 v3 = lds128(cur0 ^ 48u);
                 transpose_planes(v2, v3, ph);
 #pragma unroll
                 for (int b = 0; b < 8; ++b) p[b] = mk64(pl[b], ph[b]);
@@ -351,7 +394,8 @@ k_chain64(const __grid_constant__ ChainDev cd, const Args A)
             const u64 alnum = (p[6] & letter5) | digit, word = alnum | cls_underscore(p);
             u64 space = 0;
             if (bneed & (1u << AK_SPACE)) space = cls_space(p);
-            u64 c[NCLS];
+            NaClasses<NCLS> nc;
+            u64 (&c)[NCLS] = nc.c;
 #pragma unroll
             for (int k = 0; k < NCLS; ++k) {
                 u64 v = 0;
@@ -366,7 +410,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const Args A)
                 }
                 c[k] = v;
             }
-            u64 al = alnum;
+            nc.al = alnum;
             const u64 nl = need_nl ? (cls_eq(p, '\n') & ~na) : 0ull;
             uint32_t a_next = 0;
             const uint32_t nl_next = next_byte == '\n';
@@ -379,24 +423,26 @@ k_chain64(const __grid_constant__ ChainDev cd, const Args A)
             }
             const bool utf8 = __any_sync(FULL, na != 0);
             u64 cont = 0;
+            int rounds = 0;
             if (utf8) {
-                classify_non_ascii64<NCLS>(cd, A, slot, ws + 64 * (int)lane, na, c, al);
+                if (na) nc = classify_non_ascii64<NCLS>(cd, A, cur0, ws + 64 * (int)lane, na, nc);
                 cont = p[7] & ~p[6];
+                const u64 lead3 = p[7] & p[6] & p[5];  // lead byte of a 3- or 4-byte character
+                rounds = 1 + (int)__any_sync(FULL, lead3 != 0) + (int)__any_sync(FULL, (lead3 & p[4]) != 0);
             }
-            const u64 E = chain_eval64<NS, NCLS>(cd, c, al, nl, rs, utf8, cont, rs_next, (next_byte & 0xC0u) == 0x80u, a_next, nl_next, st, L);
+            const u64 al = nc.al;
+            const u64 E = chain_eval64<NS, NCLS>(cd, c, al, nl, rs, utf8, rounds, cont, rs_next, (next_byte & 0xC0u) == 0x80u, a_next, nl_next, st, L);
 
             // ---- sticky per-row OR of the match bits; NUL bytes make a row "dirty" (decided by the exact VM)
             const u64 nrs = ~rs;
             const u64 F = spread64(E, nrs, st.last_f, L);
             st.last_f = hi32(F);
-            S_f[2 * lane] = lo32(F);
-            S_f[2 * lane + 1] = hi32(F);
+            sts64(my_w + SM_F, lo32(F), hi32(F));
             const bool any_dirty = __any_sync(FULL, zero != 0) || d_live;
             if (any_dirty) {
                 const u64 D = spread64(zero, nrs, st.last_d, L);
                 st.last_d = hi32(D);
-                S_d[2 * lane] = lo32(D);
-                S_d[2 * lane + 1] = hi32(D);
+                sts64(my_w + SM_D, lo32(D), hi32(D));
                 d_live = __shfl_sync(FULL, hi32(D), 31) >> 31;
             }
             __syncwarp();
@@ -408,8 +454,8 @@ k_chain64(const __grid_constant__ ChainDev cd, const Args A)
                 bool hit = false, dirty = false;
                 if (inw && o > o_prev) {  // non-empty row j-1, last byte o-1 >= ws
                     const int b = o - 1 - ws;
-                    hit = (S_f[b >> 5] >> (b & 31)) & 1u;
-                    dirty = any_dirty && ((S_d[b >> 5] >> (b & 31)) & 1u);
+                    hit = stream_bit(wb + SM_F, b);
+                    dirty = any_dirty && stream_bit(wb + SM_D, b);
                     if (!dirty) A.out[j - 1] = hit;
                 }
                 if (any_dirty) {
@@ -431,8 +477,8 @@ k_chain64(const __grid_constant__ ChainDev cd, const Args A)
                         const int o2 = __ldg(A.offsets + j2), o2p = __ldg(A.offsets + j2 - 1);
                         if (o2 > o2p) {
                             const int b = o2 - 1 - ws;
-                            hit = (S_f[b >> 5] >> (b & 31)) & 1u;
-                            dirty = any_dirty && ((S_d[b >> 5] >> (b & 31)) & 1u);
+                            hit = stream_bit(wb + SM_F, b);
+                            dirty = any_dirty && stream_bit(wb + SM_D, b);
                             if (!dirty) A.out[j2 - 1] = hit;
                         }
                     }
@@ -457,6 +503,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const Args A)
     if (lane == 0 && my_matches) atomicAdd(A.total, my_matches);
 }
 
+#ifndef CUSTR_EXPERIMENT_ONLY_4_1
 template <int NS>
 static void launch_chain64_ns(const ChainDev& cd, const Args& a, int blocks)
 {
@@ -467,9 +514,15 @@ static void launch_chain64_ns(const ChainDev& cd, const Args& a, int blocks)
     else if (cd.nclasses == 2) LAUNCH(k2, blocks, THREADS, 0, cd, a);
     else LAUNCH(k4, blocks, THREADS, 0, cd, a);
 }
+#endif
 
 static void launch_chain64(const ChainDev& cd, const Args& a, int blocks)
 {
+#ifdef CUSTR_EXPERIMENT_ONLY_4_1  // quick SASS iteration on the headline instantiation (tools/sass_stat.sh)
+    auto k1 = k_chain64<4, 1>;
+    LAUNCH(k1, blocks, THREADS, 0, cd, a);
+    return;
+#else
     switch (cd.nsteps) {
     case 1: launch_chain64_ns<1>(cd, a, blocks); break;
     case 2: launch_chain64_ns<2>(cd, a, blocks); break;
@@ -480,4 +533,5 @@ static void launch_chain64(const ChainDev& cd, const Args& a, int blocks)
     case 7: launch_chain64_ns<7>(cd, a, blocks); break;
     default: launch_chain64_ns<8>(cd, a, blocks); break;
     }
+#endif
 }
