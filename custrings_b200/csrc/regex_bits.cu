@@ -114,7 +114,7 @@ __device__ __forceinline__ void transpose_planes(const uint4& lo, const uint4& h
     // find it on its own when m and ~m are both immediates
 #define DELTA_SWAP(A, B, S, M)                                                                              \
     {                                                                                                       \
-        uint32_t na, nb, bs = (B) * (1u << (S)) /* IMAD: FMA pipe, the ALU pipe is the bottleneck */, as_ = (A) >> (S); \
+        uint32_t na, nb, bs = (B) * (1u << (S)) /* IMAD: FMA pipe, the ALU pipe is the bottleneck */, as_ = __umulhi((A), 1u << (32 - (S))); \
         asm("lop3.b32 %0, %1, %2, %3, 0xE2;" : "=r"(na) : "r"(A), "r"(M), "r"(bs));                         \
         asm("lop3.b32 %0, %1, %2, %3, 0xE2;" : "=r"(nb) : "r"(as_), "r"(M), "r"(B));                        \
         (A) = na; (B) = nb;                                                                                 \
