@@ -10,6 +10,7 @@
 #include "regex_vm.cuh"
 #include "regex_bits.h"
 #include "chain_spans.cuh"
+#include "span_walk.cuh"
 #include <cub/cub.cuh>
 #include <list>
 #include <map>
@@ -305,6 +306,77 @@ k_chain_replace(ColView col, const __grid_constant__ bits::ChainDev cd, const ui
     }
 }
 
+// ---- span path over the chain kernel's bit streams (span_walk.cuh): a few word scans per match ------------------------
+__global__ void __launch_bounds__(256)
+k_span_count(ColView col, spans::Streams S, const uint8_t* __restrict__ hits, int k_chars, int32_t* __restrict__ out,
+             unsigned long long* __restrict__ total)
+{
+    for (int base = blockIdx.x * blockDim.x; base < col.n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        int found = 0;
+        if (i < col.n) {
+            if (hits[i])
+                found = spans::walk_spans(S, (const uint8_t*)col.chars, col.offsets[i], col.offsets[i + 1], k_chars, 0x7fffffff, [](int, int) {});
+            out[i] = found;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, found != 0);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(total, (unsigned long long)__popc(m));
+    }
+}
+
+// out_chars == null: size pass (out_len); else write pass
+__global__ void __launch_bounds__(256)
+k_span_replace(ColView col, spans::Streams S, const uint8_t* __restrict__ hits, int k_chars, const char* __restrict__ repl, int repl_len,
+               int maxrepl, int32_t* __restrict__ out_len, const int32_t* __restrict__ out_off, char* __restrict__ out_chars)
+{
+    const uint8_t* chars = (const uint8_t*)col.chars;
+    const int budget = maxrepl < 0 ? 0x7fffffff : maxrepl;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < col.n; i += gridDim.x * blockDim.x) {
+        const int a = col.offsets[i], b = col.offsets[i + 1];
+        if (!out_chars) {
+            int total = b - a;
+            if (hits[i]) spans::walk_spans(S, chars, a, b, k_chars, budget, [&](int s, int e) { total += repl_len - (e - s); });
+            out_len[i] = total;
+            continue;
+        }
+        char* o = out_chars + out_off[i];
+        int last = a;
+        if (hits[i])
+            spans::walk_spans(S, chars, a, b, k_chars, budget, [&](int s, int e) {
+                for (int q = last; q < s; ++q) *o++ = (char)chars[q];
+                for (int q = 0; q < repl_len; ++q) *o++ = repl[q];
+                last = e;
+            });
+        for (int q = last; q < b; ++q) *o++ = (char)chars[q];
+    }
+}
+
+// Runs the chain kernel with span streams for `c` over `col`.  False: not applicable (caller uses the scalar / VM path).
+struct SpanRun {
+    bits::SpanStreams ss;
+    BufPtr hits, keep_rows, keep_count;
+    unsigned int* dirty_count = nullptr;
+    spans::Streams view() const { return spans::Streams{ss.m, ss.k, ss.a, ss.base}; }
+};
+static bool run_span_streams(Compiled& c, const custr_column* col, SpanRun& r)
+{
+    if (!span_plan(c) || !cap_tier((int)c.prog.insts.size())) return false;
+    r.hits = dev_alloc((size_t)col->n);
+    Scratch<unsigned long long> unused(1);
+    CUSTR_CUDA(cudaMemsetAsync(unused.get(), 0, 8, g_stream));
+    int32_t* dirty_rows = nullptr;
+    const bool ok = bits::run(*c.plan_contains, col, (const uint8_t*)c.dev_image->ptr, device_unicode_flags(), (uint8_t*)r.hits->ptr,
+                              unused.get(), &dirty_rows, &r.dirty_count, r.keep_rows, r.keep_count, &r.ss);
+    return ok;  // `unused` is freed stream-ordered
+}
+static unsigned int read_dirty(const SpanRun& r)
+{
+    unsigned int h = 0;
+    CUSTR_CUDA(cudaMemcpyAsync(&h, r.dirty_count, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    return h;
+}
+
 // ---- findall / extract (capture-span callers, reference findall.cu:36-98, extract.cu:36-68) ---------------------------
 // walks the non-overlapping matches of a row exactly like count_re does and calls f(k, begin, end)
 template <int CAP, typename F>
@@ -584,7 +656,19 @@ int custr_count_re(const custr_column* col, const char* pattern, int32_t* result
             ResultBuf<int32_t> out(results, n, devmem);
             Scratch<unsigned long long> total(1);
             CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
-            if (const bits::ChainDev* cd = span_plan(*c)) {  // last-loop chain: scalar leftmost-longest scan is exact
+            if (const bits::ChainDev* cd = span_plan(*c)) {  // last-loop chain
+                SpanRun sr;
+                if (run_span_streams(*c, col, sr)) {  // bit streams + word scans (rows holding NUL: fall through)
+                    LAUNCH(k_span_count, vm_grid(n) * 2, 256, 0, view_of(col), sr.view(), (const uint8_t*)sr.hits->ptr, (int)cd->nsteps - 1, out.dev,
+                           total.get());
+                    int matches = (int)read_counter(total.get());
+                    if (read_dirty(sr) == 0) {
+                        g_last_tier = "bitspans";
+                        out.finish();
+                        return matches;
+                    }
+                    CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
+                }
                 Scratch<int> nul_seen(1);
                 CUSTR_CUDA(cudaMemsetAsync(nul_seen.get(), 0, sizeof(int), g_stream));
                 LAUNCH(k_chain_count, vm_grid(n) * 2, 256, 0, view_of(col), *cd, device_unicode_flags(), out.dev, total.get(), nul_seen.get());
@@ -731,6 +815,25 @@ custr_column* custr_replace_re(const custr_column* col, const char* pattern, con
             const bits::ChainDev* cd = span_plan(*c);
             Scratch<int> nul_seen(1);
             int h_nul = 0;
+            if (cd) {  // last-loop chain, bit streams + word scans
+                SpanRun sr;
+                if (run_span_streams(*c, col, sr)) {
+                    const int k_chars = (int)cd->nsteps - 1;
+                    LAUNCH(k_span_replace, vm_grid(n) * 2, 256, 0, view_of(col), sr.view(), (const uint8_t*)sr.hits->ptr, k_chars,
+                           (const char*)d_repl->ptr, repl_len, maxrepl, lens.get(), (const int32_t*)nullptr, (char*)nullptr);
+                    if (read_dirty(sr) == 0) {
+                        BufPtr off2;
+                        int64_t total2 = 0;
+                        finish_replace(col, lens, off2, total2);
+                        BufPtr chars2 = dev_alloc((size_t)total2);
+                        LAUNCH(k_span_replace, vm_grid(n) * 2, 256, 0, view_of(col), sr.view(), (const uint8_t*)sr.hits->ptr, k_chars,
+                               (const char*)d_repl->ptr, repl_len, maxrepl, (int32_t*)nullptr, (const int32_t*)off2->ptr, (char*)chars2->ptr);
+                        g_last_tier = "bitspans";
+                        CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+                        return make_column(chars2, off2, copy_validity(col), n, col->nulls, total2);
+                    }
+                }
+            }
             if (cd) {  // last-loop chain: scalar leftmost-longest scan is exact (rows holding NUL: whole call goes to the VM)
                 CUSTR_CUDA(cudaMemsetAsync(nul_seen.get(), 0, sizeof(int), g_stream));
                 LAUNCH(k_chain_replace, vm_grid(n) * 2, 256, 0, view_of(col), *cd, device_unicode_flags(), (const char*)d_repl->ptr, repl_len,

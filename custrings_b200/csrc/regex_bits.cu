@@ -55,6 +55,12 @@ struct Args {
     const int32_t* item_bounds;  // item_bounds[t] = first row whose start offset is >= first + t*ITEM_BYTES (k_chain64)
     const uint8_t* prog_img;  // compiled program image (exact class tests for non-ASCII characters)
     const uint8_t* uflags;
+    // span streams (count_re / replace_re of last-loop chains, span_walk.cuh): one bit per byte, word w covers the bytes
+    // [span_base + 64 w, span_base + 64 w + 64); null = not wanted
+    unsigned long long* span_m;
+    unsigned long long* span_k;
+    unsigned long long* span_a;
+    int32_t span_base;
 };
 
 struct WarpSmem {
@@ -438,8 +444,10 @@ __global__ void k_item_bounds(const int32_t* __restrict__ offsets, int n, int fi
 const PlanDev& device_plan(const Plan& plan);
 
 bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, const uint8_t* uflags, uint8_t* out,
-         unsigned long long* total, int32_t** dirty_rows, unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count)
+         unsigned long long* total, int32_t** dirty_rows, unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count,
+         SpanStreams* spans)
 {
+    if (spans && !(plan.is_chain && plan.span_ok && !g_force_generic && !g_chain32)) return false;
 
     const int32_t n = col->n;
     if (((uintptr_t)col->chars & 15) != 0) return false;  // vector loads need a 16-byte aligned base
@@ -465,6 +473,21 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     a.item_bounds = nullptr;
     a.prog_img = prog_img;
     a.uflags = uflags;
+    a.span_m = a.span_k = a.span_a = nullptr;
+    a.span_base = 0;
+    if (spans) {
+        a.span_base = a.first & ~(WIN64 - 1);
+        const size_t words = (((size_t)(a.end - a.span_base) + WIN64 - 1) / WIN64) * (WIN64 / 64);
+        spans->keep = dev_alloc(3 * words * sizeof(unsigned long long));
+        CUSTR_CUDA(cudaMemsetAsync(spans->keep->ptr, 0, 3 * words * sizeof(unsigned long long), g_stream));
+        a.span_m = (unsigned long long*)spans->keep->ptr;
+        a.span_k = a.span_m + words;
+        a.span_a = a.span_k + words;
+        spans->m = a.span_m;
+        spans->k = a.span_k;
+        spans->a = a.span_a;
+        spans->base = a.span_base;
+    }
     int blocks = (a.nitems + WARPS - 1) / WARPS;
     int cap = num_sms() * 8;
     if (blocks > cap) blocks = cap;

@@ -20,8 +20,20 @@ std::string describe(const Plan& plan);
 // byte are NOT decided: their indices are appended to *dirty_rows (count in *dirty_count, both device memory owned by the
 // returned buffers) for the exact Pike-VM kernel.  Returns false (nothing launched) if the column layout is not
 // supported (unaligned chars base).  Enqueued on g_stream.
+//
+// With `spans` (only for plans where span_chain() is non-null) the chain kernel also leaves three bit streams of the last
+// step in device memory — M (a match can begin its last step here), K (the match may continue into this byte), A (a match
+// may end after this byte) — from which span_walk.cuh derives the exact match spans of every row.
+struct SpanStreams {
+    const unsigned long long* m = nullptr;
+    const unsigned long long* k = nullptr;
+    const unsigned long long* a = nullptr;
+    int32_t base = 0;   // byte offset (into chars) of bit 0
+    BufPtr keep;
+};
 bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, const uint8_t* uflags, uint8_t* out,
-         unsigned long long* total, int32_t** dirty_rows, unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count);
+         unsigned long long* total, int32_t** dirty_rows, unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count,
+         SpanStreams* spans = nullptr);
 extern bool g_force_generic;
 extern bool g_chain32;
 

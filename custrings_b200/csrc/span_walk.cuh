@@ -1,0 +1,110 @@
+// Exact match spans of last-loop chains (x y z+ with optional assertions in front / at the end) from the three bit
+// streams the chain kernel leaves in device memory (regex_bits.cu, Args::span_*), one bit per byte of the column:
+//   M  the byte is the lead byte of a character at which a match can BEGIN ITS LAST STEP (the k characters before it matched
+//      the first k steps, the leading assertion held at the start)
+//   K  the match may continue INTO this byte (last step's class — the loop — or a continuation byte of its character)
+//   A  a match may END after this byte (last byte of a character, trailing assertion holds behind it)
+// The Pike VM's answer for this family is "leftmost start, then the longest end" (see chain_spans.cuh for the argument), and
+// count_re / replace_re resume the search at the end of the previous match (count.cu:174-195, replace.cu:50-106).  In stream
+// terms: take the first M bit m at or after the cursor, follow the run of K bits behind it, take the last A bit p of
+// [m, run end]; the match is [m - k characters, p + 1) and the cursor becomes (p + 1) + k characters.  Each match costs a few
+// word scans instead of a character-by-character NFA walk, and rows without any match are skipped by the chain kernel's
+// boolean result.
+#pragma once
+#include "common.cuh"
+#include "device_utils.cuh"
+
+namespace custr {
+namespace spans {
+
+using u64 = unsigned long long;
+
+struct Streams {
+    const u64* m;
+    const u64* k;
+    const u64* a;
+    int base;  // byte offset of bit 0
+};
+
+// first set bit of s in [from, lim), -1 when there is none (positions are byte offsets into chars)
+__device__ __forceinline__ int next_set(const u64* __restrict__ s, int base, int from, int lim)
+{
+    if (from >= lim) return -1;
+    const int r = from - base, rl = lim - base;
+    int w = r >> 6;
+    u64 v = __ldg(s + w) & (~0ull << (r & 63));
+    for (;;) {
+        if (v) {
+            const int p = (w << 6) + __ffsll((long long)v) - 1;
+            return p < rl ? p + base : -1;
+        }
+        ++w;
+        if ((w << 6) >= rl) return -1;
+        v = __ldg(s + w);
+    }
+}
+// first CLEAR bit of s in [from, lim), lim when there is none
+__device__ __forceinline__ int next_clear(const u64* __restrict__ s, int base, int from, int lim)
+{
+    if (from >= lim) return lim;
+    const int r = from - base, rl = lim - base;
+    int w = r >> 6;
+    u64 v = ~__ldg(s + w) & (~0ull << (r & 63));
+    for (;;) {
+        if (v) {
+            const int p = (w << 6) + __ffsll((long long)v) - 1;
+            return p < rl ? p + base : lim;
+        }
+        ++w;
+        if ((w << 6) >= rl) return lim;
+        v = ~__ldg(s + w);
+    }
+}
+// last set bit of s in [lo, hi] (both inclusive), -1 when there is none
+__device__ __forceinline__ int last_set(const u64* __restrict__ s, int base, int lo, int hi)
+{
+    if (hi < lo) return -1;
+    const int rlo = lo - base, rhi = hi - base;
+    int w = rhi >> 6;
+    u64 v = __ldg(s + w) & (~0ull >> (63 - (rhi & 63)));
+    for (;;) {
+        if (v) {
+            const int p = (w << 6) + 63 - __clzll((long long)v);
+            return p >= rlo ? p + base : -1;
+        }
+        --w;
+        if ((w << 6) + 63 < rlo) return -1;
+        v = __ldg(s + w);
+    }
+}
+
+// calls emit(begin, end) (byte offsets into chars) for the first `budget` matches of the row [a, b); returns their number
+template <typename F>
+__device__ __forceinline__ int walk_spans(const Streams& S, const uint8_t* __restrict__ chars, int a, int b, int k_chars, int budget, F emit)
+{
+    int found = 0;
+    int cm = a;  // smallest admissible M position
+    while (found < budget) {
+        const int m = next_set(S.m, S.base, cm, b);
+        if (m < 0) break;
+        const int run_end = next_clear(S.k, S.base, m + 1, b) - 1;
+        const int p = last_set(S.a, S.base, m, run_end);
+        if (p < 0) {  // no admissible end from this start
+            cm = m + 1;
+            continue;
+        }
+        int s = m;
+        for (int j = 0; j < k_chars; ++j) {
+            --s;
+            while (s > a && (chars[s] & 0xC0u) == 0x80u) --s;
+        }
+        emit(s, p + 1);
+        ++found;
+        cm = p + 1;  // the next match starts at or after the end of this one: its last step begins k characters later
+        for (int j = 0; j < k_chars && cm < b; ++j) cm += utf8_width(chars[cm]);
+    }
+    return found;
+}
+
+}  // namespace spans
+}  // namespace custr

@@ -114,4 +114,39 @@ def test_rows_with_nul_bytes_fall_back_exactly(oracle):
         assert lib().custr_last_regex_tier() == b"pikevm"
         assert oracle.unpack(*dev.replace(p, "#").to_arrays()) == ref.replace_re(p, "#").to_list(), p
     clean = nvstrings.to_device(["abcd efgh", "x1 y22 z333"])
-    assert clean.count(r"\d+") == [0, 3] and lib().custr_last_regex_tier() == b"chainspan"
+    assert clean.count(r"\d+") == [0, 3] and lib().custr_last_regex_tier() == b"bitspans"
+    lib().custr_set_regex_tier(2)  # generic bitstream kernel forced: span streams unavailable -> scalar chain matcher
+    try:
+        assert clean.count(r"\d+") == [0, 3] and lib().custr_last_regex_tier() == b"chainspan"
+    finally:
+        lib().custr_set_regex_tier(0)
+
+
+SPAN_PATTERNS = [r"\b\w{4,}\b", r"\d+", r"[a-z]+", r"ab", r"a\d+", r"é+", r"\w+$", r"^\w+", r"x\b", r"\w\w\w", r"日\w+", r"\bé\w*", r"[^a-c]+",
+                 r"\W+", r"\s\S+", r"\B\w+", r"l+", r"\w{2,}\b", r"\Aa\w*", r"\d\d?", r"[é-ü]+", r"😀.", r".\b", r"\w+\Z", r"\D{3}", r"_+"]
+
+
+def test_count_replace_span_streams(oracle):
+    """count_re / replace_re of last-loop chains through the chain kernel's bit streams (tier 'bitspans'), long and
+    short rows, multi-byte characters, rows straddling windows and work items"""
+    from custrings_b200 import nvstrings
+    from custrings_b200._lib import lib
+    rng = random.Random(31)
+    strs = corpus.STRINGS + corpus.random_strings(rng, 3000)
+    # long rows: many windows per row; plus a block of empty / null rows
+    for k in range(40):
+        strs.append(" ".join(rng.choice(["abcd", "x", "héllo", "12345", "a_b", "日本語", "wörld9", "_", "zz😀zz"]) for _ in range(rng.randrange(200, 900))))
+    strs += ["", None, "", "a"] * 50
+    rng.shuffle(strs)
+    dev, ref = nvstrings.to_device(strs), oracle.RefStrings.from_list(strs)
+    used = 0
+    for p in SPAN_PATTERNS:
+        want = ref.count_re(p)[0].tolist()
+        got = _none_to(0, dev.count(p))
+        tier = lib().custr_last_regex_tier()
+        assert got == want, (p, tier)
+        used += tier == b"bitspans"
+        for repl, mx in (("<>", -1), ("", 2), ("é日", 1), ("#", 0)):
+            want = ref.replace_re(p, repl, mx).to_list()
+            assert oracle.unpack(*dev.replace(p, repl, mx).to_arrays()) == want, (p, repl, mx, lib().custr_last_regex_tier())
+    assert used >= 15, used
