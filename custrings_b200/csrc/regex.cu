@@ -11,6 +11,7 @@
 #include "regex_bits.h"
 #include "chain_spans.cuh"
 #include "span_walk.cuh"
+#include "row_stage.cuh"
 #include <cub/cub.cuh>
 #include <list>
 #include <map>
@@ -349,6 +350,48 @@ k_span_replace(ColView col, spans::Streams S, const uint8_t* __restrict__ hits, 
             });
         for (int q = last; q < b; ++q) *o++ = (char)chars[q];
     }
+}
+
+// write pass, rows AND their slices of the three bit streams staged through shared memory (row_stage.cuh): the walk then
+// costs shared-memory latencies instead of a chain of dependent global loads per match
+__global__ void __launch_bounds__(stage::THREADS)
+k_span_replace_staged(ColView col, int chars_limit, spans::Streams S, const uint8_t* __restrict__ hits, int k_chars,
+                      const char* __restrict__ repl, int repl_len, int maxrepl, const int32_t* __restrict__ out_off, char* __restrict__ out_chars)
+{
+    __shared__ stage::Buffers sm;
+    __shared__ stage::StreamBuffers ss;
+    const uint8_t* chars = (const uint8_t*)col.chars;
+    const int budget = maxrepl < 0 ? 0x7fffffff : maxrepl;
+    const int warp = threadIdx.x >> 5;
+    stage::for_each_row_staged(
+        col, chars_limit, out_chars, sm, [&](int r) { return (long long)out_off[r]; },
+        [&](int in_a, int in_b, int w_, int lane) {
+            if (in_b <= in_a) return;
+            const int w0 = (in_a - S.base) >> 6, w1 = (in_b - 1 - S.base) >> 6;
+            for (int w = w0 + lane; w <= w1; w += 32) {
+                ss.w[w_][0][w - w0] = __ldg(S.m + w);
+                ss.w[w_][1][w - w0] = __ldg(S.k + w);
+                ss.w[w_][2][w - w0] = __ldg(S.a + w);
+            }
+        },
+        [&](int i, const uint8_t* src, char* dst, bool staged, int in_a) {
+            const int a = col.offsets[i], b = col.offsets[i + 1];
+            int o = out_off[i], last = a;
+            auto emit = [&](int s, int e) {
+                for (int q = last; q < s; ++q) dst[o++] = (char)src[q];
+                for (int q = 0; q < repl_len; ++q) dst[o++] = repl[q];
+                last = e;
+            };
+            if (hits[i]) {
+                if (staged) {
+                    const int w0 = (in_a - S.base) >> 6;
+                    const spans::Streams T{ss.w[warp][0] - w0, ss.w[warp][1] - w0, ss.w[warp][2] - w0, S.base};
+                    spans::walk_spans<false>(T, src, a, b, k_chars, budget, emit);
+                } else
+                    spans::walk_spans<true>(S, chars, a, b, k_chars, budget, emit);
+            }
+            for (int q = last; q < b; ++q) dst[o++] = (char)src[q];
+        });
 }
 
 // Runs the chain kernel with span streams for `c` over `col`.  False: not applicable (caller uses the scalar / VM path).
@@ -826,8 +869,9 @@ custr_column* custr_replace_re(const custr_column* col, const char* pattern, con
                         int64_t total2 = 0;
                         finish_replace(col, lens, off2, total2);
                         BufPtr chars2 = dev_alloc((size_t)total2);
-                        LAUNCH(k_span_replace, vm_grid(n) * 2, 256, 0, view_of(col), sr.view(), (const uint8_t*)sr.hits->ptr, k_chars,
-                               (const char*)d_repl->ptr, repl_len, maxrepl, (int32_t*)nullptr, (const int32_t*)off2->ptr, (char*)chars2->ptr);
+                        LAUNCH(k_span_replace_staged, stage::grid_for(n), stage::THREADS, 0, view_of(col), col->first_off + (int)col->nbytes, sr.view(),
+                               (const uint8_t*)sr.hits->ptr, k_chars, (const char*)d_repl->ptr, repl_len, maxrepl, (const int32_t*)off2->ptr,
+                               (char*)chars2->ptr);
                         g_last_tier = "bitspans";
                         CUSTR_CUDA(cudaStreamSynchronize(g_stream));
                         return make_column(chars2, off2, copy_validity(col), n, col->nulls, total2);

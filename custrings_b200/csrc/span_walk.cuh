@@ -26,13 +26,20 @@ struct Streams {
     int base;  // byte offset of bit 0
 };
 
+template <bool LDG>
+__device__ __forceinline__ u64 word_at(const u64* s, int w)
+{
+    return LDG ? __ldg(s + w) : s[w];  // LDG = false: the streams are a shared-memory copy (row_stage.cuh)
+}
+
 // first set bit of s in [from, lim), -1 when there is none (positions are byte offsets into chars)
-__device__ __forceinline__ int next_set(const u64* __restrict__ s, int base, int from, int lim)
+template <bool LDG>
+__device__ __forceinline__ int next_set(const u64* s, int base, int from, int lim)
 {
     if (from >= lim) return -1;
     const int r = from - base, rl = lim - base;
     int w = r >> 6;
-    u64 v = __ldg(s + w) & (~0ull << (r & 63));
+    u64 v = word_at<LDG>(s, w) & (~0ull << (r & 63));
     for (;;) {
         if (v) {
             const int p = (w << 6) + __ffsll((long long)v) - 1;
@@ -40,16 +47,17 @@ __device__ __forceinline__ int next_set(const u64* __restrict__ s, int base, int
         }
         ++w;
         if ((w << 6) >= rl) return -1;
-        v = __ldg(s + w);
+        v = word_at<LDG>(s, w);
     }
 }
 // first CLEAR bit of s in [from, lim), lim when there is none
-__device__ __forceinline__ int next_clear(const u64* __restrict__ s, int base, int from, int lim)
+template <bool LDG>
+__device__ __forceinline__ int next_clear(const u64* s, int base, int from, int lim)
 {
     if (from >= lim) return lim;
     const int r = from - base, rl = lim - base;
     int w = r >> 6;
-    u64 v = ~__ldg(s + w) & (~0ull << (r & 63));
+    u64 v = ~word_at<LDG>(s, w) & (~0ull << (r & 63));
     for (;;) {
         if (v) {
             const int p = (w << 6) + __ffsll((long long)v) - 1;
@@ -57,16 +65,17 @@ __device__ __forceinline__ int next_clear(const u64* __restrict__ s, int base, i
         }
         ++w;
         if ((w << 6) >= rl) return lim;
-        v = ~__ldg(s + w);
+        v = ~word_at<LDG>(s, w);
     }
 }
 // last set bit of s in [lo, hi] (both inclusive), -1 when there is none
-__device__ __forceinline__ int last_set(const u64* __restrict__ s, int base, int lo, int hi)
+template <bool LDG>
+__device__ __forceinline__ int last_set(const u64* s, int base, int lo, int hi)
 {
     if (hi < lo) return -1;
     const int rlo = lo - base, rhi = hi - base;
     int w = rhi >> 6;
-    u64 v = __ldg(s + w) & (~0ull >> (63 - (rhi & 63)));
+    u64 v = word_at<LDG>(s, w) & (~0ull >> (63 - (rhi & 63)));
     for (;;) {
         if (v) {
             const int p = (w << 6) + 63 - __clzll((long long)v);
@@ -74,21 +83,22 @@ __device__ __forceinline__ int last_set(const u64* __restrict__ s, int base, int
         }
         --w;
         if ((w << 6) + 63 < rlo) return -1;
-        v = __ldg(s + w);
+        v = word_at<LDG>(s, w);
     }
 }
 
 // calls emit(begin, end) (byte offsets into chars) for the first `budget` matches of the row [a, b); returns their number
-template <typename F>
-__device__ __forceinline__ int walk_spans(const Streams& S, const uint8_t* __restrict__ chars, int a, int b, int k_chars, int budget, F emit)
+// (`chars` only has to be valid for [a, b); LDG = false: streams and chars are shared-memory copies)
+template <bool LDG = true, typename F>
+__device__ __forceinline__ int walk_spans(const Streams& S, const uint8_t* chars, int a, int b, int k_chars, int budget, F emit)
 {
     int found = 0;
     int cm = a;  // smallest admissible M position
     while (found < budget) {
-        const int m = next_set(S.m, S.base, cm, b);
+        const int m = next_set<LDG>(S.m, S.base, cm, b);
         if (m < 0) break;
-        const int run_end = next_clear(S.k, S.base, m + 1, b) - 1;
-        const int p = last_set(S.a, S.base, m, run_end);
+        const int run_end = next_clear<LDG>(S.k, S.base, m + 1, b) - 1;
+        const int p = last_set<LDG>(S.a, S.base, m, run_end);
         if (p < 0) {  // no admissible end from this start
             cm = m + 1;
             continue;
