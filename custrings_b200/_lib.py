@@ -45,6 +45,7 @@ _SIGNATURES = {
     "custr_count_re": (ci, [vp, cp, vp, ci]),
     "custr_replace_re": (vp, [vp, cp, cp, ci]),
     "custr_replace_re_multi": (vp, [vp, vp, ci, vp]),
+    "custr_replace_with_backrefs": (vp, [vp, cp, cp]),
     "custr_regex_describe": (ci, [cp, vp, C.c_size_t]),
     "custr_findall": (ci, [vp, cp, vp, ci]),
     "custr_findall_record": (ci, [vp, cp, vp, vp, ci]),
@@ -61,6 +62,9 @@ _SIGNATURES = {
     "custr_rsplit": (ci, [vp, cp, ci, vp, ci]),
     "custr_split_record": (ci, [vp, cp, ci, vp, vp, ci]),
     "custr_rsplit_record": (ci, [vp, cp, ci, vp, vp, ci]),
+    "custr_partition": (vp, [vp, cp, ci]),
+    "custr_find_from": (ci, [vp, cp, vp, vp, vp, ci]),
+    "custr_match_strings": (ci, [vp, vp, vp, ci]),
     "custr_slice_rows": (vp, [vp, ci, ci]),
     "custr_gather": (vp, [vp, vp, ci, ci]),
     "custr_tokenize": (vp, [vp, cp]),

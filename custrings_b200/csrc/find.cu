@@ -150,6 +150,52 @@ static int find_family(const custr_column* col, const char* str, int start, int 
     return (int)cnt;
 }
 
+// find_from (find.cu:123-160): per-row start / end character positions
+__global__ void __launch_bounds__(FIND_THREADS)
+k_find_from(ColView col, const uint8_t* __restrict__ needle, int m, const int32_t* __restrict__ starts, const int32_t* __restrict__ ends,
+            int32_t* __restrict__ out, unsigned long long* __restrict__ total)
+{
+    __shared__ uint8_t sm[NEEDLE_SMEM];
+    const uint8_t* t = stage_needle(needle, m, sm);
+    for (int base = blockIdx.x * blockDim.x; base < col.n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        int counted = 0;
+        if (i < col.n) {
+            int r = -2;
+            if (col.valid(i)) {
+                const int pos = starts ? starts[i] : 0;
+                const int end = ends ? ends[i] : pos - 1;  // count = end - pos < 0: to the end of the string
+                r = row::find_chars((const uint8_t*)col.chars + col.offsets[i], col.offsets[i + 1] - col.offsets[i], t, m, pos, end, false);
+            }
+            out[i] = r;
+            counted = r != -1;
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, counted);
+        if ((threadIdx.x & 31) == 0 && mk) atomicAdd(total, (unsigned long long)__popc(mk));
+    }
+}
+
+// match_strings (find.cu:276-313): row-wise equality of two columns; two nulls are equal, a null and a string are not
+__global__ void __launch_bounds__(FIND_THREADS)
+k_match_strings(ColView a, ColView b, uint8_t* __restrict__ out, unsigned long long* __restrict__ total)
+{
+    for (int base = blockIdx.x * blockDim.x; base < a.n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        bool r = false;
+        if (i < a.n) {
+            const bool va = a.valid(i), vb = b.valid(i);
+            if (va && vb) {
+                const int na = a.offsets[i + 1] - a.offsets[i], nb = b.offsets[i + 1] - b.offsets[i];
+                r = na == nb && row::bytes_equal((const uint8_t*)a.chars + a.offsets[i], (const uint8_t*)b.chars + b.offsets[i], na);
+            } else
+                r = va == vb;
+            out[i] = r;
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, r);
+        if ((threadIdx.x & 31) == 0 && mk) atomicAdd(total, (unsigned long long)__popc(mk));
+    }
+}
+
 static BufPtr validity_copy(const custr_column* col)
 {
     if (!col->validity) return nullptr;
@@ -174,6 +220,50 @@ int custr_rfind(const custr_column* col, const char* str, int32_t start, int32_t
     return guarded([&] { return find_family(col, str, start, end, FM_RFIND, results, nullptr, devmem, 0); }, (int)CUSTR_ERR_ARG,
                    (int)CUSTR_ERR_CUDA);
 }
+int custr_find_from(const custr_column* col, const char* str, const int32_t* starts, const int32_t* ends, int32_t* results, int devmem)
+{
+    return guarded(
+        [&]() -> int {
+            if (!col || !str || !results) return 0;  // find.cu:126-127
+            const int32_t n = col->n;
+            if (n == 0) return 0;
+            const int m = (int)strlen(str);
+            BufPtr d_needle = upload(str, m + 1);
+            BufPtr ds, de;  // host arrays are staged when devmem == 0
+            if (!devmem && starts) { ds = upload(starts, sizeof(int32_t) * (size_t)n); starts = (const int32_t*)ds->ptr; }
+            if (!devmem && ends) { de = upload(ends, sizeof(int32_t) * (size_t)n); ends = (const int32_t*)de->ptr; }
+            Scratch<unsigned long long> total(1);
+            CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
+            ResultBuf<int32_t> out(results, n, devmem);
+            LAUNCH(k_find_from, row_grid(n, FIND_THREADS), FIND_THREADS, 0, view_of(col), (const uint8_t*)d_needle->ptr, m, starts, ends, out.dev,
+                   total.get());
+            const long long cnt = fetch(total.get());
+            out.finish();
+            return (int)cnt;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
+int custr_match_strings(const custr_column* col, const custr_column* other, uint8_t* results, int devmem)
+{
+    return guarded(
+        [&]() -> int {
+            if (!results) return -1;
+            if (!col || !other) return fail(CUSTR_ERR_ARG, "match_strings: null column");
+            const int32_t n = col->n;
+            if (n == 0) return 0;
+            if (other->n != n) return fail(CUSTR_ERR_INVALID, "sizes must match");
+            Scratch<unsigned long long> total(1);
+            CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
+            ResultBuf<uint8_t> out(results, n, devmem);
+            LAUNCH(k_match_strings, row_grid(n, FIND_THREADS), FIND_THREADS, 0, view_of(col), view_of(other), out.dev, total.get());
+            const long long cnt = fetch(total.get());
+            out.finish();
+            return (int)cnt;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
 int custr_contains(const custr_column* col, const char* str, uint8_t* results, int devmem)
 {
     return guarded([&] { return find_family(col, str, 0, -1, FM_CONTAINS, nullptr, results, devmem, -1); }, (int)CUSTR_ERR_ARG,

@@ -246,6 +246,58 @@ k_vm_replace(ColView col, const uint8_t* __restrict__ img, int img_bytes, const 
     }
 }
 
+// replace_backref.cu:36-118 — every match is replaced by the template with its back-references filled in.  refs[j] =
+// (group number, byte position inside the template with the \N markers removed); group 0 is the whole match, a group that
+// did not take part (or does not exist) contributes nothing.  Pass 1 (out_chars == nullptr) sizes, pass 2 writes.
+template <int CAP>
+__global__ void __launch_bounds__(VM_THREADS)
+k_vm_backrefs(ColView col, const uint8_t* __restrict__ img, int img_bytes, const uint8_t* __restrict__ uflags, const char* __restrict__ tmpl,
+              int tmpl_len, const int2* __restrict__ refs, int nrefs, int32_t* __restrict__ out_len, const int32_t* __restrict__ out_off,
+              char* __restrict__ out_chars)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    rxdev::DevProg P = rxdev::bind_program(stage_program(img, img_bytes, smem), uflags);
+    rxdev::Lists<CAP> L;
+    rxdev::Lists<CAP, true> LG;
+    L.init();
+    LG.init();
+    for (int base = blockIdx.x * blockDim.x; base < col.n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        if (i >= col.n) continue;
+        if (!col.valid(i)) { if (!out_chars) out_len[i] = 0; continue; }
+        const int b = col.offsets[i], n = col.offsets[i + 1] - b;
+        const uint8_t* s = (const uint8_t*)col.chars + b;
+        char* o = out_chars ? out_chars + out_off[i] : nullptr;
+        int total = 0, lpos = 0, begin = 0;
+        auto put = [&](const char* src, int len) {
+            total += len;
+            if (o) for (int k = 0; k < len; ++k) *o++ = src[k];
+        };
+        while (begin <= n) {
+            int mb = 0, me = 0;
+            if (!rxdev::vm_find<CAP>(P, s, n, begin, n, mb, me, L)) break;
+            put((const char*)s + lpos, mb - lpos);
+            int ilpos = 0;
+            for (int j = 0; j < nrefs; ++j) {
+                put(tmpl + ilpos, refs[j].y - ilpos);
+                ilpos = refs[j].y;
+                int gb = mb, ge = me;
+                if (refs[j].x > 0) {
+                    gb = ge = -1;
+                    if (!rxdev::vm_find<CAP, true>(P, s, n, mb, mb + 1, gb, ge, LG, refs[j].x)) continue;
+                }
+                if (gb >= 0 && ge > gb) put((const char*)s + gb, ge - gb);
+            }
+            put(tmpl + ilpos, tmpl_len - ilpos);
+            lpos = me;
+            // (the reference never terminates on an empty match, replace_backref.cu:101; step over one character instead)
+            begin = me > mb ? me : me + (me < n ? utf8_width(s[me]) : 1);
+        }
+        put((const char*)s + lpos, n - lpos);
+        if (!out_chars) out_len[i] = total;
+    }
+}
+
 // replace_multi.cu:40-106 — at every character position try each program anchored there, first hit wins
 struct MultiProgs {
     const uint8_t* const* images;  // device array of device images
@@ -908,6 +960,51 @@ custr_column* custr_replace_re(const custr_column* col, const char* pattern, con
                          (int32_t*)nullptr, (const int32_t*)off->ptr, (char*)chars->ptr);
             g_last_tier = "pikevm";
             CUSTR_CUDA(cudaStreamSynchronize(g_stream));  // d_repl / lens die with this scope
+            return make_column(chars, off, copy_validity(col), n, col->nulls, total);
+        },
+        (custr_column*)nullptr, (custr_column*)nullptr);
+}
+
+custr_column* custr_replace_with_backrefs(const custr_column* col, const char* pattern, const char* repl)
+{
+    return guarded(
+        [&]() -> custr_column* {
+            if (!col) throw ArgError{fail(CUSTR_ERR_ARG, "replace_with_backrefs: null column")};
+            if (!pattern || !*pattern) throw ArgError{fail(CUSTR_ERR_INVALID, "nvstrings::replace_with_backrefs parameter cannot be null or empty")};
+            const int32_t n = col->n;
+            if (n == 0) return custr_create_from_offsets(nullptr, 0, nullptr, nullptr, 0, 0);
+            if (!repl) return all_null_column(n);  // replace_backref.cu:127-128
+            // template parse (regex/backref.h:31-57): every backslash followed by digits is a reference
+            std::string tmpl;
+            std::vector<int2> refs;
+            for (const char* p = repl; *p;) {
+                if (*p == '\\' && p[1] >= '0' && p[1] <= '9') {
+                    char* endp = nullptr;
+                    long idx = strtol(p + 1, &endp, 10);
+                    refs.push_back(make_int2((int)(idx > 0x7fffffffL ? 0x7fffffff : idx), (int)tmpl.size()));
+                    p = endp;
+                } else
+                    tmpl.push_back(*p++);
+            }
+            CompiledPtr c = get_compiled(pattern);
+            const int cap = check_cap(*c, "replace_with_backrefs");
+            BufPtr d_tmpl = upload(tmpl.data(), tmpl.size() ? tmpl.size() : 1);
+            int2 none = make_int2(0, 0);
+            BufPtr d_refs = upload(refs.empty() ? &none : refs.data(), sizeof(int2) * (refs.empty() ? 1 : refs.size()));
+            Scratch<int32_t> lens((size_t)n + 1);
+            CUSTR_CUDA(cudaMemsetAsync(lens.get() + n, 0, sizeof(int32_t), g_stream));
+            DISPATCH_CAP(cap, k_vm_backrefs, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr, (int)c->image.size(),
+                         device_unicode_flags(), (const char*)d_tmpl->ptr, (int)tmpl.size(), (const int2*)d_refs->ptr, (int)refs.size(), lens.get(),
+                         (const int32_t*)nullptr, (char*)nullptr);
+            BufPtr off;
+            int64_t total = 0;
+            finish_replace(col, lens, off, total);
+            BufPtr chars = dev_alloc((size_t)total);
+            DISPATCH_CAP(cap, k_vm_backrefs, vm_grid(n), smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr, (int)c->image.size(),
+                         device_unicode_flags(), (const char*)d_tmpl->ptr, (int)tmpl.size(), (const int2*)d_refs->ptr, (int)refs.size(),
+                         (int32_t*)nullptr, (const int32_t*)off->ptr, (char*)chars->ptr);
+            g_last_tier = "pikevm";
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
             return make_column(chars, off, copy_validity(col), n, col->nulls, total);
         },
         (custr_column*)nullptr, (custr_column*)nullptr);

@@ -195,6 +195,81 @@ struct WsWalk {
     }
 };
 
+// ---- right-to-left splits ------------------------------------------------------------------------------------
+// rsplit(delimiter): tokens numbered left to right, found from the right (split.cu:1003-1030 column pick,
+// custring_view.inl:1281-1336 record form; both produce the same pieces).  f(k, begin, end).
+template <typename F>
+CUSTR_HD void rsplit_walk(const uint8_t* s, int n, const uint8_t* d, int m, int dcount, F f)
+{
+    int epos = n;
+    for (int c = dcount - 1; c > 0; --c) {
+        const int p = m > 0 ? rfind_bytes(s, 0, epos, d, m) : -1;
+        if (p < 0) {  // search failed early: every remaining column repeats the remainder (split.cu:1008-1012)
+            for (int k = c; k > 0; --k) f(k, 0, epos);
+            break;
+        }
+        f(c, p + m, epos);
+        epos = p;
+    }
+    f(0, 0, epos);
+}
+
+// rsplit_record(whitespace) (split.cu:563-596,655-686): the scan runs right to left over whitespace (<= ' ') runs; with
+// a token limit the leftmost piece is the untrimmed remainder [0, epos).  A row without tokens yields one EMPTY string.
+template <typename F>
+CUSTR_HD void rwsplit_record_walk(const uint8_t* s, int n, int dcount, int limit, F f)
+{
+    int sidx = dcount - 1, epos = n;
+    bool spaces = true;
+    for (int pos = n; pos > 0 && sidx >= 0; --pos) {
+        const bool sp = s[pos - 1] <= ' ';
+        if (spaces == sp) {
+            if (spaces) epos = pos - 1;
+            continue;
+        }
+        if (!spaces) {
+            if (dcount - sidx == limit) break;
+            f(sidx--, pos, epos);
+            epos = pos - 1;
+        }
+        spaces = !spaces;
+    }
+    if (sidx >= 0) {
+        if (epos > 0) f(sidx, 0, epos);
+        else f(sidx, 0, 0);
+        --sidx;
+    }
+    for (; sidx >= 0; --sidx) f(sidx, 0, 0);
+}
+
+// rsplit(whitespace) column pick (split.cu:1098-1137), evaluated for one column `col` of `ncols`: false = null entry.
+// (The limit test uses the column count of the whole call, not the row's own token count — kept as is.)
+CUSTR_HD bool rwsplit_column(const uint8_t* s, int n, int dcount, int ncols, int limit, int col, int& b, int& e)
+{
+    int c = dcount - 1, spos = 0, epos = n;
+    bool spaces = true;
+    for (int pos = n; pos > 0; --pos) {
+        const bool sp = s[pos - 1] <= ' ';
+        if (spaces == sp) {
+            if (spaces) epos = pos - 1;
+            else spos = pos - 1;
+            continue;
+        }
+        if (!spaces) {
+            spos = 0;
+            if (ncols - c == limit) break;
+            spos = pos;
+            if (c == col) break;
+            epos = pos - 1;
+            spos = 0;
+            --c;
+        }
+        spaces = !spaces;
+    }
+    if (spos < epos) { b = spos; e = epos; return true; }
+    return false;
+}
+
 // ---- tokenize (text/tokens.cu:41-121): delimiter = whitespace (null set) or any character of a set -----------
 struct DelimSet {
     const uint32_t* chars;  // packed chars; nullptr => whitespace (byte <= ' ')

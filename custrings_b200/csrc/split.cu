@@ -23,6 +23,8 @@ struct SplitParams {
     int set_count;
     int mode;                // 0 = split(delim), 1 = split(ws), 2 = tokenize
     int record;              // split_record flavour of the whitespace placeholder ("" instead of null)
+    int right;               // rsplit / rsplit_record (split.cu:435-735,960-1160)
+    int ncols;               // rsplit(whitespace): column count of the whole call (see row::rwsplit_column)
 };
 
 __device__ __forceinline__ int row_token_count(const SplitParams& P, const uint8_t* s, int n)
@@ -36,12 +38,24 @@ __device__ __forceinline__ int row_token_count(const SplitParams& P, const uint8
     return c;
 }
 
-// generic walker: calls f(k, begin, end, is_null) for each token of the row, k ascending
+// generic walker: calls f(k, begin, end, is_null) for each token of the row (k ascending, descending for the right-to-left forms)
 template <typename F>
 __device__ __forceinline__ void row_walk(const SplitParams& P, const uint8_t* s, int n, int dcount, F f)
 {
     int b, e;
-    if (P.mode == 0) {
+    if (P.right && P.mode == 0) {
+        row::rsplit_walk(s, n, P.delim, P.m, dcount, [&](int k, int tb, int te) {
+            if (tb >= te) tb = te = 0;  // empty (not null) token
+            f(k, tb, te, false);
+        });
+    } else if (P.right && P.mode == 1 && P.record) {
+        row::rwsplit_record_walk(s, n, dcount, P.limit, [&](int k, int tb, int te) { f(k, tb, te, false); });
+    } else if (P.right && P.mode == 1) {
+        for (int k = 0; k < dcount; ++k) {
+            const bool ok = row::rwsplit_column(s, n, dcount, P.ncols, P.limit, k, b, e);
+            f(k, ok ? b : 0, ok ? e : 0, !ok);
+        }
+    } else if (P.mode == 0) {
         row::SplitWalk w;
         w.init(s, n, P.delim, P.m, dcount);
         for (int k = 0; w.next(b, e); ++k) f(k, b, e, false);
@@ -81,7 +95,7 @@ k_split_lengths(ColView col, SplitParams P, const int32_t* __restrict__ counts, 
             row_walk(P, s, col.offsets[i + 1] - col.offsets[i], dcount, [&](int k, int b, int e, bool is_null) {
                 lens[(size_t)k * (n + 1) + i] = is_null ? 0 : e - b;
                 valid[(size_t)k * n + i] = !is_null;
-                wrote = k + 1;
+                wrote = wrote > k + 1 ? wrote : k + 1;
             });
         }
         for (int k = wrote; k < ncols; ++k) { lens[(size_t)k * (n + 1) + i] = 0; valid[(size_t)k * n + i] = 0; }
@@ -112,7 +126,7 @@ k_record_lengths(ColView col, SplitParams P, const int32_t* __restrict__ row_off
         if (dcount <= 0) continue;
         const uint8_t* s = (const uint8_t*)col.chars + col.offsets[i];
         int wrote = 0;
-        row_walk(P, s, col.offsets[i + 1] - col.offsets[i], dcount, [&](int k, int b, int e, bool) { tlens[first + k] = e - b; wrote = k + 1; });
+        row_walk(P, s, col.offsets[i + 1] - col.offsets[i], dcount, [&](int k, int b, int e, bool) { tlens[first + k] = e - b; wrote = wrote > k + 1 ? wrote : k + 1; });
         for (int k = wrote; k < dcount; ++k) tlens[first + k] = 0;
     }
 }
@@ -144,10 +158,11 @@ struct ParamHolder {
     BufPtr delim_buf, set_buf;
 };
 
-static void make_split_params(ParamHolder& h, const char* delimiter, int maxsplit, bool record)
+static void make_split_params(ParamHolder& h, const char* delimiter, int maxsplit, bool record, bool right = false)
 {
     h.P.limit = maxsplit > 0 ? maxsplit + 1 : 0;
     h.P.record = record;
+    h.P.right = right;
     if (!delimiter) { h.P.mode = 1; return; }
     h.P.mode = 0;
     h.P.m = (int)strlen(delimiter);
@@ -189,16 +204,17 @@ static int max_of(const int32_t* d, int n)
     return h;
 }
 
-static int split_columns(const custr_column* col, const char* delimiter, int maxsplit, custr_column** out, int cap)
+static int split_columns(const custr_column* col, const char* delimiter, int maxsplit, custr_column** out, int cap, bool right = false)
 {
     if (!col || (!out && cap > 0)) return fail(CUSTR_ERR_ARG, "split: null argument");
     int32_t n = col->n;
     if (n == 0) return 0;
     ParamHolder h;
-    make_split_params(h, delimiter, maxsplit, false);
+    make_split_params(h, delimiter, maxsplit, false, right);
     Scratch<int32_t> counts((size_t)n + 1);
     LAUNCH(k_token_counts, row_grid(n), SPLIT_THREADS, 0, view_of(col), h.P, counts.get());
     int ncols = max_of(counts.get(), n);
+    h.P.ncols = ncols;
     if (ncols == 0) {  // every row null: one all-null column (split.cu:756-757)
         if (cap > 0) out[0] = all_null_column(n);
         return 1;
@@ -256,6 +272,66 @@ static custr_column* flat_tokens(const custr_column* col, const ParamHolder& h, 
     return make_column(chars, tok_off, nullptr, (int32_t)ntok, 0, total);
 }
 
+// partition / rpartition (split.cu:1165-1262,1268-1372): three strings per row, row-major in ONE column of 3n rows:
+// [left, delimiter, right] around the first (partition) or last (rpartition) delimiter; without a delimiter
+// [row, "", ""] (partition) or ["", "", row] (rpartition); a null row gives three nulls.
+__global__ void __launch_bounds__(SPLIT_THREADS)
+k_partition(ColView col, const uint8_t* __restrict__ d, int m, int right, int32_t* __restrict__ lens, const int32_t* __restrict__ off,
+            char* __restrict__ out, uint8_t* __restrict__ valid)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < col.n; i += gridDim.x * blockDim.x) {
+        const bool ok = col.valid(i);
+        const uint8_t* s = (const uint8_t*)col.chars + col.offsets[i];
+        const int n = col.offsets[i + 1] - col.offsets[i];
+        int b[3] = {0, 0, 0}, e[3] = {0, 0, 0};
+        bool delim_piece = false;
+        if (ok) {
+            const int p = right ? row::rfind_bytes(s, 0, n, d, m) : row::find_bytes(s, 0, n, d, m);
+            if (p >= 0) { e[0] = p; delim_piece = true; b[2] = p + m; e[2] = n; }
+            else if (right) { e[2] = n; }
+            else { e[0] = n; }
+        }
+        for (int k = 0; k < 3; ++k) {
+            const int len = (k == 1) ? (delim_piece ? m : 0) : e[k] - b[k];
+            if (!out) { lens[3 * (size_t)i + k] = len; valid[3 * (size_t)i + k] = ok; }
+            else {
+                char* o = out + off[3 * (size_t)i + k];
+                if (k == 1) for (int j = 0; j < len; ++j) o[j] = (char)d[j];
+                else for (int j = 0; j < len; ++j) o[j] = (char)s[b[k] + j];
+            }
+        }
+    }
+}
+
+static custr_column* partition_rows(const custr_column* col, const char* delimiter, bool right)
+{
+    const int32_t n = col->n;
+    if (n == 0) return custr_create_from_offsets(nullptr, 0, nullptr, nullptr, 0, 0);
+    if ((int64_t)n * 3 > 0x7fffffff) throw ArgError{fail(CUSTR_ERR_INVALID, "partition: too many rows")};
+    const int m = (int)strlen(delimiter);
+    BufPtr d = upload(delimiter, m);
+    const int32_t n3 = 3 * n;
+    Scratch<int32_t> lens((size_t)n3 + 1);
+    Scratch<uint8_t> valid((size_t)n3);
+    CUSTR_CUDA(cudaMemsetAsync(lens.get() + n3, 0, 4, g_stream));
+    LAUNCH(k_partition, row_grid(n), SPLIT_THREADS, 0, view_of(col), (const uint8_t*)d->ptr, m, right ? 1 : 0, lens.get(), (const int32_t*)nullptr,
+           (char*)nullptr, valid.get());
+    BufPtr off = dev_alloc(sizeof(int32_t) * (size_t)(n3 + 1));
+    const int64_t total = scan_lengths_to_offsets(lens.get(), (int32_t*)off->ptr, n3);
+    BufPtr chars = dev_alloc((size_t)total);
+    LAUNCH(k_partition, row_grid(n), SPLIT_THREADS, 0, view_of(col), (const uint8_t*)d->ptr, m, right ? 1 : 0, (int32_t*)nullptr,
+           (const int32_t*)off->ptr, (char*)chars->ptr, (uint8_t*)nullptr);
+    BufPtr bits;
+    int32_t nulls = 0;
+    if (col->nulls) {
+        bits = dev_alloc((n3 + 7) / 8);
+        pack_bits(valid.get(), (uint8_t*)bits->ptr, n3);
+        nulls = 3 * col->nulls;
+    }
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    return make_column(chars, off, bits, n3, nulls, total);
+}
+
 }  // namespace custr
 
 using namespace custr;
@@ -267,9 +343,9 @@ int custr_split(const custr_column* col, const char* delimiter, int32_t maxsplit
     return guarded([&] { return split_columns(col, delimiter, maxsplit, out, cap); }, (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
 }
 
-int custr_rsplit(const custr_column*, const char*, int32_t, custr_column**, int32_t)
+int custr_rsplit(const custr_column* col, const char* delimiter, int32_t maxsplit, custr_column** out, int32_t cap)
 {
-    return fail(CUSTR_ERR_INVALID, "rsplit: not implemented yet (SURVEY.md section 8f, 'next' row)");
+    return guarded([&] { return split_columns(col, delimiter, maxsplit, out, cap, true); }, (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
 }
 
 int custr_split_record(const custr_column* col, const char* delimiter, int32_t maxsplit, custr_column** tokens, int32_t* row_offsets,
@@ -287,9 +363,30 @@ int custr_split_record(const custr_column* col, const char* delimiter, int32_t m
         (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
 }
 
-int custr_rsplit_record(const custr_column*, const char*, int32_t, custr_column**, int32_t*, int)
+int custr_rsplit_record(const custr_column* col, const char* delimiter, int32_t maxsplit, custr_column** tokens, int32_t* row_offsets,
+                        int devmem)
 {
-    return fail(CUSTR_ERR_INVALID, "rsplit_record: not implemented yet (SURVEY.md section 8f, 'next' row)");
+    return guarded(
+        [&]() -> int {
+            if (!col || !tokens) return fail(CUSTR_ERR_ARG, "rsplit_record: null argument");
+            ParamHolder h;
+            make_split_params(h, delimiter, maxsplit, true, true);
+            int total = 0;
+            *tokens = flat_tokens(col, h, row_offsets, devmem, &total);
+            return total;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
+custr_column* custr_partition(const custr_column* col, const char* delimiter, int right)
+{
+    return guarded(
+        [&]() -> custr_column* {
+            if (!col) throw ArgError{fail(CUSTR_ERR_ARG, "partition: null column")};
+            if (!delimiter || !*delimiter) throw ArgError{fail(CUSTR_ERR_INVALID, "partition: delimiter is null or empty")};
+            return partition_rows(col, delimiter, right != 0);
+        },
+        (custr_column*)nullptr, (custr_column*)nullptr);
 }
 
 custr_column* custr_tokenize(const custr_column* col, const char* delimiter)

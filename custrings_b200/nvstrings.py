@@ -264,6 +264,14 @@ class nvstrings:
         h = fn(self.m_cptr, _enc(pat), _enc(repl), int(n))
         return nvstrings(check_handle(h, "replace"))
 
+    def replace_with_backrefs(self, pat, repl):
+        """Replace every match of `pat` by `repl` with its \\1..\\N back-references filled in from the capture groups.
+        reference nvstrings.py:1540 -> replace_backref.cu:122"""
+        if pat is None or pat == "":
+            raise ValueError("replace_with_backrefs: pattern cannot be null or empty")
+        h = lib().custr_replace_with_backrefs(self.m_cptr, _enc(pat), _enc(repl))
+        return nvstrings(check_handle(h, "replace_with_backrefs"))
+
     def replace_multi(self, pats, repls, regex=True):
         """reference nvstrings.py:1487 -> replace_multi.cu:110 (regex) / modify.cu:263 (literal)"""
         if isinstance(repls, str):
@@ -338,6 +346,31 @@ class nvstrings:
         """reference nvstrings.py:2073"""
         return self._host_result(lib().custr_endswith, np.uint8, devptr, "endswith", None, True, _enc(pat))
 
+    def find_from(self, sub, starts=None, ends=None, devptr=0):
+        """find() with per-row start / end character positions (host int32 sequences here; device pointers together with
+        devptr).  reference nvstrings.py:1829 -> find.cu:123-160"""
+        n = self.size()
+        if devptr:
+            check_rc(lib().custr_find_from(self.m_cptr, _enc(sub), as_ptr(starts) if starts else None, as_ptr(ends) if ends else None,
+                                           as_ptr(devptr), 1), "find_from")
+            return devptr
+        hs = None if starts is None else np.ascontiguousarray(starts, np.int32)
+        he = None if ends is None else np.ascontiguousarray(ends, np.int32)
+        out = np.zeros(max(n, 1), np.int32)
+        check_rc(lib().custr_find_from(self.m_cptr, _enc(sub), None if hs is None else as_ptr(hs), None if he is None else as_ptr(he),
+                                       as_ptr(out), 0), "find_from")
+        return [None if v < -1 else int(v) for v in out[:n]]
+
+    def match_strings(self, strs, devptr=0):
+        """Row-wise equality with another nvstrings of the same size.  reference nvstrings.py:2018 -> find.cu:276-313"""
+        n = self.size()
+        if devptr:
+            check_rc(lib().custr_match_strings(self.m_cptr, strs.m_cptr, as_ptr(devptr), 1), "match_strings")
+            return devptr
+        out = np.zeros(max(n, 1), np.uint8)
+        check_rc(lib().custr_match_strings(self.m_cptr, strs.m_cptr, as_ptr(out), 0), "match_strings")
+        return [bool(v) for v in out[:n]]
+
     def find_multiple(self, strs, devptr=0):
         """reference nvstrings.py:2550: one row of positions per string"""
         n, m = self.size(), strs.size()
@@ -396,6 +429,30 @@ class nvstrings:
     def rsplit_record(self, delimiter=None, n=-1):
         """reference nvstrings.py:969"""
         return self._split_record(lib().custr_rsplit_record, delimiter, n, "rsplit_record")
+
+    def _partition(self, delimiter, right, what):
+        if delimiter is None or delimiter == "" or delimiter == b"":
+            return []  # reference returns without results (split.cu:1167-1171)
+        h = lib().custr_partition(self.m_cptr, _enc(delimiter), 1 if right else 0)
+        flat = nvstrings(check_handle(h, what))
+        res = []
+        for i in range(self.size()):
+            res.append(nvstrings(check_handle(lib().custr_slice_rows(flat.m_cptr, 3 * i, 3 * i + 3), what)))
+        return res
+
+    def partition(self, delimiter=" "):
+        """One nvstrings of 3 strings per row: [left, delimiter, right] around the first delimiter ([row, '', ''] when it
+        does not occur, three nulls for a null row).  reference nvstrings.py:1127 -> split.cu:1165-1262"""
+        return self._partition(delimiter, False, "partition")
+
+    def rpartition(self, delimiter=" "):
+        """Same around the LAST delimiter (['', '', row] when it does not occur).  reference nvstrings.py:1163 -> split.cu:1268-1372"""
+        return self._partition(delimiter, True, "rpartition")
+
+    def partition_flat(self, delimiter=" ", right=False):
+        """The 3n-row column partition()/rpartition() are views of."""
+        h = lib().custr_partition(self.m_cptr, _enc(delimiter), 1 if right else 0)
+        return nvstrings(check_handle(h, "partition"))
 
     def split_record_flat(self, delimiter=None, n=-1, right=False):
         """(tokens nvstrings, row_offsets int32[n+1]) — the flat form split_record is built on."""

@@ -90,6 +90,10 @@ int custr_count_re(const custr_column* col, const char* pattern, int32_t* result
 custr_column* custr_replace_re(const custr_column* col, const char* pattern, const char* repl, int32_t maxrepl);
 custr_column* custr_replace_re_multi(const custr_column* col, const char* const* patterns, int32_t npatterns,
                                      const custr_column* repls);
+/* NVStrings::replace_with_backrefs replace_backref.cu:122-213 (template parse regex/backref.h:31-57): every match is replaced
+ * by `repl` with \1..\N substituted by the text of that capture group (\0 = whole match, unmatched / unknown group = nothing).
+ * repl == NULL gives an all-null column; a NULL / empty pattern is INVALID. */
+custr_column* custr_replace_with_backrefs(const custr_column* col, const char* pattern, const char* repl);
 /* Capture-span callers ("next" rows of the scope table): NVStrings::findall findall.cu:99-170 (column c = c-th match of each
  * row, null where a row has fewer), findall_record findall_record.cu:97 (flat: all matches in row order + row offsets),
  * extract extract.cu:69-150 (one column per capture group of the FIRST match; null when the row does not match or the group
@@ -107,6 +111,11 @@ int custr_rfind(const custr_column* col, const char* str, int32_t start, int32_t
 int custr_contains(const custr_column* col, const char* str, uint8_t* results, int devmem);
 int custr_startswith(const custr_column* col, const char* str, uint8_t* results, int devmem);
 int custr_endswith(const custr_column* col, const char* str, uint8_t* results, int devmem);
+/* NVStrings::find_from find.cu:123-160: per-row start / end character positions (NULL = 0 / end of string); the arrays live
+ * where `devmem` says (the reference takes device pointers only).  NVStrings::match_strings find.cu:276-313: row-wise
+ * equality with another column of the same size (two nulls are equal); returns the number of equal rows. */
+int custr_find_from(const custr_column* col, const char* str, const int32_t* starts, const int32_t* ends, int32_t* results, int devmem);
+int custr_match_strings(const custr_column* col, const custr_column* other, uint8_t* results, int devmem);
 int custr_find_multiple(const custr_column* col, const custr_column* targets, int32_t* results, int devmem);
 custr_column* custr_replace(const custr_column* col, const char* str, const char* repl, int32_t maxrepl);
 custr_column* custr_replace_multi(const custr_column* col, const custr_column* targets, const custr_column* repls);
@@ -124,6 +133,10 @@ int custr_split_record(const custr_column* col, const char* delimiter, int32_t m
                        int32_t* row_offsets, int devmem);
 int custr_rsplit_record(const custr_column* col, const char* delimiter, int32_t maxsplit, custr_column** tokens,
                         int32_t* row_offsets, int devmem);
+/* NVStrings::partition split.cu:1165-1262 / rpartition :1268-1372 (right != 0): three strings per row — [left, delimiter,
+ * right] around the first / last delimiter, [row, "", ""] / ["", "", row] when it does not occur, three nulls for a null
+ * row — returned row-major as ONE column of 3n rows instead of n objects.  NULL on error (empty delimiter: INVALID). */
+custr_column* custr_partition(const custr_column* col, const char* delimiter, int right);
 /* sub-range view [first, last) of a column as a new column (used to materialise one row of split_record). */
 custr_column* custr_slice_rows(const custr_column* col, int32_t first, int32_t last);
 /* gather rows by index (device or host int32 indices; negative/out-of-range -> null row). */

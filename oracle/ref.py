@@ -29,7 +29,7 @@ def lib():
         L = C.CDLL(_SO)
         vp, ci, cp = C.c_void_p, C.c_int, C.c_char_p
         L.ref_last_error.restype = cp
-        for name in ("ref_create", "ref_create_from_array", "ref_replace_re", "ref_replace_re_multi", "ref_replace",
+        for name in ("ref_create", "ref_create_from_array", "ref_replace_re", "ref_replace_re_multi", "ref_replace", "ref_replace_with_backrefs",
                      "ref_replace_multi", "ref_tokenize", "ref_tokenize_multi", "ref_cat_create", "ref_cat_create_multi",
                      "ref_cat_keys", "ref_cat_to_strings"):
             getattr(L, name).restype = vp
@@ -43,11 +43,14 @@ def lib():
         for name in ("ref_contains_re", "ref_match", "ref_count_re", "ref_contains", "ref_startswith", "ref_endswith"):
             getattr(L, name).argtypes = [vp, cp, vp]
         L.ref_replace_re.argtypes = [vp, cp, cp, ci]
+        L.ref_replace_with_backrefs.argtypes = [vp, cp, cp]
         L.ref_replace_re_multi.argtypes = [vp, vp, ci, vp]
         L.ref_replace.argtypes = [vp, cp, cp, ci]
         L.ref_replace_multi.argtypes = [vp, vp, vp]
         L.ref_find.argtypes = [vp, cp, ci, ci, vp]
         L.ref_rfind.argtypes = [vp, cp, ci, ci, vp]
+        L.ref_find_from.argtypes = [vp, cp, vp, vp, vp]
+        L.ref_match_strings.argtypes = [vp, vp, vp]
         L.ref_find_multiple.argtypes = [vp, vp, vp]
         L.ref_split.argtypes = [vp, cp, ci, ci, vp, ci]
         L.ref_split_record.argtypes = [vp, cp, ci, ci, vp]
@@ -179,6 +182,18 @@ class RefStrings:
     def hash(self): return self._rows(lib().ref_hash, np.uint32)
     def token_count(self, delim=None): return self._rows(lib().ref_token_count, np.uint32, _b(delim))
 
+    def find_from(self, s, starts=None, ends=None):
+        hs = None if starts is None else np.ascontiguousarray(starts, np.int32)
+        he = None if ends is None else np.ascontiguousarray(ends, np.int32)
+        out = np.zeros(max(self.size(), 1), np.int32)
+        rc = lib().ref_find_from(self.h, _b(s), None if hs is None else _ptr(hs), None if he is None else _ptr(he), _ptr(out))
+        return out[: self.size()], rc
+
+    def match_strings(self, other):
+        out = np.zeros(max(self.size(), 1), np.bool_)
+        rc = lib().ref_match_strings(self.h, other.h, _ptr(out))
+        return out[: self.size()], rc
+
     def find_multiple(self, targets):
         out = np.zeros(max(self.size() * targets.size(), 1), np.int32)
         rc = lib().ref_find_multiple(self.h, targets.h, _ptr(out))
@@ -187,6 +202,12 @@ class RefStrings:
     # ---- column results
     def replace_re(self, pat, repl, maxrepl=-1):
         return RefStrings(lib().ref_replace_re(self.h, _b(pat), _b(repl), maxrepl))
+
+    def replace_with_backrefs(self, pat, repl):
+        h = lib().ref_replace_with_backrefs(self.h, _b(pat), _b(repl))
+        if not h:
+            raise ValueError(lib().ref_last_error().decode())
+        return RefStrings(h)
 
     def replace_re_multi(self, pats, repls):
         arr = (C.c_char_p * len(pats))(*[_b(p) for p in pats])

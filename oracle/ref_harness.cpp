@@ -74,6 +74,10 @@ void* ref_replace_re_multi(void* h, const char** pats, int npats, void* repls)
     std::vector<const char*> v(pats, pats + npats);
     GUARD(return ((NVStrings*)h)->replace_re(v, *(NVStrings*)repls), nullptr);
 }
+void* ref_replace_with_backrefs(void* h, const char* pat, const char* repl)
+{
+    GUARD(return ((NVStrings*)h)->replace_with_backrefs(pat, repl), nullptr);
+}
 void* ref_replace(void* h, const char* str, const char* repl, int maxrepl)
 {
     GUARD(return ((NVStrings*)h)->replace(str, repl, maxrepl), nullptr);
@@ -84,6 +88,8 @@ void* ref_replace_multi(void* h, void* tgts, void* repls)
 }
 
 int ref_find(void* h, const char* str, int start, int end, int* out) { GUARD(return (int)((NVStrings*)h)->find(str, start, end, out, false), -100); }
+int ref_find_from(void* h, const char* str, int* starts, int* ends, int* out) { GUARD(return (int)((NVStrings*)h)->find_from(str, starts, ends, out, false), -100); }
+int ref_match_strings(void* h, void* other, bool* out) { GUARD(return ((NVStrings*)h)->match_strings(*(NVStrings*)other, out, false), -100); }
 int ref_rfind(void* h, const char* str, int start, int end, int* out) { GUARD(return (int)((NVStrings*)h)->rfind(str, start, end, out, false), -100); }
 int ref_contains(void* h, const char* str, bool* out) { GUARD(return ((NVStrings*)h)->contains(str, out, false), -100); }
 int ref_startswith(void* h, const char* str, bool* out) { GUARD(return (int)((NVStrings*)h)->startswith(str, out, false), -100); }

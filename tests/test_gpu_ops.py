@@ -84,6 +84,57 @@ def test_split_record(cols, oracle):
     assert rows[14] is None and rows[0].to_host() == ["abc de"]
 
 
+def test_rsplit_columns_and_records(cols, oracle):
+    strs, dev, ref = cols
+    for d, mx in ((",", -1), (",", 1), (" ", -1), (" ", 2), ("::", -1), ("::", 1), (None, -1), (None, 1), (None, 2), (None, 3), ("é", -1),
+                  ("é", 1), ("zzz", -1)):
+        want = [c.to_list() for c in ref.split(d, mx, right=True)]
+        got = [oracle.unpack(*c.to_arrays()) for c in dev.rsplit(d, mx)]
+        assert got == want, ("rsplit", d, mx)
+        want_rows, want_total = ref.split_record(d, mx, right=True)
+        want = [None if r is None else r.to_list() for r in want_rows]
+        tokens, row_off = dev.split_record_flat(d, mx, right=True)
+        flat = oracle.unpack(*tokens.to_arrays())
+        got = [None if s is None else flat[row_off[i]:row_off[i + 1]] for i, s in enumerate(strs)]
+        assert got == want, ("rsplit_record", d, mx)
+        assert tokens.size() == want_total
+
+
+def test_find_from_and_match_strings(cols, oracle):
+    from custrings_b200 import nvstrings
+    strs, dev, ref = cols
+    rng = random.Random(3)
+    n = len(strs)
+    starts = [rng.randrange(0, 6) for _ in range(n)]
+    ends = [st + rng.randrange(0, 12) for st in starts]
+    for sub in ("a", "é", "b", " ", "de"):
+        want, wrc = ref.find_from(sub, starts, ends)
+        assert dev.find_from(sub, starts, ends) == [None if v == -2 else int(v) for v in want], sub
+        want, _ = ref.find_from(sub, starts, None)
+        assert dev.find_from(sub, starts, None) == [None if v == -2 else int(v) for v in want], sub
+        want, _ = ref.find_from(sub, None, None)
+        assert dev.find_from(sub) == [None if v == -2 else int(v) for v in want], sub
+    other = list(strs)
+    for k in range(0, n, 3):
+        other[k] = rng.choice(["abc de", None, "", "x"])
+    want, wrc = ref.match_strings(oracle.RefStrings.from_list(other))
+    assert dev.match_strings(nvstrings.to_device(other)) == [bool(v) for v in want]
+
+
+def test_partition(cols, oracle):
+    strs, dev, ref = cols
+    for d in (",", " ", "::", "é", "zzz", "a"):
+        for right in (False, True):
+            want_rows, _ = ref.partition(d, right)
+            want = [None if r is None else r.to_list() for r in want_rows]
+            flat = oracle.unpack(*dev.partition_flat(d, right).to_arrays())
+            got = [flat[3 * i:3 * i + 3] for i in range(len(strs))]
+            assert got == want, (d, right)
+    rows = dev.partition(",")
+    assert len(rows) == len(strs) and rows[0].to_host() == ["abc de", "", ""]
+    assert dev.rpartition(" ")[0].to_host() == ["abc", " ", "de"]
+
+
 def test_tokenize(cols, oracle):
     from custrings_b200 import nvtext
     strs, dev, ref = cols

@@ -103,6 +103,17 @@ def test_findall_extract_capture_spans(cols, oracle):
     assert dev.extract(r"\d+") == []  # no capture groups -> no columns (extract.cu:96-100)
 
 
+def test_replace_with_backrefs(cols, oracle):
+    strs, dev, ref = cols
+    cases = [(r"([a-z])-([a-z])", r"X\1+\2Z"), (r"(\w)(\w)", r"\2\1"), (r"(\w+) (\w+)", r"[\2|\1]"), (r"([a-z])([0-9])", r"\0!"),
+             (r"(\d+)", r"<\1>"), (r"(a)|(b)", r"<\1\2>"), (r"(\w+)@(\w+)", r"\2 at \1"), (r"(é)(.)", r"\2\1"), (r"(\w)(\w)?", r"\2-\3-\12"),
+             (r"\b(\w)(\w*)\b", r"\2\1ay"), (r"(l+)", "none"), (r"(a(b)?)", r"[\2]")]
+    for p, repl in cases:
+        want = ref.replace_with_backrefs(p, repl).to_list()
+        got = oracle.unpack(*dev.replace_with_backrefs(p, repl).to_arrays())
+        assert got == want, (p, repl)
+
+
 def test_rows_with_nul_bytes_fall_back_exactly(oracle):
     from custrings_b200 import nvstrings
     from custrings_b200._lib import lib
