@@ -98,6 +98,10 @@ NVStrings* NVStrings::replace_re(const char* pattern, const char* repl, int maxr
 {
     return new NVStrings(checked(custr_replace_re(col_, pattern, repl, maxrepl)));
 }
+NVStrings* NVStrings::replace_with_backrefs(const char* pattern, const char* repl)
+{
+    return new NVStrings(checked(custr_replace_with_backrefs(col_, pattern, repl)));
+}
 NVStrings* NVStrings::replace_re(std::vector<const char*>& patterns, NVStrings& repls)
 {
     return new NVStrings(checked(custr_replace_re_multi(col_, patterns.data(), (int)patterns.size(), repls.col_)));
@@ -149,6 +153,14 @@ unsigned int NVStrings::rfind(const char* str, int start, int end, int* results,
 {
     return (unsigned)checked(custr_rfind(col_, str, start, end, results, devmem));
 }
+unsigned int NVStrings::find_from(const char* str, int* starts, int* ends, int* results, bool devmem)
+{
+    return (unsigned)checked(custr_find_from(col_, str, starts, ends, results, devmem));
+}
+int NVStrings::match_strings(NVStrings& strs, bool* results, bool devmem)
+{
+    return checked(custr_match_strings(col_, strs.col_, (uint8_t*)results, devmem));
+}
 unsigned int NVStrings::find_multiple(NVStrings& strs, int* results, bool devmem)
 {
     return (unsigned)checked(custr_find_multiple(col_, strs.col_, results, devmem));
@@ -174,12 +186,25 @@ NVStrings* NVStrings::replace(NVStrings& strs, NVStrings& repls)
     return new NVStrings(checked(custr_replace_multi(col_, strs.col_, repls.col_)));
 }
 
+typedef int (*RecordFn)(const custr_column*, const char*, int32_t, custr_column**, int32_t*, int);
+typedef int (*ColumnsFn)(const custr_column*, const char*, int32_t, custr_column**, int32_t);
+
 int NVStrings::split_record(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results)
+{
+    return record_split_(delimiter, maxsplit, results, false);
+}
+int NVStrings::rsplit_record(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results)
+{
+    return record_split_(delimiter, maxsplit, results, true);
+}
+int NVStrings::rsplit_record(int maxsplit, std::vector<NVStrings*>& results) { return rsplit_record(nullptr, maxsplit, results); }
+int NVStrings::record_split_(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results, bool right)
 {
     unsigned n = size();
     custr_column* tokens = nullptr;
     std::vector<int> row_off(n + 1, 0);
-    int total = checked(custr_split_record(col_, delimiter, maxsplit, &tokens, row_off.data(), 0));
+    RecordFn fn = right ? custr_rsplit_record : custr_split_record;
+    int total = checked(fn(col_, delimiter, maxsplit, &tokens, row_off.data(), 0));
     checked(tokens);
     std::vector<unsigned char> val((n + 7) / 8 + 1);
     if (n) custr_set_null_bitarray(col_, val.data(), 0, 0);
@@ -194,10 +219,31 @@ int NVStrings::split_record(int maxsplit, std::vector<NVStrings*>& results) { re
 
 unsigned int NVStrings::split(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results)
 {
+    return column_split_(delimiter, maxsplit, results, false);
+}
+unsigned int NVStrings::rsplit(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results)
+{
+    return column_split_(delimiter, maxsplit, results, true);
+}
+unsigned int NVStrings::rsplit(int maxsplit, std::vector<NVStrings*>& results) { return rsplit(nullptr, maxsplit, results); }
+int NVStrings::partition_(const char* delimiter, std::vector<NVStrings*>& results, bool right)
+{
+    if (!delimiter || !*delimiter) return 0;  // split.cu:1167-1171
+    custr_column* flat = checked(custr_partition(col_, delimiter, right ? 1 : 0));
+    const unsigned n = size();
+    for (unsigned i = 0; i < n; ++i) results.push_back(new NVStrings(checked(custr_slice_rows(flat, 3 * (int)i, 3 * (int)i + 3))));
+    custr_column_free(flat);
+    return (int)n;
+}
+int NVStrings::partition(const char* delimiter, std::vector<NVStrings*>& results) { return partition_(delimiter, results, false); }
+int NVStrings::rpartition(const char* delimiter, std::vector<NVStrings*>& results) { return partition_(delimiter, results, true); }
+unsigned int NVStrings::column_split_(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results, bool right)
+{
     int cap = 64;
+    ColumnsFn fn = right ? custr_rsplit : custr_split;
     for (;;) {
         std::vector<custr_column*> out((size_t)cap, nullptr);
-        int cols = checked(custr_split(col_, delimiter, maxsplit, out.data(), cap));
+        int cols = checked(fn(col_, delimiter, maxsplit, out.data(), cap));
         if (cols <= cap) {
             for (int c = 0; c < cols; ++c) results.push_back(new NVStrings(out[c]));
             return (unsigned)results.size();

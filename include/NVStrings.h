@@ -42,6 +42,7 @@ public:
     int count_re(const char* pattern, int* results, bool devmem = true);                                // :981
     NVStrings* replace_re(const char* pattern, const char* repl, int maxrepl = -1);                     // :766
     NVStrings* replace_re(std::vector<const char*>& patterns, NVStrings& repls);                        // :779
+    NVStrings* replace_with_backrefs(const char* pattern, const char* repl);     // :793  replace_backref.cu:122
 
     // capture-span callers ("next" rows): findall.cu:99, findall_record.cu:97, extract.cu:69
     int findall(const char* pattern, std::vector<NVStrings*>& results);          // :943  column c = c-th match of each row
@@ -51,7 +52,9 @@ public:
     // literal: find.cu:75-387, modify.cu:109-299
     unsigned int find(const char* str, int start, int end, int* results, bool devmem = true);           // :861
     unsigned int rfind(const char* str, int start, int end, int* results, bool devmem = true);          // :873
+    unsigned int find_from(const char* str, int* starts, int* ends, int* results, bool devmem = true);  // :885  (starts/ends live where devmem says)
     unsigned int find_multiple(NVStrings& strs, int* results, bool devmem = true);                      // :898
+    int match_strings(NVStrings& strs, bool* results, bool devmem = true);                              // :916
     int contains(const char* str, bool* results, bool devmem = true);                                   // :907
     unsigned int startswith(const char* str, bool* results, bool devmem = true);                        // :925
     unsigned int endswith(const char* str, bool* results, bool devmem = true);                          // :934
@@ -64,9 +67,21 @@ public:
     int split_record(int maxsplit, std::vector<NVStrings*>& results);                                   // :484
     unsigned int split(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results);          // :504
     unsigned int split(int maxsplit, std::vector<NVStrings*>& results);                                 // :524
+    int rsplit_record(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results);          // :474
+    int rsplit_record(int maxsplit, std::vector<NVStrings*>& results);                                  // :494
+    unsigned int rsplit(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results);         // :514
+    unsigned int rsplit(int maxsplit, std::vector<NVStrings*>& results);                                // :534
+    // one instance of 3 strings per row (three nulls for a null row): split.cu:1165-1372
+    int partition(const char* delimiter, std::vector<NVStrings*>& results);                             // :547
+    int rpartition(const char* delimiter, std::vector<NVStrings*>& results);                            // :560
 
     NVStrings* gather(const int* pos, unsigned int count, bool devmem = true);                          // :270
     NVStrings* sublist(unsigned int start, unsigned int end, int step = 0);                             // :261
 
     custr_column* column() const { return col_; }  // escape hatch to the C-ABI handle
+
+private:
+    int record_split_(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results, bool right);
+    unsigned int column_split_(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results, bool right);
+    int partition_(const char* delimiter, std::vector<NVStrings*>& results, bool right);
 };

@@ -32,6 +32,11 @@ class OracleAPI:
     def endswith(self, c, s): return c.endswith(s)[0].tolist()
     def split(self, c, d, n): return [self.strings(x) for x in c.split(d, n)]
     def split_record(self, c, d, n): return [None if r is None else self.strings(r) for r in c.split_record(d, n)[0]]
+    def rsplit(self, c, d, n): return [self.strings(x) for x in c.split(d, n, right=True)]
+    def rsplit_record(self, c, d, n): return [None if r is None else self.strings(r) for r in c.split_record(d, n, right=True)[0]]
+    def partition(self, c, d): return [self.strings(r) for r in c.partition(d)[0]]
+    def rpartition(self, c, d): return [self.strings(r) for r in c.partition(d, right=True)[0]]
+    def replace_with_backrefs(self, c, p, r): return self.strings(c.replace_with_backrefs(p, r))
     def tokenize(self, c, d): return self.strings(c.tokenize(d))
     def token_count(self, c, d): return c.token_count(d)[0].tolist()
     def hash(self, c): return c.hash()[0].tolist()
@@ -73,6 +78,11 @@ class ProductAPI:
     def endswith(self, c, s): return self._f(c.endswith(s), False)
     def split(self, c, d, n): return [x.to_host() for x in c.split(d, n)]
     def split_record(self, c, d, n): return [None if r is None else r.to_host() for r in c.split_record(d, n)]
+    def rsplit(self, c, d, n): return [x.to_host() for x in c.rsplit(d, n)]
+    def rsplit_record(self, c, d, n): return [None if r is None else r.to_host() for r in c.rsplit_record(d, n)]
+    def partition(self, c, d): return [r.to_host() for r in c.partition(d)]
+    def rpartition(self, c, d): return [r.to_host() for r in c.rpartition(d)]
+    def replace_with_backrefs(self, c, p, r): return c.replace_with_backrefs(p, r).to_host()
     def tokenize(self, c, d): return self.nvt.tokenize(c, d).to_host()
     def token_count(self, c, d): return self.nvt.token_count(c, d)
     def hash(self, c): return self._f(c.hash(), 0)

@@ -129,6 +129,40 @@ int main()
         EXPECT(s->split_record("s", -1, rows) == 7);
         EXPECT(rows.size() == 5 && rows[1] == nullptr && same(rows[0], {"Héllo the", "é"}) && same(rows[3], {"té", "t String"}) && same(rows[4], {""}));
         for (auto r : rows) if (r) NVStrings::destroy(r);
+        // right-to-left and partition forms: test_split.cpp:24-56,86-110,158-205
+        cols.clear();
+        EXPECT(s->rsplit(-1, cols) == 2);
+        EXPECT(same(cols[0], {"Héllo", nullptr, "are", "tést", nullptr}) && same(cols[1], {"thesé", nullptr, "some", "String", nullptr}));
+        for (auto c : cols) NVStrings::destroy(c);
+        cols.clear();
+        EXPECT(s->rsplit("s", 2, cols) == 2);
+        EXPECT(same(cols[0], {"Héllo the", nullptr, "are ", "té", ""}) && same(cols[1], {"é", nullptr, "ome", "t String", nullptr}));
+        for (auto c : cols) NVStrings::destroy(c);
+        rows.clear();
+        s->rsplit_record(-1, rows);
+        EXPECT(rows.size() == 5 && rows[1] == nullptr && same(rows[0], {"Héllo", "thesé"}) && same(rows[2], {"are", "some"}) && same(rows[4], {""}));
+        for (auto r : rows) if (r) NVStrings::destroy(r);
+        rows.clear();
+        EXPECT(s->partition(" ", rows) == 5);
+        EXPECT(same(rows[0], {"Héllo", " ", "thesé"}) && same(rows[1], {nullptr, nullptr, nullptr}) && same(rows[3], {"tést", " ", "String"}) &&
+               same(rows[4], {"", "", ""}));
+        for (auto r : rows) if (r) NVStrings::destroy(r);
+        rows.clear();
+        EXPECT(s->rpartition(" ", rows) == 5);
+        EXPECT(same(rows[0], {"Héllo", " ", "thesé"}) && same(rows[1], {nullptr, nullptr, nullptr}) && same(rows[2], {"are", " ", "some"}));
+        for (auto r : rows) if (r) NVStrings::destroy(r);
+        NVStrings::destroy(s);
+    }
+    {   // test_replace.cpp:131-148
+        std::vector<const char*> h{"the quick brown fox jumps over the lazy dog", "the fat cat lays next to the other accénted cat",
+                                   "a slow moving turtlé cannot catch the bird", "which can be composéd together to form a more complete",
+                                   "thé result does not include the value in the sum in", "", "absent stop words"};
+        NVStrings* s = NVStrings::create_from_array(h.data(), h.size());
+        NVStrings* got = s->replace_with_backrefs("(\\w) (\\w)", "\\1-\\2");
+        EXPECT(same(got, {"the-quick-brown-fox-jumps-over-the-lazy-dog", "the-fat-cat-lays-next-to-the-other-accénted-cat",
+                          "a-slow-moving-turtlé-cannot-catch-the-bird", "which-can-be-composéd-together-to-form-a more-complete",
+                          "thé-result-does-not-include-the-value-in-the-sum-in", "", "absent-stop-words"}));
+        NVStrings::destroy(got);
         NVStrings::destroy(s);
     }
     {   // test_text.cu:15-39, test_convert.cu:9-23, cattest.cu

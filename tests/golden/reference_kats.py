@@ -54,6 +54,17 @@ KATS += [
     ("split", SPLIT_STRS, ("s", -1), [["Héllo the", None, "are ", "té", ""], ["é", None, "ome", "t String", None]]),      # test_split.cpp:36-41
     ("split_record", SPLIT_STRS, (None, -1), [["Héllo", "thesé"], None, ["are", "some"], ["tést", "String"], [""]]),      # test_split.cpp:62-67
     ("split_record", SPLIT_STRS, ("s", -1), [["Héllo the", "é"], None, ["are ", "ome"], ["té", "t String"], [""]]),       # test_split.cpp:100-105
+    ("rsplit", SPLIT_STRS, (None, -1), [["Héllo", None, "are", "tést", None], ["thesé", None, "some", "String", None]]),  # test_split.cpp:24-31
+    ("rsplit", SPLIT_STRS, ("s", 2), [["Héllo the", None, "are ", "té", ""], ["é", None, "ome", "t String", None]]),      # test_split.cpp:46-53
+    ("rsplit_record", SPLIT_STRS, (None, -1), [["Héllo", "thesé"], None, ["are", "some"], ["tést", "String"], [""]]),     # test_split.cpp:86-96
+    ("partition", SPLIT_STRS, (" ",),                                                                                      # test_split.cpp:158-168
+     [["Héllo", " ", "thesé"], [None, None, None], ["are", " ", "some"], ["tést", " ", "String"], ["", "", ""]]),
+    ("rpartition", SPLIT_STRS, (" ",),                                                                                     # test_split.cpp:180-190
+     [["Héllo", " ", "thesé"], [None, None, None], ["are", " ", "some"], ["tést", " ", "String"], ["", "", ""]]),
+    ("replace_with_backrefs", REPLACE_STRS, (r"(\w) (\w)", r"\1-\2"),                                                      # test_replace.cpp:131-142
+     ["the-quick-brown-fox-jumps-over-the-lazy-dog", "the-fat-cat-lays-next-to-the-other-accénted-cat",
+      "a-slow-moving-turtlé-cannot-catch-the-bird", "which-can-be-composéd-together-to-form-a more-complete",
+      "thé-result-does-not-include-the-value-in-the-sum-in", "", "absent-stop-words"]),
 ]
 
 TEXT_STRS = ["the fox jumped over the dog", "the dog chased the cat", "the cat chased the mouse", None, "",
