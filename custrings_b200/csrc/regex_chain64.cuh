@@ -197,6 +197,31 @@ __device__ __noinline__ NaClasses<NCLS> classify_non_ascii64(const ChainDev& cd,
     return r;
 }
 
+// where one lane's 64-bit words of the span streams go: this work item owns the bits of [byte_a, byte_b) — whole words
+// are stored, boundary words OR-ed into the pre-cleared streams
+struct SpanSink {
+    u64* m;
+    u64* k;
+    u64* a;
+    size_t widx;
+    int wp, byte_a, byte_b;
+};
+__device__ __noinline__ void store_spans(const SpanSink s, u64 m, u64 k, u64 a)
+{
+    if (s.wp >= s.byte_a && s.wp + 64 <= s.byte_b) {
+        s.m[s.widx] = m;
+        s.k[s.widx] = k;
+        s.a[s.widx] = a;
+    } else if (s.wp + 64 > s.byte_a && s.wp < s.byte_b) {
+        u64 mask = ~0ull;
+        if (s.wp < s.byte_a) mask &= ~0ull << (s.byte_a - s.wp);
+        if (s.wp + 64 > s.byte_b) mask &= ~0ull >> (s.wp + 64 - s.byte_b);
+        if (m & mask) atomicOr(s.m + s.widx, m & mask);
+        if (k & mask) atomicOr(s.k + s.widx, k & mask);
+        if (a & mask) atomicOr(s.a + s.widx, a & mask);
+    }
+}
+
 template <int NS>
 struct ChainState64 {  // top words of the previous window's streams (only their top bit is ever used)
     uint32_t last[NS];
@@ -208,7 +233,7 @@ struct ChainState64 {  // top words of the previous window's streams (only their
 template <int NS, int NCLS>
 __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[NCLS], u64 al, u64 nl, u64 rs, bool utf8, int rounds, u64 cont,
                                             uint32_t rs_next, uint32_t next_is_cont, uint32_t a_next, uint32_t nl_next,
-                                            ChainState64<NS>& st, const LaneCtx& L, bool want_spans, u64 (&sp)[3])
+                                            ChainState64<NS>& st, const LaneCtx& L, const SpanSink& sink)
 {
     const u64 nrs = ~rs;
     u64 fin = ~0ull;       // last byte of a character
@@ -259,11 +284,10 @@ __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[N
         st.last[s] = hi32(Z);
         old_prev = old;
         P = Z & fin;
-        if (s == NS - 1 && want_spans) {  // span streams of the last step (span_walk.cuh)
-            sp[0] = t;                                              // M: first character of the last step, lead byte
-            sp[1] = cd.steps[s].loop ? (ck & nrs) : (ck & cont);    // K: the match may continue INTO this byte
-            sp[2] = cd.end_mask ? apply_after64(fin, cd.end_mask, as) : fin;  // A: a match may end after this byte
-        }
+        if (s == NS - 1 && sink.m != nullptr)  // span streams of the last step (span_walk.cuh); out of line: cold for contains_re / match
+            store_spans(sink, t,                                                           // M: first character of the last step, lead byte
+                        cd.steps[s].loop ? (ck & nrs) : (ck & cont),                       // K: the match may continue INTO this byte
+                        cd.end_mask ? apply_after64_generic(fin, cd.end_mask, as) : fin);  // A: a match may end after this byte
     }
     return cd.end_mask ? apply_after64(P, cd.end_mask, as) : P;
 }
@@ -436,26 +460,9 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
                 rounds = 1 + (int)__any_sync(FULL, lead3 != 0) + (int)__any_sync(FULL, (lead3 & p[4]) != 0);
             }
             const u64 al = nc.al;
-            const bool want_spans = A.span_m != nullptr;
-            u64 sp[3] = {0, 0, 0};
+            const SpanSink sink{A.span_m, A.span_k, A.span_a, (size_t)((ws + 64 * (int)lane - A.span_base) >> 6), ws + 64 * (int)lane, byte_a, byte_b};
             const u64 E = chain_eval64<NS, NCLS>(cd, c, al, nl, rs, utf8, rounds, cont, rs_next, (next_byte & 0xC0u) == 0x80u, a_next, nl_next, st, L,
-                                                 want_spans, sp);
-            if (want_spans) {  // this item owns the bits of [byte_a, byte_b): whole words are stored, boundary words OR-ed in
-                const int wp = ws + 64 * (int)lane;
-                const size_t widx = (size_t)((wp - A.span_base) >> 6);
-                if (wp >= byte_a && wp + 64 <= byte_b) {
-                    A.span_m[widx] = sp[0];
-                    A.span_k[widx] = sp[1];
-                    A.span_a[widx] = sp[2];
-                } else if (wp + 64 > byte_a && wp < byte_b) {
-                    u64 mask = ~0ull;
-                    if (wp < byte_a) mask &= ~0ull << (byte_a - wp);
-                    if (wp + 64 > byte_b) mask &= ~0ull >> (wp + 64 - byte_b);
-                    if (sp[0] & mask) atomicOr(A.span_m + widx, sp[0] & mask);
-                    if (sp[1] & mask) atomicOr(A.span_k + widx, sp[1] & mask);
-                    if (sp[2] & mask) atomicOr(A.span_a + widx, sp[2] & mask);
-                }
-            }
+                                                 sink);
 
             // ---- sticky per-row OR of the match bits; NUL bytes make a row "dirty" (decided by the exact VM)
             const u64 nrs = ~rs;
