@@ -10,6 +10,23 @@
 // synchronisation the ring needs.
 #pragma once
 
+// Plan view: how the kernel reads the flags of the chain it executes.  The ahead-of-time kernels read them from the
+// parameter block (one binary interprets every chain); a plan-specialised build defines them as literals so that ptxas
+// folds every flag test, select and constant-bank read away.
+#ifndef PV_SPECIALISED
+#define PV_NEEDS (cd.needs)
+#define PV_ANCHORED (cd.anchored)
+#define PV_END_MASK (cd.end_mask)
+#define PV_BEFORE0 (cd.steps[0].before)
+#define PV_STEP_CLS(s) (cd.steps[s].cls)
+#define PV_STEP_LOOP(s) (cd.steps[s].loop)
+#define PV_NCLASSES (cd.nclasses)
+#define PV_CLS_BUILTINS(k) (cd.classes[k].builtins)
+#define PV_CLS_NATOMS(k) (cd.classes[k].natoms)
+#define PV_CLS_NEGATE(k) (cd.classes[k].negate)
+#define PV_BUILTIN_UNION (cd.builtin_union)
+#endif
+
 constexpr int WIN64 = 2048;
 constexpr int RING_STAGES = 2;
 using u64 = unsigned long long;
@@ -185,13 +202,13 @@ __device__ __noinline__ NaClasses<NCLS> classify_non_ascii64(const ChainDev& cd,
             const uint32_t cp = ((ch >> 2) & 0x7C0u) | (ch & 0x3Fu);
 #pragma unroll
             for (int k = 0; k < NCLS; ++k)
-                if (k < (int)cd.nclasses) r.c[k] = ((cd.classes[k].na2[cp >> 5] >> (cp & 31)) & 1u) ? (r.c[k] | bits) : (r.c[k] & ~bits);
+                if (k < (int)PV_NCLASSES) r.c[k] = ((cd.classes[k].na2[cp >> 5] >> (cp & 31)) & 1u) ? (r.c[k] | bits) : (r.c[k] & ~bits);
             r.al = ((cd.na2_alnum[cp >> 5] >> (cp & 31)) & 1u) ? (r.al | bits) : (r.al & ~bits);
             continue;
         }
 #pragma unroll
         for (int k = 0; k < NCLS; ++k)
-            if (k < (int)cd.nclasses) r.c[k] = na_char_matches(cd.classes[k], A, ch) ? (r.c[k] | bits) : (r.c[k] & ~bits);
+            if (k < (int)PV_NCLASSES) r.c[k] = na_char_matches(cd.classes[k], A, ch) ? (r.c[k] | bits) : (r.c[k] & ~bits);
         r.al = is_alnum_packed(ch, A.uflags) ? (r.al | bits) : (r.al & ~bits);
     }
     return r;
@@ -246,12 +263,12 @@ __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[N
     as.rs = rs;
     as.nl = nl;
     as.bow_b = as.bow_a = as.bolc_b = as.lb = as.eold_a = 0;
-    if (cd.needs & (AS_BOW | AS_NBOW)) {
+    if (PV_NEEDS & (AS_BOW | AS_NBOW)) {
         as.bow_b = al ^ (adv64(al, st.last_al, L) & nrs);
         as.bow_a = al ^ shift_down64(al & nrs, a_next, L);
         st.last_al = hi32(al);
     }
-    if (cd.needs & (AS_BOL_CARET | AS_EOL_DOLLAR | AS_EOL_Z)) {
+    if (PV_NEEDS & (AS_BOL_CARET | AS_EOL_DOLLAR | AS_EOL_Z)) {
         as.bolc_b = rs | (adv64(nl, st.last_nl, L) & nrs);
         as.lb = shift_down64(rs, rs_next, L);
         as.eold_a = as.lb | shift_down64(nl & nrs, nl_next, L);
@@ -263,19 +280,19 @@ __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[N
     for (int s = 0; s < NS; ++s) {
         u64 t;
         if (s == 0) {
-            t = cd.anchored ? rs : ~0ull;
-            const uint32_t before = cd.steps[0].before;
+            t = PV_ANCHORED ? rs : ~0ull;
+            const uint32_t before = PV_BEFORE0;
             if (before) t = apply_before64(t, before, as);
         } else {
             // the marker of step s-1 moves to the next position; the carry (previous window's stream) is dropped when
             // this window starts inside a character: that marker was not on a final byte
             t = adv64(P, cont0 ? 0u : old_prev, L) & nrs;
         }
-        const u64 ck = sel_class64<NCLS>(c, cd.steps[s].cls);
+        const u64 ck = sel_class64<NCLS>(c, PV_STEP_CLS(s));
         t &= ck & ~cont;
         const uint32_t old = st.last[s];
         u64 Z = t;
-        if (cd.steps[s].loop) Z = spread64(t, ck & nrs, old, L);
+        if (PV_STEP_LOOP(s)) Z = spread64(t, ck & nrs, old, L);
         else if (utf8) {  // move the marker from the lead byte to the last byte of its character: one round per
                           // continuation byte of the longest character in the window (`rounds`, warp-uniform)
 #pragma unroll 1
@@ -286,10 +303,10 @@ __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[N
         P = Z & fin;
         if (s == NS - 1 && sink.m != nullptr)  // span streams of the last step (span_walk.cuh); out of line: cold for contains_re / match
             store_spans(sink, t,                                                           // M: first character of the last step, lead byte
-                        cd.steps[s].loop ? (ck & nrs) : (ck & cont),                       // K: the match may continue INTO this byte
-                        cd.end_mask ? apply_after64_generic(fin, cd.end_mask, as) : fin);  // A: a match may end after this byte
+                        PV_STEP_LOOP(s) ? (ck & nrs) : (ck & cont),                       // K: the match may continue INTO this byte
+                        PV_END_MASK ? apply_after64_generic(fin, PV_END_MASK, as) : fin);  // A: a match may end after this byte
     }
-    return cd.end_mask ? apply_after64(P, cd.end_mask, as) : P;
+    return PV_END_MASK ? apply_after64(P, PV_END_MASK, as) : P;
 }
 
 // copy of window [ws, ws + 2048) into a ring stage; `dst0` = shared address of this lane's chunk 0 in that stage,
@@ -333,8 +350,8 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
     asm volatile("" : "+r"(wb), "+r"(my0), "+r"(my_w));  // keep them in registers instead of re-deriving them per use
     const int warps_total = gridDim.x * WARPS;
     unsigned long long my_matches = 0;
-    const uint32_t bneed = cd.builtin_union | ((cd.needs & (AS_BOW | AS_NBOW)) ? (1u << AK_ALNUM) : 0u);
-    const bool need_nl = (cd.needs & (AS_BOL_CARET | AS_EOL_DOLLAR | AS_EOL_Z)) != 0;
+    const uint32_t bneed = PV_BUILTIN_UNION | ((PV_NEEDS & (AS_BOW | AS_NBOW)) ? (1u << AK_ALNUM) : 0u);
+    const bool need_nl = (PV_NEEDS & (AS_BOL_CARET | AS_EOL_DOLLAR | AS_EOL_Z)) != 0;
 
     // work items are handed out dynamically (one atomicAdd per 32 KiB item): the grid is exactly the resident set, so
     // there is no partial last wave and the tail is a single item
@@ -428,14 +445,14 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
 #pragma unroll
             for (int k = 0; k < NCLS; ++k) {
                 u64 v = 0;
-                if (k < (int)cd.nclasses) {
-                    const uint32_t f = cd.classes[k].builtins;
-                    if (cd.classes[k].natoms == 0 && f == (1u << AK_WORD)) v = word;          // single builtin: inline
-                    else if (cd.classes[k].natoms == 0 && f == (1u << AK_DIGIT)) v = digit;
-                    else if (cd.classes[k].natoms == 0 && f == (1u << AK_ALNUM)) v = alnum;
-                    else if (cd.classes[k].natoms == 0 && f == (1u << AK_SPACE)) v = space;
+                if (k < (int)PV_NCLASSES) {
+                    const uint32_t f = PV_CLS_BUILTINS(k);
+                    if (PV_CLS_NATOMS(k) == 0 && f == (1u << AK_WORD)) v = word;          // single builtin: inline
+                    else if (PV_CLS_NATOMS(k) == 0 && f == (1u << AK_DIGIT)) v = digit;
+                    else if (PV_CLS_NATOMS(k) == 0 && f == (1u << AK_ALNUM)) v = alnum;
+                    else if (PV_CLS_NATOMS(k) == 0 && f == (1u << AK_SPACE)) v = space;
                     else v = class_generic64(cd.classes[k], p, letter5, digit, alnum, word, space);
-                    if (cd.classes[k].negate) v = ~v;
+                    if (PV_CLS_NEGATE(k)) v = ~v;
                 }
                 c[k] = v;
             }
@@ -443,7 +460,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
             const u64 nl = need_nl ? (cls_eq(p, '\n') & ~na) : 0ull;
             uint32_t a_next = 0;
             const uint32_t nl_next = next_byte == '\n';
-            if (cd.needs & (AS_BOW | AS_NBOW)) {
+            if (PV_NEEDS & (AS_BOW | AS_NBOW)) {
                 if (next_byte < 0x80u) a_next = (next_byte - '0' < 10u) || ((next_byte | 0x20u) - 'a' < 26u);
                 else if ((next_byte & 0xC0u) != 0x80u) {
                     int w;
