@@ -17,6 +17,8 @@
 #include "regex_bits.h"
 #include "regex_bits_plan.h"
 #include "regex_vm.cuh"
+#include <cub/cub.cuh>
+#include <cstddef>
 
 namespace custr {
 namespace bits {
@@ -511,6 +513,89 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
 #ifndef CUSTR_EXPERIMENT_ONLY_4_1
     LAUNCH(k_bitstream, blocks, THREADS, 0, device_plan(plan), a);
 #endif
+    return true;
+}
+
+#include "tokenize_bits.cuh"
+
+// NVText::tokenize through the bit-stream compaction kernels.  delims == nullptr: whitespace.  False = not applicable
+// (unaligned chars base, empty column): the caller uses the per-row path.
+bool tokenize_flat(const custr_column* col, const uint8_t* delims, int ndelims, BufPtr& out_chars, BufPtr& out_off, int64_t& ntok, int64_t& nbytes)
+{
+    if (((uintptr_t)col->chars & 15) != 0 || col->nbytes == 0 || col->n == 0 || ndelims > TOK_DELIMS_MAX) return false;
+    const int32_t n = col->n;
+    TokArgs a{};
+    a.chars = col->chars;
+    a.offsets = col->offsets;
+    a.n = n;
+    a.first = col->first_off;
+    a.end = col->first_off + (int32_t)col->nbytes;
+    a.nitems = (int)((col->nbytes + ITEM_BYTES - 1) / ITEM_BYTES);
+    a.whitespace = delims ? 0u : 1u;
+    a.ndelims = delims ? (uint32_t)ndelims : 0u;
+    for (int k = 0; k < ndelims && delims; ++k) a.delims[k] = delims[k];
+    if (!col->item_bounds || col->item_bounds_count != a.nitems) {
+        col->item_bounds = dev_alloc(sizeof(int32_t) * (size_t)(a.nitems + 2));
+        col->item_bounds_count = a.nitems;
+        LAUNCH(k_item_bounds, (n + 1 + 255) / 256, 256, 0, a.offsets, n, a.first, a.nitems, (int32_t*)col->item_bounds->ptr);
+    }
+    a.item_bounds = (const int32_t*)col->item_bounds->ptr;
+    const int win_base = a.first & ~(WIN64 - 1);
+    const size_t nwin = ((size_t)(a.end - win_base) + WIN64 - 1) / WIN64;
+    // every item adds at most one shared window; + one empty slot whose exclusive sum is the grand total
+    const size_t nslots = nwin + (size_t)a.nitems + 1;
+    Scratch<int32_t> item_w((size_t)a.nitems + 1), item_slot((size_t)a.nitems + 1);
+    CUSTR_CUDA(cudaMemsetAsync(item_w.get() + a.nitems, 0, sizeof(int32_t), g_stream));
+    LAUNCH(k_tok_item_windows, (a.nitems + 255) / 256, 256, 0, a.offsets, a.item_bounds, a.nitems, item_w.get());
+    {
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, item_w.get(), item_slot.get(), a.nitems + 1, g_stream);
+        BufPtr t = dev_alloc(tb);
+        CUSTR_CUDA(cub::DeviceScan::ExclusiveSum(t->ptr, tb, item_w.get(), item_slot.get(), a.nitems + 1, g_stream));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    a.item_slot = item_slot.get();
+    BufPtr counts = dev_alloc(sizeof(unsigned long long) * nslots), base = dev_alloc(sizeof(unsigned long long) * nslots);
+    BufPtr counter = dev_alloc(2 * sizeof(unsigned int));
+    CUSTR_CUDA(cudaMemsetAsync(counts->ptr, 0, sizeof(unsigned long long) * nslots, g_stream));
+    CUSTR_CUDA(cudaMemsetAsync(counter->ptr, 0, 2 * sizeof(unsigned int), g_stream));
+    a.slot_counts = (unsigned long long*)counts->ptr;
+    a.slot_base = (const unsigned long long*)base->ptr;
+    const int smem = WARPS * (int)sizeof(WarpSmTok);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUSTR_CUDA(cudaFuncSetAttribute(k_tokenize64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUSTR_CUDA(cudaFuncSetAttribute(k_tokenize64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    int blocks = (a.nitems + WARPS - 1) / WARPS;
+    const int resident = num_sms() * 3;
+    if (blocks > resident) blocks = resident;
+    a.item_counter = (unsigned int*)counter->ptr;
+    auto kc = k_tokenize64<false>;
+    LAUNCH(kc, blocks, THREADS, smem, a);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, a.slot_counts, (unsigned long long*)base->ptr, (int)nslots, g_stream);
+    BufPtr tmp = dev_alloc(tmp_bytes);
+    CUSTR_CUDA(cub::DeviceScan::ExclusiveSum(tmp->ptr, tmp_bytes, a.slot_counts, (unsigned long long*)base->ptr, (int)nslots, g_stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    unsigned long long total = 0;
+    CUSTR_CUDA(cudaMemcpyAsync(&total, (unsigned long long*)base->ptr + (nslots - 1), sizeof(total), cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    ntok = (int64_t)(total >> 32);
+    nbytes = (int64_t)(total & 0xffffffffull);
+    out_chars = dev_alloc((size_t)nbytes);
+    out_off = dev_alloc(sizeof(int32_t) * (size_t)(ntok + 1));
+    const int32_t last = (int32_t)nbytes;
+    CUSTR_CUDA(cudaMemcpyAsync((int32_t*)out_off->ptr + ntok, &last, sizeof(int32_t), cudaMemcpyHostToDevice, g_stream));
+    if (ntok) {
+        a.tok_off = (int32_t*)out_off->ptr;
+        a.out = (char*)out_chars->ptr;
+        a.item_counter = (unsigned int*)counter->ptr + 1;
+        auto kw = k_tokenize64<true>;
+        LAUNCH(kw, blocks, THREADS, smem, a);
+    }
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));  // `last` and the scratch buffers die with this scope
     return true;
 }
 

@@ -34,6 +34,10 @@ struct SpanStreams {
 bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, const uint8_t* uflags, uint8_t* out,
          unsigned long long* total, int32_t** dirty_rows, unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count,
          SpanStreams* spans = nullptr);
+// NVText::tokenize as a bit-stream compaction (tokenize_bits.cuh): whitespace (delims == nullptr) or up to 8 ASCII
+// delimiter bytes.  Produces the flat token column (chars + int32 offsets[ntok + 1]).  False = not applicable.
+bool tokenize_flat(const custr_column* col, const uint8_t* delims, int ndelims, BufPtr& out_chars, BufPtr& out_off, int64_t& ntok,
+                   int64_t& nbytes);
 extern bool g_force_generic;
 extern bool g_chain32;
 

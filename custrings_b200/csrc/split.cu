@@ -8,6 +8,7 @@
 // split_record / tokenize return ONE flat token column (+ row offsets) instead of N objects.
 #include "common.cuh"
 #include "rowops.cuh"
+#include "regex_bits.h"
 #include <cub/cub.cuh>
 
 namespace custr {
@@ -394,6 +395,15 @@ custr_column* custr_tokenize(const custr_column* col, const char* delimiter)
     return guarded(
         [&]() -> custr_column* {
             if (!col) throw ArgError{fail(CUSTR_ERR_ARG, "tokenize: null column")};
+            // whitespace or a few ASCII delimiter bytes: bit-stream compaction, no per-row walk (tokenize_bits.cuh)
+            bool ascii_set = delimiter != nullptr && strlen(delimiter) >= 1 && strlen(delimiter) <= 8;
+            for (const char* p = delimiter; ascii_set && *p; ++p) ascii_set = (unsigned char)*p < 0x80;
+            if ((!delimiter || ascii_set) && !bits::g_force_generic) {
+                BufPtr chars, off;
+                int64_t ntok = 0, nbytes = 0;
+                if (bits::tokenize_flat(col, (const uint8_t*)delimiter, delimiter ? (int)strlen(delimiter) : 0, chars, off, ntok, nbytes))
+                    return make_column(chars, off, nullptr, (int32_t)ntok, 0, nbytes);
+            }
             ParamHolder h;
             make_token_params(h, delimiter);
             int total = 0;

@@ -145,6 +145,40 @@ def test_tokenize(cols, oracle):
         assert nvtext.token_count(dev, d) == wc.tolist(), d
 
 
+def test_tokenize_bitstream_large(oracle):
+    """tokenize through the bit-stream compaction kernels on a column spanning many windows and work items: rows longer
+    than a 32 KiB item (several item boundaries inside one row / one window), empty and null rows, multi-byte characters"""
+    from custrings_b200 import nvstrings, nvtext
+    from custrings_b200._lib import lib
+    rng = random.Random(17)
+    words = ["a", "bb", "ccc", "héllo", "日本", "x1", "_", "tab\tsep", "new\nline", "zz😀", "0"]
+    strs = []
+    for i in range(20000):
+        r = rng.random()
+        if r < 0.02:
+            strs.append(None)
+        elif r < 0.05:
+            strs.append("")
+        elif r < 0.07:
+            strs.append(" " * rng.randrange(1, 40))
+        elif r < 0.0708:
+            strs.append((" ".join(rng.choice(words) for _ in range(rng.randrange(8000, 20000)))))  # 30-80 KB rows
+        else:
+            sep = rng.choice([" ", "  ", ",", ", ", " : "])
+            strs.append(sep.join(rng.choice(words) for _ in range(rng.randrange(0, 30))) + rng.choice(["", " ", ","]))
+    dev, ref = nvstrings.to_device(strs), oracle.RefStrings.from_list(strs)
+    for d in (None, " ", ",", ",: ", "a"):
+        want = ref.tokenize(d).to_list()
+        got = oracle.unpack(*nvtext.tokenize(dev, d).to_arrays())
+        assert len(got) == len(want), (d, len(got), len(want))
+        assert got == want, d
+    lib().custr_set_regex_tier(2)  # per-row path for comparison
+    try:
+        assert oracle.unpack(*nvtext.tokenize(dev, None).to_arrays()) == ref.tokenize(None).to_list()
+    finally:
+        lib().custr_set_regex_tier(0)
+
+
 def test_category(oracle):
     from custrings_b200 import nvstrings, nvcategory
     rng = random.Random(5)
