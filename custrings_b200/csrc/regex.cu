@@ -404,46 +404,142 @@ k_span_replace(ColView col, spans::Streams S, const uint8_t* __restrict__ hits, 
     }
 }
 
-// write pass, rows AND their slices of the three bit streams staged through shared memory (row_stage.cuh): the walk then
-// costs shared-memory latencies instead of a chain of dependent global loads per match
-__global__ void __launch_bounds__(stage::THREADS)
-k_span_replace_staged(ColView col, int chars_limit, spans::Streams S, const uint8_t* __restrict__ hits, int k_chars,
+// write pass as a warp-cooperative SPLICE.  A warp takes 32 consecutive rows: their chars are one contiguous byte range and
+// so is their output.  (1) The range and its slices of the three bit streams are staged in shared memory with coalesced
+// loads.  (2) Every lane walks the matches of its own row (word scans over the shared streams) and records them in two
+// shared bit maps over the same byte range: DROP (bytes inside a match) and INS (first byte of a match).  (3) The warp
+// then rewrites the whole range cooperatively — lane = one 64-byte word: kept bytes and replacement strings land at
+// (warp prefix of popc(keep) + repl_len * popc(ins)) in a shared output tile, no per-row control flow — and (4) the
+// tile leaves with coalesced 16-byte stores.  Blocks that do not fit (very long rows / much longer output) take the
+// direct lane-per-row path.
+namespace splice {
+using u64 = unsigned long long;
+constexpr int ROWS = 32, CAP = 4352, WARPS = 4, THREADS = WARPS * 32;
+constexpr int WORDS = (CAP + 64) / 64 + 2;
+struct __align__(16) Sm {
+    char in[WARPS][CAP + 64 + 32];   // from the 64-byte aligned start of the block: in[p - a64]
+    char out[WARPS][CAP + 32];       // out[(out_a & 15) + k]
+    u64 m[WARPS][WORDS], k[WARPS][WORDS], a[WARPS][WORDS], drop[WARPS][WORDS], ins[WARPS][WORDS];
+};
+// relative positions [lo, hi), hi > lo; 32-bit shared-memory atomics (ATOMS.OR) on the halves of the 64-bit words
+__device__ __forceinline__ void set_bits(uint32_t* arr, int lo, int hi)
+{
+    const int wl = lo >> 5, wh = (hi - 1) >> 5;
+    for (int w = wl; w <= wh; ++w) {
+        uint32_t mask = ~0u;
+        if (w == wl) mask &= ~0u << (lo & 31);
+        if (w == wh) mask &= ~0u >> (31 - ((hi - 1) & 31));
+        atomicOr(arr + w, mask);
+    }
+}
+}  // namespace splice
+
+__global__ void __launch_bounds__(splice::THREADS)
+k_span_replace_splice(ColView col, int chars_limit, spans::Streams S, const uint8_t* __restrict__ hits, int k_chars,
                       const char* __restrict__ repl, int repl_len, int maxrepl, const int32_t* __restrict__ out_off, char* __restrict__ out_chars)
 {
-    __shared__ stage::Buffers sm;
-    __shared__ stage::StreamBuffers ss;
+    using namespace splice;
+    __shared__ Sm sm;
     const uint8_t* chars = (const uint8_t*)col.chars;
     const int budget = maxrepl < 0 ? 0x7fffffff : maxrepl;
-    const int warp = threadIdx.x >> 5;
-    stage::for_each_row_staged(
-        col, chars_limit, out_chars, sm, [&](int r) { return (long long)out_off[r]; },
-        [&](int in_a, int in_b, int w_, int lane) {
-            if (in_b <= in_a) return;
-            const int w0 = (in_a - S.base) >> 6, w1 = (in_b - 1 - S.base) >> 6;
-            for (int w = w0 + lane; w <= w1; w += 32) {
-                ss.w[w_][0][w - w0] = __ldg(S.m + w);
-                ss.w[w_][1][w - w0] = __ldg(S.k + w);
-                ss.w[w_][2][w - w0] = __ldg(S.a + w);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nblocks = (col.n + ROWS - 1) / ROWS;
+    for (int blk = blockIdx.x * WARPS + warp; blk < nblocks; blk += gridDim.x * WARPS) {
+        const int r0 = blk * ROWS, r1 = r0 + ROWS < col.n ? r0 + ROWS : col.n;
+        const int in_a = col.offsets[r0], in_b = col.offsets[r1];
+        const long long out_a = out_off[r0], out_b = out_off[r1];
+        const int i = r0 + lane;
+        const int a64 = in_a & ~63;
+        const bool fits = in_b > in_a && (in_b - a64) <= CAP + 64 && (out_b - (out_a & ~15ll)) <= CAP + 16;
+        if (!fits) {  // direct path, lane per row
+            if (i < r1) {
+                const int a = col.offsets[i], b = col.offsets[i + 1];
+                char* o = out_chars + out_off[i];
+                int last = a;
+                if (hits[i])
+                    spans::walk_spans<true>(S, chars, a, b, k_chars, budget, [&](int s, int e) {
+                        for (int q = last; q < s; ++q) *o++ = (char)chars[q];
+                        for (int q = 0; q < repl_len; ++q) *o++ = repl[q];
+                        last = e;
+                    });
+                for (int q = last; q < b; ++q) *o++ = (char)chars[q];
             }
-        },
-        [&](int i, const uint8_t* src, char* dst, bool staged, int in_a) {
-            const int a = col.offsets[i], b = col.offsets[i + 1];
-            int o = out_off[i], last = a;
-            auto emit = [&](int s, int e) {
-                for (int q = last; q < s; ++q) dst[o++] = (char)src[q];
-                for (int q = 0; q < repl_len; ++q) dst[o++] = repl[q];
-                last = e;
-            };
-            if (hits[i]) {
-                if (staged) {
-                    const int w0 = (in_a - S.base) >> 6;
-                    const spans::Streams T{ss.w[warp][0] - w0, ss.w[warp][1] - w0, ss.w[warp][2] - w0, S.base};
-                    spans::walk_spans<false>(T, src, a, b, k_chars, budget, emit);
-                } else
-                    spans::walk_spans<true>(S, chars, a, b, k_chars, budget, emit);
+            continue;
+        }
+        // (1) stage chars + stream slices, clear the bit maps
+        stage::copy_in(sm.in[warp], col.chars, a64, in_b, chars_limit, lane);
+        const int w0 = (a64 - S.base) >> 6, nwords = ((in_b - 1 - a64) >> 6) + 1;
+        for (int w = lane; w < nwords; w += 32) {
+            sm.m[warp][w] = __ldg(S.m + w0 + w);
+            sm.k[warp][w] = __ldg(S.k + w0 + w);
+            sm.a[warp][w] = __ldg(S.a + w0 + w);
+            sm.drop[warp][w] = 0;
+            sm.ins[warp][w] = 0;
+        }
+        __syncwarp();
+        // (2) matches of my row -> DROP / INS bits
+        if (i < r1 && hits[i]) {
+            const spans::Streams T{sm.m[warp] - w0, sm.k[warp] - w0, sm.a[warp] - w0, S.base};
+            spans::walk_spans<false>(T, (const uint8_t*)sm.in[warp] - a64, col.offsets[i], col.offsets[i + 1], k_chars, budget, [&](int s, int e) {
+                set_bits((uint32_t*)sm.drop[warp], s - a64, e - a64);
+                atomicOr((uint32_t*)sm.ins[warp] + ((s - a64) >> 5), 1u << ((s - a64) & 31));
+            });
+        }
+        __syncwarp();
+        // (3) cooperative rewrite, lane = one 64-byte word
+        const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(sm.out[warp]) + (uint32_t)(out_a & 15);
+        int running = 0;
+        for (int base_w = 0; base_w < nwords; base_w += 32) {
+            const int j = base_w + lane;
+            u64 keep = 0, insb = 0;
+            if (j < nwords) {
+                const int wp = a64 + 64 * j;  // chars offset of bit 0 of this word
+                u64 own = ~0ull;
+                if (wp < in_a) own &= ~0ull << (in_a - wp);
+                if (wp + 64 > in_b) own &= ~0ull >> (wp + 64 - in_b);
+                keep = own & ~sm.drop[warp][j];
+                insb = own & sm.ins[warp][j];
             }
-            for (int q = last; q < b; ++q) dst[o++] = (char)src[q];
-        });
+            const int cnt = __popcll(keep) + repl_len * __popcll(insb);
+            int pre = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, pre, d);
+                if (lane >= d) pre += v;
+            }
+            const int tot = __shfl_sync(0xffffffffu, pre, 31);
+            const uint32_t o0 = tile_s + (uint32_t)(running + pre - cnt);  // shared address of this word's first output byte
+            if (keep) {  // kept bytes: straight-line, one predicated byte store per input byte; insertions only move the cursor
+                const uint32_t* w32 = (const uint32_t*)(sm.in[warp] + 64 * j);
+                uint32_t o = o0;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const uint32_t kq = (uint32_t)(keep >> (4 * q)) & 15u, iq = (uint32_t)(insb >> (4 * q)) & 15u;
+                    const uint32_t v = w32[q];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        o += ((iq >> b) & 1u) * (uint32_t)repl_len;
+                        if (kq & (1u << b)) {
+                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(o), "r"(v >> (8 * b)) : "memory");
+                            ++o;
+                        }
+                    }
+                }
+            }
+            for (u64 t = insb; t;) {  // the replacement strings (a few per word)
+                const int bit = __ffsll((long long)t) - 1;
+                t &= t - 1;
+                const u64 below = (1ull << bit) - 1ull;
+                uint32_t o = o0 + (uint32_t)(__popcll(keep & below) + repl_len * __popcll(insb & below));
+                for (int r = 0; r < repl_len; ++r) asm volatile("st.shared.u8 [%0], %1;" ::"r"(o + r), "r"((uint32_t)(uint8_t)repl[r]) : "memory");
+            }
+            running += tot;
+        }
+        __syncwarp();
+        // (4) tile -> output
+        stage::copy_out(sm.out[warp], out_chars, out_a, out_b, lane);
+        __syncwarp();
+    }
 }
 
 // Runs the chain kernel with span streams for `c` over `col`.  False: not applicable (caller uses the scalar / VM path).
@@ -921,7 +1017,7 @@ custr_column* custr_replace_re(const custr_column* col, const char* pattern, con
                         int64_t total2 = 0;
                         finish_replace(col, lens, off2, total2);
                         BufPtr chars2 = dev_alloc((size_t)total2);
-                        LAUNCH(k_span_replace_staged, stage::grid_for(n), stage::THREADS, 0, view_of(col), col->first_off + (int)col->nbytes, sr.view(),
+                        LAUNCH(k_span_replace_splice, stage::grid_for(n), splice::THREADS, 0, view_of(col), col->first_off + (int)col->nbytes, sr.view(),
                                (const uint8_t*)sr.hits->ptr, k_chars, (const char*)d_repl->ptr, repl_len, maxrepl, (const int32_t*)off2->ptr,
                                (char*)chars2->ptr);
                         g_last_tier = "bitspans";
