@@ -77,6 +77,7 @@ _SIGNATURES = {
     "custr_category_values": (ci, [vp, vp, ci]),
     "custr_category_values_cptr": (vp, [vp]),
     "custr_category_remap_to_union": (vp, [vp, vp]),
+    "custr_category_merge": (vp, [vp, ci, ci]),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)

@@ -126,7 +126,7 @@ __global__ void k_lookup_keys(ColView local, ColView global, int32_t* __restrict
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= local.n) return;
-    if (!local.valid(i)) { map[i] = 0; return; }  // null key is key 0 wherever it exists
+    if (!local.valid(i)) { map[i] = (global.n > 0 && !global.valid(0)) ? 0 : -1; return; }  // the null key is key 0 wherever it exists
     const uint8_t* s = (const uint8_t*)local.chars + local.offsets[i];
     int n = local.offsets[i + 1] - local.offsets[i];
     int lo = 0, hi = global.n - 1, found = -1;
@@ -309,6 +309,78 @@ custr_category* custr_category_remap_to_union(const custr_category* cat, const c
                 CUSTR_CUDA(cudaStreamSynchronize(g_stream));
             }
             return out;
+        },
+        (custr_category*)nullptr, (custr_category*)nullptr);
+}
+
+// NVCategory::create_from_categories / merge_and_remap (NVCategory.cu:430-514,1339-1345; sorted != 0): keys = sorted
+// distinct union of every input's keys, values = the inputs' values remapped and appended in input order.
+// NVCategory::merge_category (NVCategory.cu:1223-1336; sorted == 0, exactly two inputs): keys = first input's keys followed by
+// the second input's keys that are new (in their own order), first values unchanged, second values remapped and appended.
+custr_category* custr_category_merge(const custr_category* const* cats, int32_t ncats, int sorted)
+{
+    return guarded(
+        [&]() -> custr_category* {
+            if (!cats || ncats <= 0) throw ArgError{fail(CUSTR_ERR_ARG, "category merge: no inputs")};
+            if (!sorted && ncats != 2) throw ArgError{fail(CUSTR_ERR_ARG, "merge_category takes exactly two categories")};
+            int64_t total = 0;
+            std::vector<const custr_column*> keycols;
+            for (int c = 0; c < ncats; ++c) {
+                if (!cats[c] || !cats[c]->keys) throw ArgError{fail(CUSTR_ERR_ARG, "category merge: null input")};
+                total += cats[c]->n;
+                keycols.push_back(cats[c]->keys);
+            }
+            if (total > 0x7fffffffLL) throw ArgError{fail(CUSTR_ERR_INVALID, "category merge: more than 2^31 values")};
+            custr_category* out = new custr_category;
+            std::unique_ptr<custr_category, void (*)(custr_category*)> guard(out, [](custr_category* c) { custr_category_free(c); });
+            out->n = (int32_t)total;
+            out->values_buf = dev_alloc(sizeof(int32_t) * (size_t)(total ? total : 1));
+            std::vector<BufPtr> maps(ncats);
+            if (sorted) {
+                std::unique_ptr<custr_column> all(concat_columns(keycols.data(), ncats));
+                std::unique_ptr<custr_category, void (*)(custr_category*)> uni(build_category(all.get()), [](custr_category* c) { custr_category_free(c); });
+                out->keys = uni->keys;
+                uni->keys = nullptr;
+                for (int c = 0; c < ncats; ++c) {
+                    const int32_t k = cats[c]->keys->n;
+                    maps[c] = dev_alloc(sizeof(int32_t) * (size_t)(k ? k : 1));
+                    if (k) LAUNCH(k_lookup_keys, (k + 255) / 256, 256, 0, view_of(cats[c]->keys), view_of(out->keys), (int32_t*)maps[c]->ptr);
+                }
+            } else {
+                const custr_column *k1 = cats[0]->keys, *k2 = cats[1]->keys;
+                const int32_t n1 = k1->n, n2 = k2->n;
+                maps[1] = dev_alloc(sizeof(int32_t) * (size_t)(n2 ? n2 : 1));
+                std::vector<int32_t> h_map((size_t)n2), fresh;
+                if (n2) {
+                    LAUNCH(k_lookup_keys, (n2 + 255) / 256, 256, 0, view_of(k2), view_of(k1), (int32_t*)maps[1]->ptr);
+                    CUSTR_CUDA(cudaMemcpyAsync(h_map.data(), maps[1]->ptr, sizeof(int32_t) * (size_t)n2, cudaMemcpyDeviceToHost, g_stream));
+                    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+                }
+                for (int32_t i = 0; i < n2; ++i)   // key sets are small (dictionary entries, not rows): host bookkeeping
+                    if (h_map[i] < 0) { h_map[i] = n1 + (int32_t)fresh.size(); fresh.push_back(i); }
+                if (n2) CUSTR_CUDA(cudaMemcpyAsync(maps[1]->ptr, h_map.data(), sizeof(int32_t) * (size_t)n2, cudaMemcpyHostToDevice, g_stream));
+                std::unique_ptr<custr_column> added(custr_gather(k2, fresh.data(), (int32_t)fresh.size(), 0));
+                if (!added) throw ArgError{CUSTR_ERR_INVALID};
+                const custr_column* both[2] = {k1, added.get()};
+                out->keys = concat_columns(both, 2);
+                CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            }
+            int64_t pos = 0;
+            for (int c = 0; c < ncats; ++c) {
+                const int32_t n = cats[c]->n;
+                if (n) {
+                    if (maps[c])
+                        LAUNCH(k_remap_values, (n + 255) / 256, 256, 0, (const int32_t*)cats[c]->values_buf->ptr, (const int32_t*)maps[c]->ptr, n,
+                               (int32_t*)out->values_buf->ptr + pos);
+                    else
+                        CUSTR_CUDA(cudaMemcpyAsync((int32_t*)out->values_buf->ptr + pos, cats[c]->values_buf->ptr, sizeof(int32_t) * (size_t)n,
+                                                   cudaMemcpyDeviceToDevice, g_stream));
+                }
+                pos += n;
+            }
+            out->has_null_key = out->keys->nulls > 0;
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            return guard.release();
         },
         (custr_category*)nullptr, (custr_category*)nullptr);
 }

@@ -327,6 +327,23 @@ NVStrings* NVCategory::to_strings()
     return new NVStrings(checked(r));
 }
 
+NVCategory* NVCategory::create_from_categories(std::vector<NVCategory*>& cats)
+{
+    std::vector<const custr_category*> v;
+    for (NVCategory* c : cats) v.push_back(c->cat_);
+    return new NVCategory(checked_cat(custr_category_merge(v.data(), (int)v.size(), 1)));
+}
+NVCategory* NVCategory::merge_category(NVCategory& cat)
+{
+    const custr_category* v[2] = {cat_, cat.cat_};
+    return new NVCategory(checked_cat(custr_category_merge(v, 2, 0)));
+}
+NVCategory* NVCategory::merge_and_remap(NVCategory& cat)
+{
+    const custr_category* v[2] = {cat_, cat.cat_};
+    return new NVCategory(checked_cat(custr_category_merge(v, 2, 1)));
+}
+
 // -------------------------------------------------------------------------------------------------------------- NVText
 NVStrings* NVText::tokenize(NVStrings& strs, const char* delimiter) { return new NVStrings(checked(custr_tokenize(strs.column(), delimiter))); }
 unsigned int NVText::token_count(NVStrings& strs, const char* delimiter, unsigned int* results, bool devmem)

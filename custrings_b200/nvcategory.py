@@ -111,6 +111,13 @@ def from_strings_sharded(strs, group=None):
     return nvcategory(check_handle(h, "from_strings_sharded"))
 
 
+def from_categories(cats):
+    """NVCategory::create_from_categories (NVCategory.cu:430-514): one category over the concatenation of the inputs'
+    rows, built from their keys and values only (no pass over strings)."""
+    arr = (C.c_void_p * len(cats))(*[c.m_cptr for c in cats])
+    return nvcategory(check_handle(lib().custr_category_merge(arr, len(cats), 1), "from_categories"))
+
+
 class nvcategory:
     """Dictionary-encoded strings: sorted unique keys + int32 values.  reference nvcategory.py:136"""
 
@@ -154,6 +161,17 @@ class nvcategory:
     def to_strings(self):
         """reference nvcategory.py:492"""
         return self.keys().gather(self.values_cpointer(), self.size())
+
+    def merge_and_remap(self, other):
+        """New category over this + other: keys = sorted union, values = both value arrays remapped and appended.
+        reference nvcategory.py:merge_and_remap -> NVCategory.cu:1339 (create_from_categories :430)"""
+        return from_categories([self, other])
+
+    def merge_category(self, other):
+        """New category: this one's keys followed by other's new keys (not re-sorted), this one's values unchanged,
+        other's remapped and appended.  reference nvcategory.py:merge_category -> NVCategory.cu:1223"""
+        arr = (C.c_void_p * 2)(self.m_cptr, other.m_cptr)
+        return nvcategory(check_handle(lib().custr_category_merge(arr, 2, 0), "merge_category"))
 
     def __getattr__(self, name):
         if name.startswith("_") or name == "m_cptr":

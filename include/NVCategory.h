@@ -29,4 +29,8 @@ public:
     int get_values(int* results, bool devmem = true);  // :225
     const int* values_cptr();     // :232
     NVStrings* to_strings();      // :326
+    // category algebra (NVCategory.cu:430-514,1223-1345)
+    static NVCategory* create_from_categories(std::vector<NVCategory*>& cats);   // :122  sorted union of keys, values remapped + appended
+    NVCategory* merge_category(NVCategory& cat);                                 // :261  keys appended (not re-sorted)
+    NVCategory* merge_and_remap(NVCategory& cat);                                // :270  = create_from_categories({this, cat})
 };

@@ -159,6 +159,11 @@ const int32_t* custr_category_values_cptr(const custr_category* cat);      /* de
  * given this shard's category and the union of all shards' keys (any order, duplicates allowed) returns a new
  * category whose keys are the sorted distinct union and whose values are remapped. */
 custr_category* custr_category_remap_to_union(const custr_category* cat, const custr_column* all_keys);
+/* Category algebra.  sorted != 0: NVCategory::create_from_categories / merge_and_remap NVCategory.cu:430-514,1339-1345 — keys =
+ * sorted distinct union, values = every input's values remapped and appended in input order.  sorted == 0 (exactly two
+ * inputs): NVCategory::merge_category :1223-1336 — keys = the first input's keys followed by the second's new keys, the first
+ * values unchanged. */
+custr_category* custr_category_merge(const custr_category* const* cats, int32_t ncats, int sorted);
 
 #ifdef __cplusplus
 }

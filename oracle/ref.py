@@ -31,7 +31,7 @@ def lib():
         L.ref_last_error.restype = cp
         for name in ("ref_create", "ref_create_from_array", "ref_replace_re", "ref_replace_re_multi", "ref_replace", "ref_replace_with_backrefs",
                      "ref_replace_multi", "ref_tokenize", "ref_tokenize_multi", "ref_cat_create", "ref_cat_create_multi",
-                     "ref_cat_keys", "ref_cat_to_strings"):
+                     "ref_cat_keys", "ref_cat_to_strings", "ref_cat_merge", "ref_cat_from_categories"):
             getattr(L, name).restype = vp
         L.ref_create.argtypes = [vp, ci, vp, vp, ci]
         L.ref_destroy.argtypes = [vp]
@@ -69,6 +69,8 @@ def lib():
         L.ref_cat_keys.argtypes = [vp]
         L.ref_cat_values.argtypes = [vp, vp]
         L.ref_cat_to_strings.argtypes = [vp]
+        L.ref_cat_merge.argtypes = [vp, vp, ci]
+        L.ref_cat_from_categories.argtypes = [vp, ci]
         _lib = L
     return _lib
 
@@ -271,7 +273,10 @@ class RefStrings:
 
 
 class RefCategory:
-    def __init__(self, strs):
+    def __init__(self, strs, handle=None):
+        if handle is not None:
+            self.h = C.c_void_p(handle)
+            return
         if isinstance(strs, (list, tuple)):
             arr = (C.c_void_p * len(strs))(*[s.h for s in strs])
             h = lib().ref_cat_create_multi(arr, len(strs))
@@ -293,6 +298,13 @@ class RefCategory:
     def keys_size(self): return int(lib().ref_cat_keys_size(self.h))
     def keys(self): return RefStrings(lib().ref_cat_keys(self.h))
     def to_strings(self): return RefStrings(lib().ref_cat_to_strings(self.h))
+    def merge_category(self, other): return RefCategory(None, lib().ref_cat_merge(self.h, other.h, 0))
+    def merge_and_remap(self, other): return RefCategory(None, lib().ref_cat_merge(self.h, other.h, 1))
+
+    @staticmethod
+    def from_categories(cats):
+        arr = (C.c_void_p * len(cats))(*[c.h for c in cats])
+        return RefCategory(None, lib().ref_cat_from_categories(arr, len(cats)))
 
     def values(self):
         out = np.zeros(max(self.size(), 1), np.int32)

@@ -207,6 +207,17 @@ unsigned ref_cat_size(void* c) { return ((NVCategory*)c)->size(); }
 unsigned ref_cat_keys_size(void* c) { return ((NVCategory*)c)->keys_size(); }
 void* ref_cat_keys(void* c) { GUARD(return ((NVCategory*)c)->get_keys(), nullptr); }
 int ref_cat_values(void* c, int* out) { GUARD(return ((NVCategory*)c)->get_values(out, false), -100); }
+// kind 0: merge_category, 1: merge_and_remap
+void* ref_cat_merge(void* c1, void* c2, int kind)
+{
+    GUARD(return kind ? ((NVCategory*)c1)->merge_and_remap(*(NVCategory*)c2) : ((NVCategory*)c1)->merge_category(*(NVCategory*)c2), nullptr);
+}
+void* ref_cat_from_categories(void** cs, int n)
+{
+    std::vector<NVCategory*> v;
+    for (int i = 0; i < n; ++i) v.push_back((NVCategory*)cs[i]);
+    GUARD(return NVCategory::create_from_categories(v), nullptr);
+}
 void* ref_cat_to_strings(void* c) { GUARD(return ((NVCategory*)c)->to_strings(), nullptr); }
 
 }  // extern "C"

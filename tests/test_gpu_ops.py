@@ -145,6 +145,25 @@ def test_tokenize(cols, oracle):
         assert nvtext.token_count(dev, d) == wc.tolist(), d
 
 
+def test_category_merge(oracle):
+    from custrings_b200 import nvstrings, nvcategory
+    rng = random.Random(9)
+    pools = [["eee", "aaa", "ddd", None, "é"], ["zzz", "aaa", "", "bbb", None, "日本"], ["ccc", "eee", "a", "B"], ["x"]]
+    lists = [[rng.choice(p) for _ in range(rng.randrange(50, 400))] for p in pools]
+    lists.append([s for s in lists[0] if s is not None])  # no null key on this side
+    dev = [nvcategory.from_strings(nvstrings.to_device(l)) for l in lists]
+    ref = [oracle.RefCategory(oracle.RefStrings.from_list(l)) for l in lists]
+
+    def same(d, r):
+        assert d.keys().to_host() == [None if k is None else k.decode() for k in r.keys().to_list()]
+        assert d.values() == r.values().tolist()
+
+    for i, j in ((0, 1), (1, 0), (2, 3), (3, 2), (4, 1), (1, 4), (0, 0)):
+        same(dev[i].merge_and_remap(dev[j]), ref[i].merge_and_remap(ref[j]))
+        same(dev[i].merge_category(dev[j]), ref[i].merge_category(ref[j]))
+    same(nvcategory.from_categories(dev[:4]), oracle.RefCategory.from_categories(ref[:4]))
+
+
 def test_tokenize_bitstream_large(oracle):
     """tokenize through the bit-stream compaction kernels on a column spanning many windows and work items: rows longer
     than a 32 KiB item (several item boundaries inside one row / one window), empty and null rows, multi-byte characters"""
