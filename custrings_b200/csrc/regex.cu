@@ -360,48 +360,63 @@ k_chain_replace(ColView col, const __grid_constant__ bits::ChainDev cd, const ui
 }
 
 // ---- span path over the chain kernel's bit streams (span_walk.cuh): a few word scans per match ------------------------
+// Rows the chain kernel's boolean result rejected have no match: only the others are walked.  A warp compacts the hit rows
+// of 128 consecutive rows into a dense list first, so every lane of the (divergent, loop-heavy) walk has a row to work on.
+// (Staging the stream slices in shared memory as the splice does was measured slower here: these walks live on occupancy.)
+template <typename Miss, typename Hit>
+__device__ __forceinline__ void for_hit_rows(int n, const uint8_t* __restrict__ hits, Miss on_miss, Hit on_hit)
+{
+    constexpr int CHUNK = 128;
+    __shared__ int32_t lists[8][CHUNK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    int32_t* list = lists[warp];
+    for (int base = (blockIdx.x * warps + warp) * CHUNK; base < n; base += gridDim.x * warps * CHUNK) {
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < CHUNK / 32; ++k) {
+            const int i = base + 32 * k + lane;
+            const bool h = i < n && hits[i];
+            if (i < n && !h) on_miss(i);
+            const unsigned m = __ballot_sync(0xffffffffu, h);
+            if (h) list[cnt + __popc(m & ((1u << lane) - 1u))] = i;
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        for (int idx = lane; idx < cnt; idx += 32) on_hit(list[idx]);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_span_count(ColView col, spans::Streams S, const uint8_t* __restrict__ hits, int k_chars, int32_t* __restrict__ out,
              unsigned long long* __restrict__ total)
 {
-    for (int base = blockIdx.x * blockDim.x; base < col.n; base += gridDim.x * blockDim.x) {
-        const int i = base + threadIdx.x;
-        int found = 0;
-        if (i < col.n) {
-            if (hits[i])
-                found = spans::walk_spans(S, (const uint8_t*)col.chars, col.offsets[i], col.offsets[i + 1], k_chars, 0x7fffffff, [](int, int) {});
+    unsigned long long mine = 0;
+    for_hit_rows(
+        col.n, hits, [&](int i) { out[i] = 0; },
+        [&](int i) {
+            const int found = spans::walk_spans(S, (const uint8_t*)col.chars, col.offsets[i], col.offsets[i + 1], k_chars, 0x7fffffff, [](int, int) {});
             out[i] = found;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, found != 0);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(total, (unsigned long long)__popc(m));
-    }
+            mine += found != 0;
+        });
+    if (mine) atomicAdd(total, mine);
 }
 
-// out_chars == null: size pass (out_len); else write pass
+// size pass of replace_re: new byte length of every row
 __global__ void __launch_bounds__(256)
-k_span_replace(ColView col, spans::Streams S, const uint8_t* __restrict__ hits, int k_chars, const char* __restrict__ repl, int repl_len,
-               int maxrepl, int32_t* __restrict__ out_len, const int32_t* __restrict__ out_off, char* __restrict__ out_chars)
+k_span_replace(ColView col, spans::Streams S, const uint8_t* __restrict__ hits, int k_chars, int repl_len, int maxrepl,
+               int32_t* __restrict__ out_len)
 {
     const uint8_t* chars = (const uint8_t*)col.chars;
     const int budget = maxrepl < 0 ? 0x7fffffff : maxrepl;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < col.n; i += gridDim.x * blockDim.x) {
-        const int a = col.offsets[i], b = col.offsets[i + 1];
-        if (!out_chars) {
+    for_hit_rows(
+        col.n, hits, [&](int i) { out_len[i] = col.offsets[i + 1] - col.offsets[i]; },
+        [&](int i) {
+            const int a = col.offsets[i], b = col.offsets[i + 1];
             int total = b - a;
-            if (hits[i]) spans::walk_spans(S, chars, a, b, k_chars, budget, [&](int s, int e) { total += repl_len - (e - s); });
+            spans::walk_spans(S, chars, a, b, k_chars, budget, [&](int s, int e) { total += repl_len - (e - s); });
             out_len[i] = total;
-            continue;
-        }
-        char* o = out_chars + out_off[i];
-        int last = a;
-        if (hits[i])
-            spans::walk_spans(S, chars, a, b, k_chars, budget, [&](int s, int e) {
-                for (int q = last; q < s; ++q) *o++ = (char)chars[q];
-                for (int q = 0; q < repl_len; ++q) *o++ = repl[q];
-                last = e;
-            });
-        for (int q = last; q < b; ++q) *o++ = (char)chars[q];
-    }
+        });
 }
 
 // write pass as a warp-cooperative SPLICE.  A warp takes 32 consecutive rows: their chars are one contiguous byte range and
@@ -1010,8 +1025,8 @@ custr_column* custr_replace_re(const custr_column* col, const char* pattern, con
                 SpanRun sr;
                 if (run_span_streams(*c, col, sr)) {
                     const int k_chars = (int)cd->nsteps - 1;
-                    LAUNCH(k_span_replace, vm_grid(n) * 2, 256, 0, view_of(col), sr.view(), (const uint8_t*)sr.hits->ptr, k_chars,
-                           (const char*)d_repl->ptr, repl_len, maxrepl, lens.get(), (const int32_t*)nullptr, (char*)nullptr);
+                    LAUNCH(k_span_replace, vm_grid(n) * 2, 256, 0, view_of(col), sr.view(), (const uint8_t*)sr.hits->ptr, k_chars, repl_len, maxrepl,
+                           lens.get());
                     if (read_dirty(sr) == 0) {
                         BufPtr off2;
                         int64_t total2 = 0;
