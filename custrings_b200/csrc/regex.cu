@@ -564,15 +564,17 @@ struct SpanRun {
     unsigned int* dirty_count = nullptr;
     spans::Streams view() const { return spans::Streams{ss.m, ss.k, ss.a, ss.base}; }
 };
-static bool run_span_streams(Compiled& c, const custr_column* col, SpanRun& r)
+// (r.ss.counts_out set: count mode — per-row match counts straight from the chain kernel, `total` = rows with a match)
+static bool run_span_streams(Compiled& c, const custr_column* col, SpanRun& r, unsigned long long* total = nullptr)
 {
     if (!span_plan(c) || !cap_tier((int)c.prog.insts.size())) return false;
+    if (r.ss.counts_out && !bits::count_in_kernel_ok(*c.plan_contains)) return false;
     r.hits = dev_alloc((size_t)col->n);
     Scratch<unsigned long long> unused(1);
     CUSTR_CUDA(cudaMemsetAsync(unused.get(), 0, 8, g_stream));
     int32_t* dirty_rows = nullptr;
     const bool ok = bits::run(*c.plan_contains, col, (const uint8_t*)c.dev_image->ptr, device_unicode_flags(), (uint8_t*)r.hits->ptr,
-                              unused.get(), &dirty_rows, &r.dirty_count, r.keep_rows, r.keep_count, &r.ss);
+                              total ? total : unused.get(), &dirty_rows, &r.dirty_count, r.keep_rows, r.keep_count, &r.ss);
     return ok;  // `unused` is freed stream-ordered
 }
 static unsigned int read_dirty(const SpanRun& r)
@@ -863,6 +865,19 @@ int custr_count_re(const custr_column* col, const char* pattern, int32_t* result
             Scratch<unsigned long long> total(1);
             CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
             if (const bits::ChainDev* cd = span_plan(*c)) {  // last-loop chain
+                {   // every step on the loop's class: the chain kernel counts by itself (k_chain64 count mode)
+                    SpanRun cr;
+                    cr.ss.counts_out = out.dev;
+                    if (run_span_streams(*c, col, cr, total.get())) {
+                        int matches = (int)read_counter(total.get());
+                        if (read_dirty(cr) == 0) {
+                            g_last_tier = "bitcount";
+                            out.finish();
+                            return matches;
+                        }
+                        CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
+                    }
+                }
                 SpanRun sr;
                 if (run_span_streams(*c, col, sr)) {  // bit streams + word scans (rows holding NUL: fall through)
                     LAUNCH(k_span_count, vm_grid(n) * 2, 256, 0, view_of(col), sr.view(), (const uint8_t*)sr.hits->ptr, (int)cd->nsteps - 1, out.dev,

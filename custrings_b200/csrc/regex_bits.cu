@@ -59,6 +59,7 @@ struct Args {
     const uint8_t* uflags;
     // span streams (count_re / replace_re of last-loop chains, span_walk.cuh): one bit per byte, word w covers the bytes
     // [span_base + 64 w, span_base + 64 w + 64); null = not wanted
+    int32_t* counts;          // non-null: count mode of k_chain64 (matches per row instead of the boolean result)
     unsigned long long* span_m;
     unsigned long long* span_k;
     unsigned long long* span_a;
@@ -445,15 +446,29 @@ __global__ void k_item_bounds(const int32_t* __restrict__ offsets, int n, int fi
 
 const PlanDev& device_plan(const Plan& plan);
 
+// count_re inside the chain kernel (see k_chain64's count mode): the last step loops and every step uses its class
+bool count_in_kernel_ok(const Plan& plan)
+{
+    if (!plan.is_chain || !plan.span_ok) return false;
+    const ChainDev& cd = plan.chain;
+    if (cd.nsteps == 0 || !cd.steps[cd.nsteps - 1].loop) return false;
+    for (uint32_t s = 0; s < cd.nsteps; ++s)
+        if (cd.steps[s].cls != cd.steps[cd.nsteps - 1].cls) return false;
+    return true;
+}
+
 bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, const uint8_t* uflags, uint8_t* out,
          unsigned long long* total, int32_t** dirty_rows, unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count,
          SpanStreams* spans)
 {
     if (spans && !(plan.is_chain && plan.span_ok && !g_force_generic && !g_chain32)) return false;
+    int32_t* counts = spans ? spans->counts_out : nullptr;
+    if (counts && !count_in_kernel_ok(plan)) return false;
 
     const int32_t n = col->n;
     if (((uintptr_t)col->chars & 15) != 0) return false;  // vector loads need a 16-byte aligned base
-    CUSTR_CUDA(cudaMemsetAsync(out, 0, (size_t)n, g_stream));
+    if (counts) CUSTR_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n, g_stream));
+    else CUSTR_CUDA(cudaMemsetAsync(out, 0, (size_t)n, g_stream));
     keep_rows = dev_alloc(sizeof(int32_t) * (size_t)(n ? n : 1));
     keep_count = dev_alloc(2 * sizeof(unsigned int));  // [0] dirty-row count, [1] work-item counter
     CUSTR_CUDA(cudaMemsetAsync(keep_count->ptr, 0, 2 * sizeof(unsigned int), g_stream));
@@ -477,7 +492,8 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     a.uflags = uflags;
     a.span_m = a.span_k = a.span_a = nullptr;
     a.span_base = 0;
-    if (spans) {
+    a.counts = counts;
+    if (spans && !counts) {
         a.span_base = a.first & ~(WIN64 - 1);
         const size_t words = (((size_t)(a.end - a.span_base) + WIN64 - 1) / WIN64) * (WIN64 / 64);
         spans->keep = dev_alloc(3 * words * sizeof(unsigned long long));

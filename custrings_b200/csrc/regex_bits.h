@@ -30,7 +30,11 @@ struct SpanStreams {
     const unsigned long long* a = nullptr;
     int32_t base = 0;   // byte offset (into chars) of bit 0
     BufPtr keep;
+    // count mode: when set (and count_in_kernel_ok(plan)) the kernel writes the number of matches of every row here and
+    // leaves no streams; `out` of run() is then unused
+    int32_t* counts_out = nullptr;
 };
+bool count_in_kernel_ok(const Plan& plan);
 bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, const uint8_t* uflags, uint8_t* out,
          unsigned long long* total, int32_t** dirty_rows, unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count,
          SpanStreams* spans = nullptr);

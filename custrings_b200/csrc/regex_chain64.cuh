@@ -129,8 +129,9 @@ __device__ __forceinline__ u64 sel_class64(const u64 (&c)[NCLS], uint32_t k)
 struct __align__(64) WarpSm64 {
     char ring[RING_STAGES][WIN64];
     uint32_t rs[64], f[64], d[64];
+    uint32_t pc[32];  // count mode: exclusive prefix of popc over the lanes' words of the stream in f
 };
-constexpr uint32_t SM_RS = RING_STAGES * WIN64, SM_F = SM_RS + 256, SM_D = SM_F + 256;
+constexpr uint32_t SM_RS = RING_STAGES * WIN64, SM_F = SM_RS + 256, SM_D = SM_F + 256, SM_C = SM_D + 256;
 __device__ __forceinline__ uint32_t lds32(uint32_t a)
 {
     uint32_t v;
@@ -372,6 +373,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
         for (int s = 0; s < NS; ++s) st.last[s] = 0;
         st.last_al = st.last_nl = st.last_f = st.last_d = 0;
         uint32_t d_live = 0;
+        int carry = 0;  // count mode: matches of the straddling row found in earlier windows
         int ws = byte_a & ~(WIN64 - 1);
         int kcur = ra + 1;       // next offsets index to consume; offsets[j] >= ws for every j >= kcur
         int prev_o = byte_a;     // offsets[kcur - 1]
@@ -482,9 +484,50 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
                                                  sink);
 
             // ---- sticky per-row OR of the match bits; NUL bytes make a row "dirty" (decided by the exact VM)
+            // Count mode (count_re of chains whose steps all use the loop's class, e.g. \b\w{4,}\b, \d+): every match lies
+            // inside one maximal run of the class and a run holds at most one match (its first admissible start, then the
+            // LAST end in the run), so the number of matches of a row is the number of runs holding at least one match end
+            // = the number of match-end bits that are the first one of their run:  V = E & ~(advance(spread(E, K)) & K).
+            // A row's count is then a difference of prefix popcounts of V (+ a carry for the row that straddles windows).
             const u64 nrs = ~rs;
-            const u64 F = spread64(E, nrs, st.last_f, L);
-            st.last_f = hi32(F);
+            const bool count_mode = A.counts != nullptr;
+            u64 F;
+            uint32_t vtotal = 0;
+            if (!count_mode) {
+                F = spread64(E, nrs, st.last_f, L);
+                st.last_f = hi32(F);
+            } else {
+                const u64 K = sel_class64<NCLS>(c, PV_STEP_CLS(NS - 1)) & nrs;
+                const uint32_t oldg = st.last_f;
+                const u64 G = spread64(E, K, oldg, L);
+                st.last_f = hi32(G);
+                F = E & ~(adv64(G, oldg, L) & K);
+                const uint32_t pcnt = (uint32_t)__popcll(F);
+                uint32_t inc = pcnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL, inc, d);
+                    if ((int)lane >= d) inc += v;
+                }
+                vtotal = __shfl_sync(FULL, inc, 31);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(wb + SM_C + 4u * lane), "r"(inc - pcnt) : "memory");
+            }
+            auto prefix_at = [&](int x) -> int {  // V bits of this window at positions < x
+                if (x >= WIN64) return (int)vtotal;
+                const uint32_t l = (uint32_t)x >> 6;
+                return (int)lds32(wb + SM_C + 4u * l) + __popcll(lds64(wb + SM_F + 8u * l) & ((1ull << (x & 63)) - 1ull));
+            };
+            auto row_result = [&](int o_begin, int o_end, int row, bool dirty) -> bool {  // row [o_begin, o_end), o_end in (ws, we]
+                if (!count_mode) {
+                    const bool hit = stream_bit(wb + SM_F, o_end - 1 - ws);
+                    if (!dirty) A.out[row] = hit;
+                    return hit;
+                }
+                const int x0 = o_begin - ws;
+                const int cnt = prefix_at(o_end - ws) - (x0 > 0 ? prefix_at(x0) : 0) + (x0 < 0 ? carry : 0);
+                if (!dirty) A.counts[row] = cnt;
+                return cnt != 0;
+            };
             sts64(my_w + SM_F, lo32(F), hi32(F));
             const bool any_dirty = __any_sync(FULL, zero != 0) || d_live;
             if (any_dirty) {
@@ -501,10 +544,8 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
                 if (lane == 0) o_prev = prev_o;
                 bool hit = false, dirty = false;
                 if (inw && o > o_prev) {  // non-empty row j-1, last byte o-1 >= ws
-                    const int b = o - 1 - ws;
-                    hit = stream_bit(wb + SM_F, b);
-                    dirty = any_dirty && stream_bit(wb + SM_D, b);
-                    if (!dirty) A.out[j - 1] = hit;
+                    dirty = any_dirty && stream_bit(wb + SM_D, o - 1 - ws);
+                    hit = row_result(o_prev, o, j - 1, dirty);
                 }
                 if (any_dirty) {
                     const unsigned dm = __ballot_sync(FULL, dirty);
@@ -524,10 +565,8 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
                     if (j2 < kcur + consumed) {
                         const int o2 = __ldg(A.offsets + j2), o2p = __ldg(A.offsets + j2 - 1);
                         if (o2 > o2p) {
-                            const int b = o2 - 1 - ws;
-                            hit = stream_bit(wb + SM_F, b);
-                            dirty = any_dirty && stream_bit(wb + SM_D, b);
-                            if (!dirty) A.out[j2 - 1] = hit;
+                            dirty = any_dirty && stream_bit(wb + SM_D, o2 - 1 - ws);
+                            hit = row_result(o2p, o2, j2 - 1, dirty);
                         }
                     }
                     const unsigned dm = __ballot_sync(FULL, dirty);
@@ -544,6 +583,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
                 prev_o = m_in == FULL ? __ldg(A.offsets + kcur + consumed - 1) : __shfl_sync(FULL, o, consumed - 1);
                 kcur += consumed;
             }
+            if (count_mode) carry = consumed ? (prev_o >= we ? 0 : (int)vtotal - prefix_at(prev_o - ws)) : carry + (int)vtotal;
             pend = at_we ? 0 : -1;
             __syncwarp();
         }

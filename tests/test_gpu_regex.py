@@ -125,7 +125,8 @@ def test_rows_with_nul_bytes_fall_back_exactly(oracle):
         assert lib().custr_last_regex_tier() == b"pikevm"
         assert oracle.unpack(*dev.replace(p, "#").to_arrays()) == ref.replace_re(p, "#").to_list(), p
     clean = nvstrings.to_device(["abcd efgh", "x1 y22 z333"])
-    assert clean.count(r"\d+") == [0, 3] and lib().custr_last_regex_tier() == b"bitspans"
+    assert clean.count(r"\d+") == [0, 3] and lib().custr_last_regex_tier() == b"bitcount"   # counted inside the chain kernel
+    assert clean.count(r"x\d+") == [0, 1] and lib().custr_last_regex_tier() == b"bitspans"  # prefix outside the loop class: stream walk
     lib().custr_set_regex_tier(2)  # generic bitstream kernel forced: span streams unavailable -> scalar chain matcher
     try:
         assert clean.count(r"\d+") == [0, 3] and lib().custr_last_regex_tier() == b"chainspan"
@@ -150,14 +151,15 @@ def test_count_replace_span_streams(oracle):
     strs += ["", None, "", "a"] * 50
     rng.shuffle(strs)
     dev, ref = nvstrings.to_device(strs), oracle.RefStrings.from_list(strs)
-    used = 0
+    used = counted = 0
     for p in SPAN_PATTERNS:
         want = ref.count_re(p)[0].tolist()
         got = _none_to(0, dev.count(p))
         tier = lib().custr_last_regex_tier()
         assert got == want, (p, tier)
-        used += tier == b"bitspans"
+        used += tier in (b"bitspans", b"bitcount")
+        counted += tier == b"bitcount"
         for repl, mx in (("<>", -1), ("", 2), ("é日", 1), ("#", 0), ("<" * 37 + ">", -1)):  # the long one overflows the splice tile
             want = ref.replace_re(p, repl, mx).to_list()
             assert oracle.unpack(*dev.replace(p, repl, mx).to_arrays()) == want, (p, repl, mx, lib().custr_last_regex_tier())
-    assert used >= 15, used
+    assert used >= 15 and counted >= 8, (used, counted)
