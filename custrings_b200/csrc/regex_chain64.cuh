@@ -302,7 +302,7 @@ __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[N
         st.last[s] = hi32(Z);
         old_prev = old;
         P = Z & fin;
-        if (s == NS - 1 && sink.m != nullptr)  // span streams of the last step (span_walk.cuh); out of line: cold for contains_re / match
+        if (s == NS - 1 && __builtin_expect(sink.m != nullptr, 0))  // span streams of the last step (span_walk.cuh); out of line: cold for contains_re / match
             store_spans(sink, t,                                                           // M: first character of the last step, lead byte
                         PV_STEP_LOOP(s) ? (ck & nrs) : (ck & cont),                       // K: the match may continue INTO this byte
                         PV_END_MASK ? apply_after64_generic(fin, PV_END_MASK, as) : fin);  // A: a match may end after this byte
@@ -400,7 +400,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
             const unsigned m_in = __ballot_sync(FULL, inw);
             bool at_we = __any_sync(FULL, inw && o == we);
             int consumed = __popc(m_in);
-            if (m_in == FULL) {  // more than 32 rows end in this window (short / empty rows): generic loop
+            if (__builtin_expect(m_in == FULL, 0)) {  // more than 32 rows end in this window (short / empty rows): generic loop
                 for (;;) {
                     int j2 = kcur + consumed + (int)lane;
                     int o2 = j2 <= rb ? __ldg(A.offsets + j2) : 0x7fffffff;
@@ -493,7 +493,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
             const bool count_mode = A.counts != nullptr;
             u64 F;
             uint32_t vtotal = 0;
-            if (!count_mode) {
+            if (__builtin_expect(!count_mode, 1)) {
                 F = spread64(E, nrs, st.last_f, L);
                 st.last_f = hi32(F);
             } else {
@@ -518,7 +518,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
                 return (int)lds32(wb + SM_C + 4u * l) + __popcll(lds64(wb + SM_F + 8u * l) & ((1ull << (x & 63)) - 1ull));
             };
             auto row_result = [&](int o_begin, int o_end, int row, bool dirty) -> bool {  // row [o_begin, o_end), o_end in (ws, we]
-                if (!count_mode) {
+                if (__builtin_expect(!count_mode, 1)) {
                     const bool hit = stream_bit(wb + SM_F, o_end - 1 - ws);
                     if (!dirty) A.out[row] = hit;
                     return hit;
@@ -530,7 +530,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
             };
             sts64(my_w + SM_F, lo32(F), hi32(F));
             const bool any_dirty = __any_sync(FULL, zero != 0) || d_live;
-            if (any_dirty) {
+            if (__builtin_expect(any_dirty, 0)) {
                 const u64 D = spread64(zero, nrs, st.last_d, L);
                 st.last_d = hi32(D);
                 sts64(my_w + SM_D, lo32(D), hi32(D));
@@ -547,7 +547,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
                     dirty = any_dirty && stream_bit(wb + SM_D, o - 1 - ws);
                     hit = row_result(o_prev, o, j - 1, dirty);
                 }
-                if (any_dirty) {
+                if (__builtin_expect(any_dirty, 0)) {
                     const unsigned dm = __ballot_sync(FULL, dirty);
                     if (dm) {
                         unsigned basei = 0;
@@ -558,7 +558,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
                 }
                 my_matches += __popc(__ballot_sync(FULL, hit && !dirty));
             }
-            if (m_in == FULL) {  // remaining chunks: reload
+            if (__builtin_expect(m_in == FULL, 0)) {  // remaining chunks: reload
                 for (int k2 = kcur + 32; k2 < kcur + consumed; k2 += 32) {
                     const int j2 = k2 + (int)lane;
                     bool hit = false, dirty = false;
@@ -583,7 +583,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
                 prev_o = m_in == FULL ? __ldg(A.offsets + kcur + consumed - 1) : __shfl_sync(FULL, o, consumed - 1);
                 kcur += consumed;
             }
-            if (count_mode) carry = consumed ? (prev_o >= we ? 0 : (int)vtotal - prefix_at(prev_o - ws)) : carry + (int)vtotal;
+            if (__builtin_expect(count_mode, 0)) carry = consumed ? (prev_o >= we ? 0 : (int)vtotal - prefix_at(prev_o - ws)) : carry + (int)vtotal;
             pend = at_we ? 0 : -1;
             __syncwarp();
         }
