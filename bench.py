@@ -191,6 +191,7 @@ def main():
     L.custr_set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L.custr_set_stream(torch.cuda.current_stream().cuda_stream)
     L.custr_set_regex_tier(args.tier)
