@@ -4,7 +4,7 @@
 // not a CPU fallback: nothing in custrings_b200/ links or loads it.
 #include "../../custrings_b200/csrc/regex_vm.cuh"
 #include "../../custrings_b200/csrc/rowops.cuh"
-#include "../../custrings_b200/csrc/regex_bits_core.cuh"
+#include "../../custrings_b200/csrc/regex_bits.h"
 #include "../../custrings_b200/csrc/chain_spans.cuh"
 #include <vector>
 #include <string>
