@@ -188,6 +188,20 @@ __device__ __noinline__ NaClasses<NCLS> classify_non_ascii64(const ChainDev& cd,
     };
     while (na) {
         const int b = __ffsll((long long)na) - 1;
+        if (b < 63) {  // fast path: a 2-byte character (U+0080..U+07FF) that lies inside this lane's 64 bytes
+            const uint32_t lead = lds8((my0 ^ (uint32_t)(b & 48)) + (uint32_t)(b & 15));
+            const uint32_t next = lds8((my0 ^ (uint32_t)((b + 1) & 48)) + (uint32_t)((b + 1) & 15));
+            if ((lead & 0xE0u) == 0xC0u && (next & 0xC0u) == 0x80u) {
+                const uint32_t cp = ((lead & 0x1Fu) << 6) | (next & 0x3Fu);
+                const u64 bits = 3ull << b;
+                na &= ~bits;
+#pragma unroll
+                for (int k = 0; k < NCLS; ++k)
+                    if (k < (int)PV_NCLASSES) r.c[k] = ((cd.classes[k].na2[cp >> 5] >> (cp & 31)) & 1u) ? (r.c[k] | bits) : (r.c[k] & ~bits);
+                r.al = ((cd.na2_alnum[cp >> 5] >> (cp & 31)) & 1u) ? (r.al | bits) : (r.al & ~bits);
+                continue;
+            }
+        }
         int q = lane_base + b;
         while (q > A.first && (byte_at(q) & 0xC0u) == 0x80u) --q;  // only the leading continuation run has to walk back
         uint32_t ch = byte_at(q);

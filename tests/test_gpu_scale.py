@@ -135,10 +135,11 @@ def test_c4_category_roundtrip_large():
 def test_c1_split_csv_shape(oracle):
     from custrings_b200 import nvstrings
     rng = np.random.Generator(np.random.PCG64(3))
-    rows = ["%d,%s,%d.%02d,%s,,x" % (i, "ab" * int(rng.integers(0, 4)), rng.integers(0, 99), rng.integers(0, 99), "é" if i % 7 == 0 else "q")
-            for i in range(985)]
+    rows = ["%d,%s,%d.%02d,%s,,x,%d,Sacramento,CA,%05d,Residential,%d" %
+            (i, "ab" * int(rng.integers(0, 4)), rng.integers(0, 99), rng.integers(0, 99), "é" if i % 7 == 0 else "q", rng.integers(1, 6),
+             rng.integers(0, 99999), rng.integers(1000, 900000)) for i in range(985)]  # 985 rows x 12 columns like data/985-rows.csv
     cols = nvstrings.to_device(rows).split(",")
     want = oracle.RefStrings.from_list(rows).split(",")
-    assert len(cols) == len(want) == 6
+    assert len(cols) == len(want) == 12
     for a, b in zip(cols, want):
         assert oracle.unpack(*a.to_arrays()) == b.to_list()
