@@ -84,6 +84,72 @@ k_representatives(const int32_t* __restrict__ heads, const int32_t* __restrict__
         if (heads[j]) { int g = gids[j] - 1; reps[g] = rows[j]; group_ids[g] = g; }
 }
 
+// ---- hash-table path: few distinct keys (the usual shape of categorical data) ------------------------------------------------
+// Pass 1 hashes every row and inserts the hash into an open-addressing table (linear probing; a plain read first, the CAS
+// only while the slot still looks empty, so the ~N lookups of K << N distinct keys are cache hits, not contended atomics).
+// The thread that wins a slot registers its row as the key's representative.  Pass 2 (after the K representatives were
+// sorted with the reference's comparator) compares every row with its representative BYTE FOR BYTE — a 64-bit collision
+// or a table that fills beyond half sends the whole build to the sort path below — and writes values[row] = rank.
+constexpr int HT_BITS = 20;  // 1 Mi slots: up to 512 Ki distinct keys
+__global__ void __launch_bounds__(CAT_THREADS)
+k_ht_insert(ColView col, uint64_t seed, unsigned long long* __restrict__ tab, int32_t* __restrict__ slot_group, int32_t* __restrict__ reps,
+            int32_t* __restrict__ nkeys, int32_t* __restrict__ row_slot, int32_t* __restrict__ null_rep)
+{
+    const uint32_t mask = (1u << HT_BITS) - 1u;
+    const int32_t max_keys = 1 << (HT_BITS - 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < col.n; i += gridDim.x * blockDim.x) {
+        if (*(volatile int32_t*)nkeys > max_keys) { row_slot[i] = -2; continue; }  // too many distinct keys: the host switches paths
+        if (!col.valid(i)) {
+            row_slot[i] = -1;
+            if (*(volatile int32_t*)null_rep < 0) atomicCAS(null_rep, -1, i);
+            continue;
+        }
+        const uint8_t* s = (const uint8_t*)col.chars + col.offsets[i];
+        const int n = col.offsets[i + 1] - col.offsets[i];
+        uint64_t h = seed ^ ((uint64_t)n * 0x9E3779B97F4A7C15ULL);
+        int k = 0;
+        for (; k + 8 <= n; k += 8) {
+            uint64_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v |= (uint64_t)s[k + j] << (8 * j);
+            h = mix64(h ^ v) + 0x9E3779B97F4A7C15ULL;
+        }
+        uint64_t v = 0;
+        for (int j = 0; k + j < n; ++j) v |= (uint64_t)s[k + j] << (8 * j);
+        h = mix64(h ^ v);
+        if (h == 0) h = 1;  // 0 = empty slot
+        uint32_t slot = (uint32_t)(h >> 20) & mask;
+        for (int probe = 0;; ++probe) {
+            unsigned long long cur = *(volatile unsigned long long*)(tab + slot);
+            if (cur == 0) {
+                cur = atomicCAS(tab + slot, 0ull, (unsigned long long)h);
+                if (cur == 0) {  // this thread created the key
+                    const int g = atomicAdd(nkeys, 1);
+                    if (g < max_keys) reps[g] = i;
+                    slot_group[slot] = g;
+                    cur = h;
+                }
+            }
+            if (cur == h) { row_slot[i] = (int32_t)slot; break; }
+            slot = (slot + 1) & mask;
+            if ((probe & 63) == 63 && *(volatile int32_t*)nkeys > max_keys) { row_slot[i] = -2; break; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CAT_THREADS)
+k_ht_values(ColView col, const int32_t* __restrict__ row_slot, const int32_t* __restrict__ slot_group, const int32_t* __restrict__ reps,
+            const int32_t* __restrict__ rank, int null_group, int32_t* __restrict__ values, int* __restrict__ collision)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < col.n; i += gridDim.x * blockDim.x) {
+        const int slot = row_slot[i];
+        if (slot < 0) { values[i] = slot == -1 ? rank[null_group] : 0; if (slot == -2) *collision = 1; continue; }
+        const int g = slot_group[slot];
+        if (!rows_equal(col, i, reps[g])) *collision = 1;  // two different strings with one 64-bit hash
+        values[i] = rank[g];
+    }
+}
+
 struct KeyLess {
     ColView col;
     __device__ bool operator()(const int32_t& a, const int32_t& b) const
@@ -96,6 +162,17 @@ struct KeyLess {
     }
 };
 
+__global__ void k_iota(int32_t* __restrict__ a, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+// after the sort: sorted_reps[r] is the representative of group sorted_groups[r]
+__global__ void k_scatter_reps(const int32_t* __restrict__ sorted_reps, const int32_t* __restrict__ sorted_groups, int k, int32_t* __restrict__ rep_of_group)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < k) rep_of_group[sorted_groups[r]] = sorted_reps[r];
+}
 __global__ void k_rank_of_group(const int32_t* __restrict__ sorted_groups, int k, int32_t* __restrict__ rank)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,6 +256,60 @@ static custr_column* concat_columns(const custr_column* const* cols, int ncols)
     return make_column(chars, off, bits, (int32_t)rows, nulls, bytes);
 }
 
+// false: more than 512 Ki distinct keys or a hash collision -> the caller takes the sort path
+static bool build_category_hashed(const custr_column* col, custr_category* cat)
+{
+    const int32_t n = col->n;
+    const size_t slots = (size_t)1 << HT_BITS;
+    const int32_t max_keys = 1 << (HT_BITS - 1);
+    BufPtr tab = dev_alloc(sizeof(unsigned long long) * slots);
+    Scratch<int32_t> slot_group(slots), reps((size_t)max_keys + 1), row_slot(n), counters(2);
+    Scratch<int> collision(1);
+    CUSTR_CUDA(cudaMemsetAsync(tab->ptr, 0, sizeof(unsigned long long) * slots, g_stream));
+    const int32_t init[2] = {0, -1};  // nkeys, null representative
+    CUSTR_CUDA(cudaMemcpyAsync(counters.get(), init, sizeof(init), cudaMemcpyHostToDevice, g_stream));
+    CUSTR_CUDA(cudaMemsetAsync(collision.get(), 0, sizeof(int), g_stream));
+    LAUNCH(k_ht_insert, row_grid(n), CAT_THREADS, 0, view_of(col), 0x243F6A8885A308D3ULL, (unsigned long long*)tab->ptr, slot_group.get(),
+           reps.get(), counters.get(), row_slot.get(), counters.get() + 1);
+    int32_t h_cnt[2] = {0, -1};
+    CUSTR_CUDA(cudaMemcpyAsync(h_cnt, counters.get(), sizeof(h_cnt), cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    int32_t nkeys = h_cnt[0];
+    if (nkeys > max_keys) return false;
+    int null_group = 0;
+    if (h_cnt[1] >= 0) {  // the null key: one more representative (it sorts first)
+        null_group = nkeys;
+        CUSTR_CUDA(cudaMemcpyAsync(reps.get() + nkeys, &h_cnt[1], sizeof(int32_t), cudaMemcpyHostToDevice, g_stream));
+        ++nkeys;
+    }
+    Scratch<int32_t> groups(nkeys ? nkeys : 1), rank(nkeys ? nkeys : 1);
+    if (nkeys) {
+        LAUNCH(k_iota, (nkeys + 255) / 256, 256, 0, groups.get(), nkeys);
+        size_t merge_bytes = 0;
+        KeyLess less{view_of(col)};
+        cub::DeviceMergeSort::SortPairs(nullptr, merge_bytes, reps.get(), groups.get(), nkeys, less, g_stream);
+        BufPtr mtmp = dev_alloc(merge_bytes);
+        CUSTR_CUDA(cub::DeviceMergeSort::SortPairs(mtmp->ptr, merge_bytes, reps.get(), groups.get(), nkeys, less, g_stream));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        LAUNCH(k_rank_of_group, (nkeys + 255) / 256, 256, 0, (const int32_t*)groups.get(), nkeys, rank.get());
+    }
+    // reps is now in key order; the value pass needs the representative of a GROUP: keep an unsorted copy
+    // (sorted reps feed the keys gather, group -> representative goes through rank)
+    Scratch<int32_t> rep_of_group(nkeys ? nkeys : 1);
+    if (nkeys) LAUNCH(k_scatter_reps, (nkeys + 255) / 256, 256, 0, (const int32_t*)reps.get(), (const int32_t*)groups.get(), nkeys, rep_of_group.get());
+    LAUNCH(k_ht_values, row_grid(n), CAT_THREADS, 0, view_of(col), (const int32_t*)row_slot.get(), (const int32_t*)slot_group.get(),
+           (const int32_t*)rep_of_group.get(), (const int32_t*)rank.get(), null_group, (int32_t*)cat->values_buf->ptr, collision.get());
+    int hit = 0;
+    CUSTR_CUDA(cudaMemcpyAsync(&hit, collision.get(), sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    if (hit) return false;
+    cat->keys = custr_gather(col, reps.get(), nkeys, 1);
+    if (!cat->keys) throw CudaError{cudaErrorUnknown};
+    cat->has_null_key = col->nulls > 0;
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    return true;
+}
+
 static custr_category* build_category(const custr_column* col)
 {
     const int32_t n = col->n;
@@ -190,6 +321,7 @@ static custr_category* build_category(const custr_column* col)
         cat->keys = custr_create_from_offsets(nullptr, 0, nullptr, nullptr, 0, 0);
         return guard.release();
     }
+    if (build_category_hashed(col, cat)) return guard.release();
     Scratch<uint64_t> h_in(n), h_out(n);
     Scratch<int32_t> r_in(n), r_out(n), heads(n), gids(n);
     Scratch<int> collision(1);

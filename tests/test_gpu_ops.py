@@ -145,6 +145,18 @@ def test_tokenize(cols, oracle):
         assert nvtext.token_count(dev, d) == wc.tolist(), d
 
 
+def test_category_many_distinct_keys(oracle):
+    """more distinct keys than the hash-table path holds (512 Ki): the build must switch to the sort path, same result"""
+    from custrings_b200 import nvstrings, nvcategory
+    rng = random.Random(2)
+    strs = ["k%07d" % rng.randrange(0, 900000) for _ in range(1200000)] + [None, "", "k0000001"]
+    cat = nvcategory.from_strings(nvstrings.to_device(strs))
+    ref = oracle.RefCategory(oracle.RefStrings.from_list(strs))
+    assert cat.keys_size() == ref.keys_size() > 600000
+    assert cat.keys().to_host() == [None if k is None else k.decode() for k in ref.keys().to_list()]
+    assert cat.values() == ref.values().tolist()
+
+
 def test_category_merge(oracle):
     from custrings_b200 import nvstrings, nvcategory
     rng = random.Random(9)
