@@ -16,16 +16,17 @@ std::atomic<long long> g_launches{0};
 
 DeviceBuf::DeviceBuf(size_t n) : bytes(n)
 {
-    static bool pool_ready = false;
-    if (!pool_ready) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+    static std::atomic<unsigned long long> pools_ready{0};  // one bit per device ordinal
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(pools_ready.load(std::memory_order_relaxed) & bit)) {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            uint64_t thr = UINT64_MAX;
+            uint64_t thr = UINT64_MAX;  // keep freed memory cached in the pool instead of returning it to the driver
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
-        pool_ready = true;
+        pools_ready.fetch_or(bit, std::memory_order_relaxed);
     }
     cudaError_t e = cudaMallocAsync(&ptr, n, g_stream);
     if (e != cudaSuccess) {

@@ -578,12 +578,9 @@ bool tokenize_flat(const custr_column* col, const uint8_t* delims, int ndelims, 
     a.slot_counts = (unsigned long long*)counts->ptr;
     a.slot_base = (const unsigned long long*)base->ptr;
     const int smem = WARPS * (int)sizeof(WarpSmTok);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUSTR_CUDA(cudaFuncSetAttribute(k_tokenize64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CUSTR_CUDA(cudaFuncSetAttribute(k_tokenize64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    // (per device and cheap: set on every call rather than caching a flag that would be wrong after custr_set_device)
+    CUSTR_CUDA(cudaFuncSetAttribute(k_tokenize64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUSTR_CUDA(cudaFuncSetAttribute(k_tokenize64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int blocks = (a.nitems + WARPS - 1) / WARPS;
     const int resident = num_sms() * 3;
     if (blocks > resident) blocks = resident;
