@@ -823,6 +823,7 @@ void custr_set_regex_tier(int tier)
     g_forced_tier = tier == 1 ? 1 : 0;
     bits::g_force_generic = tier == 2;  // 2: bitstream tier, generic DAG interpreter even for chain-shaped plans
     bits::g_chain32 = tier == 3;        // 3: bitstream tier, 32-bit-stream chain kernel
+    bits::g_no_spec = tier == 4;        // 4: 64-bit chain kernel without the shape specialisations
 }
 
 int custr_regex_describe(const char* pattern, char* buf, size_t buflen)

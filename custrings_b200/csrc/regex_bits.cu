@@ -31,6 +31,7 @@ struct Plan {
     std::string text;
 };
 
+bool g_no_spec = false;        // A/B switch: never use the shape-specialised chain kernels
 bool g_force_generic = false;  // A/B switch: run chain-shaped plans on the generic interpreter kernel
 bool g_chain32 = false;        // A/B switch: 32-bit-stream chain kernel instead of the 64-bit one
 

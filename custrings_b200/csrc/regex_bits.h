@@ -43,6 +43,7 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
 bool tokenize_flat(const custr_column* col, const uint8_t* delims, int ndelims, BufPtr& out_chars, BufPtr& out_off, int64_t& ntok,
                    int64_t& nbytes);
 extern bool g_force_generic;
+extern bool g_no_spec;
 extern bool g_chain32;
 
 // Non-null when the plan is a linear chain whose only loop is its last step: for those patterns the match SPAN the Pike VM

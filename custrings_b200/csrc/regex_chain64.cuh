@@ -10,22 +10,43 @@
 // synchronisation the ring needs.
 #pragma once
 
-// Plan view: how the kernel reads the flags of the chain it executes.  The ahead-of-time kernels read them from the
-// parameter block (one binary interprets every chain); a plan-specialised build defines them as literals so that ptxas
-// folds every flag test, select and constant-bank read away.
-#ifndef PV_SPECIALISED
-#define PV_NEEDS (cd.needs)
-#define PV_ANCHORED (cd.anchored)
-#define PV_END_MASK (cd.end_mask)
-#define PV_BEFORE0 (cd.steps[0].before)
-#define PV_STEP_CLS(s) (cd.steps[s].cls)
+// Plan view: how the kernel reads the flags of the chain it executes.  The generic kernels (SPEC = 0) read them from the
+// parameter block: one binary interprets every chain.  For the most common shapes — a run of ONE builtin class (\w or
+// \d), bare or word-bounded (\b...\b), searched anywhere — ahead-of-time specialisations (SPEC 1..4) see the assertion
+// and class flags as literals, so ptxas folds the flag tests, selects and constant-bank reads away (measured on C2:
+// 0.445 -> 0.42 ms with every flag literal; the assertion flags alone are worth 5 %, the class flags 4 %).
+template <int SPEC>
+struct PlanLit {  // SPEC 0: nothing is literal
+    static constexpr bool on = false;
+    static constexpr uint32_t needs = 0, end_mask = 0, before0 = 0, builtins = 0;
+};
+template <> struct PlanLit<1> { static constexpr bool on = true; static constexpr uint32_t needs = 0, end_mask = 0, before0 = 0, builtins = 1u << AK_WORD; };
+template <> struct PlanLit<2> { static constexpr bool on = true; static constexpr uint32_t needs = 0, end_mask = 0, before0 = 0, builtins = 1u << AK_DIGIT; };
+template <> struct PlanLit<3> { static constexpr bool on = true; static constexpr uint32_t needs = AS_BOW, end_mask = AS_BOW, before0 = AS_BOW, builtins = 1u << AK_WORD; };
+template <> struct PlanLit<4> { static constexpr bool on = true; static constexpr uint32_t needs = AS_BOW, end_mask = AS_BOW, before0 = AS_BOW, builtins = 1u << AK_DIGIT; };
+constexpr int CHAIN_SPECS = 4;
+// which specialisation (0 = none) covers this chain
+inline int chain_spec_of(const ChainDev& cd)
+{
+    if (cd.nclasses != 1 || cd.anchored || cd.classes[0].natoms != 0 || cd.classes[0].negate) return 0;
+    const uint32_t b = cd.classes[0].builtins;
+    const int kind = b == (1u << AK_WORD) ? 1 : (b == (1u << AK_DIGIT) ? 2 : 0);
+    if (!kind) return 0;
+    if (cd.needs == 0 && cd.end_mask == 0 && cd.steps[0].before == 0) return kind;
+    if (cd.needs == AS_BOW && cd.end_mask == AS_BOW && cd.steps[0].before == AS_BOW) return 2 + kind;
+    return 0;
+}
+#define PV_NEEDS (PL::on ? PL::needs : cd.needs)
+#define PV_ANCHORED (PL::on ? 0u : cd.anchored)
+#define PV_END_MASK (PL::on ? PL::end_mask : cd.end_mask)
+#define PV_BEFORE0 (PL::on ? PL::before0 : cd.steps[0].before)
+#define PV_STEP_CLS(s) (PL::on ? 0u : cd.steps[s].cls)
 #define PV_STEP_LOOP(s) (cd.steps[s].loop)
-#define PV_NCLASSES (cd.nclasses)
-#define PV_CLS_BUILTINS(k) (cd.classes[k].builtins)
-#define PV_CLS_NATOMS(k) (cd.classes[k].natoms)
-#define PV_CLS_NEGATE(k) (cd.classes[k].negate)
-#define PV_BUILTIN_UNION (cd.builtin_union)
-#endif
+#define PV_NCLASSES (PL::on ? 1u : cd.nclasses)
+#define PV_CLS_BUILTINS(k) (PL::on ? PL::builtins : cd.classes[k].builtins)
+#define PV_CLS_NATOMS(k) (PL::on ? 0u : cd.classes[k].natoms)
+#define PV_CLS_NEGATE(k) (PL::on ? 0u : cd.classes[k].negate)
+#define PV_BUILTIN_UNION (PL::on ? PL::builtins : cd.builtin_union)
 
 constexpr int WIN64 = 2048;
 constexpr int RING_STAGES = 2;
@@ -197,7 +218,7 @@ __device__ __noinline__ NaClasses<NCLS> classify_non_ascii64(const ChainDev& cd,
                 na &= ~bits;
 #pragma unroll
                 for (int k = 0; k < NCLS; ++k)
-                    if (k < (int)PV_NCLASSES) r.c[k] = ((cd.classes[k].na2[cp >> 5] >> (cp & 31)) & 1u) ? (r.c[k] | bits) : (r.c[k] & ~bits);
+                    if (k < (int)cd.nclasses) r.c[k] = ((cd.classes[k].na2[cp >> 5] >> (cp & 31)) & 1u) ? (r.c[k] | bits) : (r.c[k] & ~bits);
                 r.al = ((cd.na2_alnum[cp >> 5] >> (cp & 31)) & 1u) ? (r.al | bits) : (r.al & ~bits);
                 continue;
             }
@@ -217,13 +238,13 @@ __device__ __noinline__ NaClasses<NCLS> classify_non_ascii64(const ChainDev& cd,
             const uint32_t cp = ((ch >> 2) & 0x7C0u) | (ch & 0x3Fu);
 #pragma unroll
             for (int k = 0; k < NCLS; ++k)
-                if (k < (int)PV_NCLASSES) r.c[k] = ((cd.classes[k].na2[cp >> 5] >> (cp & 31)) & 1u) ? (r.c[k] | bits) : (r.c[k] & ~bits);
+                if (k < (int)cd.nclasses) r.c[k] = ((cd.classes[k].na2[cp >> 5] >> (cp & 31)) & 1u) ? (r.c[k] | bits) : (r.c[k] & ~bits);
             r.al = ((cd.na2_alnum[cp >> 5] >> (cp & 31)) & 1u) ? (r.al | bits) : (r.al & ~bits);
             continue;
         }
 #pragma unroll
         for (int k = 0; k < NCLS; ++k)
-            if (k < (int)PV_NCLASSES) r.c[k] = na_char_matches(cd.classes[k], A, ch) ? (r.c[k] | bits) : (r.c[k] & ~bits);
+            if (k < (int)cd.nclasses) r.c[k] = na_char_matches(cd.classes[k], A, ch) ? (r.c[k] | bits) : (r.c[k] & ~bits);
         r.al = is_alnum_packed(ch, A.uflags) ? (r.al | bits) : (r.al & ~bits);
     }
     return r;
@@ -262,11 +283,12 @@ struct ChainState64 {  // top words of the previous window's streams (only their
 
 // One code path for ASCII and UTF-8 windows (the UTF-8 extras sit behind the warp-uniform `utf8` flag): duplicating the
 // chain for the two cases doubled the hot instruction footprint past the instruction cache.
-template <int NS, int NCLS>
+template <int NS, int NCLS, int SPEC>
 __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[NCLS], u64 al, u64 nl, u64 rs, bool utf8, int rounds, u64 cont,
                                             uint32_t rs_next, uint32_t next_is_cont, uint32_t a_next, uint32_t nl_next,
                                             ChainState64<NS>& st, const LaneCtx& L, const SpanSink& sink)
 {
+    using PL = PlanLit<SPEC>;
     const u64 nrs = ~rs;
     u64 fin = ~0ull;       // last byte of a character
     uint32_t cont0 = 0u;   // window starts inside a character
@@ -347,10 +369,11 @@ __device__ __forceinline__ void ring_issue(uint32_t dst0, const char* __restrict
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-template <int NS, int NCLS>
+template <int NS, int NCLS, int SPEC = 0>
 __global__ void __launch_bounds__(THREADS, 3)
 k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
 {
+    using PL = PlanLit<SPEC>;
     __shared__ WarpSm64 sm[WARPS];
     LaneCtx L;
     L.lane = lane_id();
@@ -394,6 +417,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
         int pend = byte_a - ws;  // window-relative position of a row start already known (-1: none)
         int o_nxt = (kcur + (int)lane <= rb) ? __ldg(A.offsets + kcur + (int)lane) : 0x7fffffff;
         int stage = 0;
+        uint32_t nb_cur = (ws + WIN64 < A.end) ? (uint32_t)(uint8_t)A.chars[ws + WIN64] : 0u;  // byte behind the first window
         __syncwarp();  // the previous item's reads of the ring are done
         ring_issue(my0, gsrc, A.chars, ws, A.end, lane);
 
@@ -433,7 +457,10 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
             __syncwarp();
             const u64 rs = lds64(my_w + SM_RS);
             const uint32_t rs_next = at_we || we >= A.end;
-            const uint32_t next_byte = (!rs_next && we < A.end) ? (uint8_t)A.chars[we] : 0;
+            // the byte behind this window (look-ahead of \b / $): its load was issued one iteration ago — issued here it sat on
+            // the critical path of the window (18 % of the stall samples)
+            const uint32_t next_byte = (!rs_next && we < A.end) ? nb_cur : 0u;
+            nb_cur = (we + WIN64 < A.end) ? (uint32_t)(uint8_t)A.chars[we + WIN64] : 0u;  // for the next window
 
             // ---- this window's bytes: wait for its cp.async group, read back my own 64 bytes, transpose to bit planes
             if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -494,7 +521,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
             }
             const u64 al = nc.al;
             const SpanSink sink{A.span_m, A.span_k, A.span_a, (size_t)((ws + 64 * (int)lane - A.span_base) >> 6), ws + 64 * (int)lane, byte_a, byte_b};
-            const u64 E = chain_eval64<NS, NCLS>(cd, c, al, nl, rs, utf8, rounds, cont, rs_next, (next_byte & 0xC0u) == 0x80u, a_next, nl_next, st, L,
+            const u64 E = chain_eval64<NS, NCLS, SPEC>(cd, c, al, nl, rs, utf8, rounds, cont, rs_next, (next_byte & 0xC0u) == 0x80u, a_next, nl_next, st, L,
                                                  sink);
 
             // ---- sticky per-row OR of the match bits; NUL bytes make a row "dirty" (decided by the exact VM)
@@ -612,6 +639,17 @@ static void launch_chain64_ns(const ChainDev& cd, const Args& a, int blocks)
     auto k1 = k_chain64<NS, 1>;
     auto k2 = k_chain64<NS, 2>;
     auto k4 = k_chain64<NS, 4>;
+    if constexpr (NS <= 4) {  // shape specialisations exist for the short chains (\w+, \d{2,}, \b\w{4,}\b ...)
+        const int spec = g_no_spec ? 0 : chain_spec_of(cd);
+        auto s1 = k_chain64<NS, 1, 1>;
+        auto s2 = k_chain64<NS, 1, 2>;
+        auto s3 = k_chain64<NS, 1, 3>;
+        auto s4 = k_chain64<NS, 1, 4>;
+        if (spec == 1) { LAUNCH(s1, blocks, THREADS, 0, cd, a); return; }
+        if (spec == 2) { LAUNCH(s2, blocks, THREADS, 0, cd, a); return; }
+        if (spec == 3) { LAUNCH(s3, blocks, THREADS, 0, cd, a); return; }
+        if (spec == 4) { LAUNCH(s4, blocks, THREADS, 0, cd, a); return; }
+    }
     if (cd.nclasses <= 1) LAUNCH(k1, blocks, THREADS, 0, cd, a);
     else if (cd.nclasses == 2) LAUNCH(k2, blocks, THREADS, 0, cd, a);
     else LAUNCH(k4, blocks, THREADS, 0, cd, a);
@@ -621,7 +659,7 @@ static void launch_chain64_ns(const ChainDev& cd, const Args& a, int blocks)
 static void launch_chain64(const ChainDev& cd, const Args& a, int blocks)
 {
 #ifdef CUSTR_EXPERIMENT_ONLY_4_1  // quick SASS iteration on the headline instantiation (tools/sass_stat.sh)
-    auto k1 = k_chain64<4, 1>;
+    auto k1 = k_chain64<4, 1, CUSTR_EXPERIMENT_ONLY_4_1>;
     LAUNCH(k1, blocks, THREADS, 0, cd, a);
     return;
 #else

@@ -46,7 +46,7 @@ long long custr_launch_count(void);
 /* name of the regex execution tier used by the last regex call on this thread ("bitstream", "pikevm") */
 const char* custr_last_regex_tier(void);
 /* force a tier for A/B testing: 0 = auto, 1 = exact Pike VM only, 2 = bitstream generic interpreter kernel,
- * 3 = bitstream 32-bit-stream chain kernel */
+ * 3 = bitstream 32-bit-stream chain kernel, 4 = 64-bit chain kernel without the shape specialisations */
 void custr_set_regex_tier(int tier);
 /* when on, regex calls bracket their dominant kernel(s) with CUDA events on the launch stream;
  * custr_last_kernel_ms() returns that device time for the last call on this thread (-1 if none) */

@@ -21,7 +21,7 @@ def _none_to(v, lst):
     return [v if x is None else x for x in lst]
 
 
-@pytest.mark.parametrize("tier", [0, 1, 2, 3])
+@pytest.mark.parametrize("tier", [0, 1, 2, 3, 4])
 def test_contains_match_count_patterns(cols, tier):
     from custrings_b200._lib import lib
     strs, dev, ref = cols
