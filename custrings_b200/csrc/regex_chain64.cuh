@@ -12,8 +12,8 @@
 
 // Plan view: how the kernel reads the flags of the chain it executes.  The generic kernels (SPEC = 0) read them from the
 // parameter block: one binary interprets every chain.  For the most common shapes — a run of ONE builtin class (\w or
-// \d), bare or word-bounded (\b...\b), searched anywhere — ahead-of-time specialisations (SPEC 1..4) see the assertion
-// and class flags as literals, so ptxas folds the flag tests, selects and constant-bank reads away (measured on C2:
+// \d) of a minimum length (x+, x{n,}), bare or word-bounded (\b...\b), searched anywhere — ahead-of-time specialisations
+// (SPEC 1..4) see the assertion, class and loop flags as literals, so ptxas folds the flag tests, selects and constant-bank reads away (measured on C2:
 // 0.445 -> 0.42 ms with every flag literal; the assertion flags alone are worth 5 %, the class flags 4 %).
 template <int SPEC>
 struct PlanLit {  // SPEC 0: nothing is literal
@@ -29,6 +29,8 @@ constexpr int CHAIN_SPECS = 4;
 inline int chain_spec_of(const ChainDev& cd)
 {
     if (cd.nclasses != 1 || cd.anchored || cd.classes[0].natoms != 0 || cd.classes[0].negate) return 0;
+    for (uint32_t s = 0; s < cd.nsteps; ++s)  // the specialisations also fix the loop structure: only the last step loops
+        if ((cd.steps[s].loop != 0) != (s + 1 == cd.nsteps)) return 0;
     const uint32_t b = cd.classes[0].builtins;
     const int kind = b == (1u << AK_WORD) ? 1 : (b == (1u << AK_DIGIT) ? 2 : 0);
     if (!kind) return 0;
@@ -41,7 +43,7 @@ inline int chain_spec_of(const ChainDev& cd)
 #define PV_END_MASK (PL::on ? PL::end_mask : cd.end_mask)
 #define PV_BEFORE0 (PL::on ? PL::before0 : cd.steps[0].before)
 #define PV_STEP_CLS(s) (PL::on ? 0u : cd.steps[s].cls)
-#define PV_STEP_LOOP(s) (cd.steps[s].loop)
+#define PV_STEP_LOOP(s) (PL::on ? (uint32_t)((s) == NS - 1) : cd.steps[s].loop)
 #define PV_NCLASSES (PL::on ? 1u : cd.nclasses)
 #define PV_CLS_BUILTINS(k) (PL::on ? PL::builtins : cd.classes[k].builtins)
 #define PV_CLS_NATOMS(k) (PL::on ? 0u : cd.classes[k].natoms)
@@ -417,7 +419,8 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
         int pend = byte_a - ws;  // window-relative position of a row start already known (-1: none)
         int o_nxt = (kcur + (int)lane <= rb) ? __ldg(A.offsets + kcur + (int)lane) : 0x7fffffff;
         int stage = 0;
-        uint32_t nb_cur = (ws + WIN64 < A.end) ? (uint32_t)(uint8_t)A.chars[ws + WIN64] : 0u;  // byte behind the first window
+        uint32_t nb_cur = 0;
+        if constexpr (SPEC != 0) nb_cur = (ws + WIN64 < A.end) ? (uint32_t)(uint8_t)A.chars[ws + WIN64] : 0u;  // byte behind the first window
         __syncwarp();  // the previous item's reads of the ring are done
         ring_issue(my0, gsrc, A.chars, ws, A.end, lane);
 
@@ -459,8 +462,13 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
             const uint32_t rs_next = at_we || we >= A.end;
             // the byte behind this window (look-ahead of \b / $): its load was issued one iteration ago — issued here it sat on
             // the critical path of the window (18 % of the stall samples)
-            const uint32_t next_byte = (!rs_next && we < A.end) ? nb_cur : 0u;
-            nb_cur = (we + WIN64 < A.end) ? (uint32_t)(uint8_t)A.chars[we + WIN64] : 0u;  // for the next window
+            // (the generic kernels have enough work between the load and its use: there the extra live register costs more)
+            uint32_t next_byte;
+            if constexpr (SPEC != 0) {
+                next_byte = (!rs_next && we < A.end) ? nb_cur : 0u;
+                nb_cur = (we + WIN64 < A.end) ? (uint32_t)(uint8_t)A.chars[we + WIN64] : 0u;  // for the next window
+            } else
+                next_byte = (!rs_next && we < A.end) ? (uint32_t)(uint8_t)A.chars[we] : 0u;
 
             // ---- this window's bytes: wait for its cp.async group, read back my own 64 bytes, transpose to bit planes
             if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
