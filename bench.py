@@ -293,7 +293,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel_ms": k_ms, "algorithmic_bytes": alg, "peak_source": peak_src,
-                         "kernel": "bits::k_chain64<4,1> (+ memset, + k_vm_bool_rows for rows holding NUL)" if tier == "bitstream" else "k_vm_bool<32>"},
+                         "kernel": "bits::k_chain64<4,1,3> (+ memset, + k_vm_bool_rows for rows holding NUL)" if tier == "bitstream" else "k_vm_bool<32>"},
             "clocks": sampler.summary(),
         }
         if world == 1:
