@@ -181,16 +181,22 @@ k_tokenize64(const __grid_constant__ TokArgs A)
             const int ntoks = (int)(total >> 16);
             const bool stage_toks = ntoks <= WIN64 / 4;
             const uint32_t tokbuf = wb + (uint32_t)stage * WIN64;
-            {
+            {   // 32-bit halves: FLO / POPC / shifts on 64-bit values cost 2-4 instructions each
                 int t = (int)(pre >> 16);
-                u64 s = S;
-                while (s) {
-                    const int b = __ffsll((long long)s) - 1;
-                    s &= s - 1;
-                    const int32_t off = (int32_t)(out_a + (pre & 0xffffu) + __popcll(T & ((1ull << b) - 1ull)));
-                    if (stage_toks) asm volatile("st.shared.u32 [%0], %1;" ::"r"(tokbuf + 4u * (uint32_t)t), "r"(off) : "memory");
-                    else A.tok_off[tok_a + t] = off;
-                    ++t;
+                int32_t off0 = (int32_t)(out_a + (pre & 0xffffu));
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t s32 = h ? hi32(S) : lo32(S);
+                    const uint32_t t32 = h ? hi32(T) : lo32(T);
+                    while (s32) {
+                        const int b = __ffs((int)s32) - 1;
+                        s32 &= s32 - 1;
+                        const int32_t off = off0 + __popc(t32 & ((1u << b) - 1u));
+                        if (stage_toks) asm volatile("st.shared.u32 [%0], %1;" ::"r"(tokbuf + 4u * (uint32_t)t), "r"(off) : "memory");
+                        else A.tok_off[tok_a + t] = off;
+                        ++t;
+                    }
+                    off0 += __popc(t32);
                 }
             }
             // bytes of my word -> tile: straight-line, one predicated byte store per input byte (the words are still in
