@@ -103,15 +103,38 @@ __device__ __forceinline__ int walk_spans(const Streams& S, const uint8_t* chars
             cm = m + 1;
             continue;
         }
-        int s = m;
-        for (int j = 0; j < k_chars; ++j) {
-            --s;
-            while (s > a && (chars[s] & 0xC0u) == 0x80u) --s;
+        // start of the match: k characters before m.  Fast path: the k bytes before m are loaded independently (not as a
+        // chain of dependent loads) and none is a continuation byte, i.e. each of them is one character.
+        int s = m - k_chars;
+        bool fast = k_chars <= 4 && s >= a;
+        if (fast) {
+            uint32_t any_cont = 0;
+#pragma unroll
+            for (int j = 1; j <= 4; ++j)
+                if (j <= k_chars) any_cont |= (uint32_t)((chars[m - j] & 0xC0u) == 0x80u);
+            fast = !any_cont;
+        }
+        if (!fast) {
+            s = m;
+            for (int j = 0; j < k_chars; ++j) {
+                --s;
+                while (s > a && (chars[s] & 0xC0u) == 0x80u) --s;
+            }
         }
         emit(s, p + 1);
         ++found;
         cm = p + 1;  // the next match starts at or after the end of this one: its last step begins k characters later
-        for (int j = 0; j < k_chars && cm < b; ++j) cm += utf8_width(chars[cm]);
+        fast = k_chars <= 4 && cm + k_chars <= b;
+        if (fast) {  // the next k bytes are all ASCII: k characters
+            uint32_t hi = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < k_chars) hi |= chars[cm + j];
+            fast = hi < 0x80u;
+        }
+        if (fast) cm += k_chars;
+        else
+            for (int j = 0; j < k_chars && cm < b; ++j) cm += utf8_width(chars[cm]);
     }
     return found;
 }
