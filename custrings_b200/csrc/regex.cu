@@ -481,7 +481,15 @@ k_span_replace_splice(ColView col, int chars_limit, spans::Streams S, const uint
             }
             continue;
         }
-        // (1) stage chars + stream slices, clear the bit maps
+        // (1) stage chars + stream slices, clear the bit maps; the range of this warp's NEXT block is pulled towards L2 now
+        {
+            const int nb = blk + gridDim.x * WARPS;
+            if (nb < nblocks) {
+                const int na = col.offsets[nb * ROWS];
+                const char* pf = col.chars + na + 128 * lane;  // 32 lanes x 128 B = 4 KiB
+                if (na + 128 * lane < chars_limit) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            }
+        }
         stage::copy_in(sm.in[warp], col.chars, a64, in_b, chars_limit, lane);
         const int w0 = (a64 - S.base) >> 6, nwords = ((in_b - 1 - a64) >> 6) + 1;
         for (int w = lane; w < nwords; w += 32) {
