@@ -106,16 +106,21 @@ __global__ void k_pack_bits(const uint8_t* __restrict__ flags, uint8_t* __restri
     bits[b] = (uint8_t)v;
 }
 
+// number of set bits among the n validity bits that start at bit vbit0: one byte per thread and step, one atomic per warp
 __global__ void k_count_valid(const uint8_t* __restrict__ bits, int32_t vbit0, int32_t n, unsigned long long* total)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int v = 0;
-    if (i < n) {
-        int b = vbit0 + i;
-        v = (bits[b >> 3] >> (b & 7)) & 1;
+    const long long first = vbit0, last = (long long)vbit0 + n;  // bit range [first, last)
+    const long long byte0 = first >> 3, byte1 = (last + 7) >> 3;
+    unsigned cnt = 0;
+    for (long long b = byte0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; b < byte1; b += (long long)gridDim.x * blockDim.x) {
+        unsigned v = bits[b];
+        const long long lo = b << 3;
+        if (lo < first) v &= 0xFFu << (first - lo);
+        if (lo + 8 > last) v &= 0xFFu >> (lo + 8 - last);
+        cnt += __popc(v);
     }
-    unsigned m = __ballot_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(total, (unsigned long long)__popc(m));
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(total, (unsigned long long)cnt);
 }
 
 // validity re-aligned to bit 0; rows past n are 0; optionally clears empties
@@ -236,7 +241,7 @@ int32_t count_zero_bits(const uint8_t* bits, int32_t vbit0, int32_t n)
     if (!bits || n == 0) return 0;
     Scratch<unsigned long long> total(1);
     CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
-    LAUNCH(k_count_valid, blocks_for(n, 256), 256, 0, bits, vbit0, n, total.get());
+    LAUNCH(k_count_valid, blocks_for((n + 7) / 8 + 1, 256 * 8), 256, 0, bits, vbit0, n, total.get());
     unsigned long long h = 0;
     CUSTR_CUDA(cudaMemcpyAsync(&h, total.get(), 8, cudaMemcpyDeviceToHost, g_stream));
     CUSTR_CUDA(cudaStreamSynchronize(g_stream));
