@@ -714,6 +714,109 @@ static unsigned long long read_counter(unsigned long long* d)
     return h;
 }
 
+// ---- top-level alternation of chains --------------------------------------------------------------------------------
+// `a|b|c` exists in a row iff one of the alternatives does (existence does not depend on thread priority), so when the
+// whole pattern is not a chain but every top-level alternative is, each alternative runs on the chain kernel (~0.45 ms per
+// GiB) and the boolean results are OR-ed — instead of the DAG interpreter kernel (~3.4 ms per GiB).
+static bool split_top_level(const char* pattern, std::vector<std::string>& parts)
+{
+    parts.clear();
+    std::string cur;
+    int depth = 0;
+    for (const char* p = pattern; *p; ++p) {
+        const char ch = *p;
+        if (ch == '\\') {
+            if (p[1] >= '0' && p[1] <= '9') return false;  // octal escapes swallow the following character: do not reason about them
+            cur.push_back(ch);
+            if (p[1]) cur.push_back(*++p);
+            continue;
+        }
+        if (ch == '[') {  // copy the class verbatim
+            cur.push_back(ch);
+            ++p;
+            if (*p == '^') cur.push_back(*p++);
+            if (*p == ']') cur.push_back(*p++);
+            for (; *p && *p != ']'; ++p) {
+                cur.push_back(*p);
+                if (*p == '\\' && p[1]) cur.push_back(*++p);
+            }
+            if (!*p) return false;
+            cur.push_back(']');
+            continue;
+        }
+        if (ch == '(') ++depth;
+        if (ch == ')') --depth;
+        if (depth < 0) return false;
+        if (ch == '|' && depth == 0) {
+            if (cur.empty()) return false;
+            parts.push_back(cur);
+            cur.clear();
+            continue;
+        }
+        cur.push_back(ch);
+    }
+    if (depth != 0 || cur.empty()) return false;
+    parts.push_back(cur);
+    return parts.size() >= 2 && parts.size() <= 8;
+}
+
+__global__ void k_or_results(const uint8_t* const* __restrict__ parts, int nparts, int n, uint8_t* __restrict__ out, unsigned long long* __restrict__ total)
+{
+    unsigned cnt = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint8_t v = 0;
+        for (int k = 0; k < nparts; ++k) v |= parts[k][i];
+        out[i] = v;
+        cnt += v;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(total, (unsigned long long)cnt);
+}
+
+static const std::shared_ptr<bits::Plan>& plan_of(Compiled& c, bool anchored)
+{
+    if (!c.plans_built) {
+        c.plan_contains = bits::lower(c.prog, false, host_unicode_flags());
+        c.plan_match = bits::lower(c.prog, true, host_unicode_flags());
+        c.plans_built = true;
+    }
+    return anchored ? c.plan_match : c.plan_contains;
+}
+
+// true: out_dev / total hold the answer for every row without a NUL byte; the rows with one are in dirty_rows (VM, full pattern)
+static bool alternation_of_chains(const custr_column* col, const char* pattern, bool anchored, uint8_t* out_dev, unsigned long long* total,
+                                  int32_t** dirty_rows, unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count)
+{
+    std::vector<std::string> alts;
+    if (bits::g_force_generic || bits::g_chain32 || !split_top_level(pattern, alts)) return false;
+    std::vector<CompiledPtr> progs;
+    for (const std::string& a : alts) {
+        progs.push_back(get_compiled(a.c_str()));
+        const std::shared_ptr<bits::Plan>& pl = plan_of(*progs.back(), anchored);
+        if (!pl || !bits::plan_is_chain(*pl) || !cap_tier((int)progs.back()->prog.insts.size())) return false;
+    }
+    const int32_t n = col->n;
+    std::vector<BufPtr> outs;
+    std::vector<const uint8_t*> ptrs;
+    Scratch<unsigned long long> unused(1);
+    CUSTR_CUDA(cudaMemsetAsync(unused.get(), 0, 8, g_stream));
+    for (size_t k = 0; k < progs.size(); ++k) {
+        outs.push_back(dev_alloc((size_t)n));
+        ptrs.push_back((const uint8_t*)outs.back()->ptr);
+        int32_t* dr = nullptr;
+        unsigned int* dc = nullptr;
+        BufPtr kr, kc;
+        if (!bits::run(*plan_of(*progs[k], anchored), col, (const uint8_t*)progs[k]->dev_image->ptr, device_unicode_flags(), (uint8_t*)outs.back()->ptr,
+                       unused.get(), &dr, &dc, kr, kc))
+            return false;
+        if (k == 0) { *dirty_rows = dr; *dirty_count = dc; keep_rows = kr; keep_count = kc; }  // the NUL rows are the same for every alternative
+    }
+    BufPtr d_ptrs = upload(ptrs.data(), sizeof(void*) * ptrs.size());
+    LAUNCH(k_or_results, num_sms() * 8, 256, 0, (const uint8_t* const*)d_ptrs->ptr, (int)ptrs.size(), n, out_dev, total);
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));  // the per-alternative buffers die with this scope
+    return true;
+}
+
 static int bool_search(const custr_column* col, const char* pattern, uint8_t* results, int devmem, bool anchored, const char* who)
 {
     if (!col || !pattern || !results) return fail(CUSTR_ERR_ARG, std::string(who) + ": null argument");
@@ -731,6 +834,26 @@ static int bool_search(const custr_column* col, const char* pattern, uint8_t* re
             c->plans_built = true;
         }
         const std::shared_ptr<bits::Plan>& plan = anchored ? c->plan_match : c->plan_contains;
+        int cap0 = cap_tier((int)c->prog.insts.size());
+        if (cap0 && (!plan || !bits::plan_is_chain(*plan))) {  // not a chain: maybe a top-level alternation of chains
+            int32_t* dirty_rows = nullptr;
+            unsigned int* dirty_count = nullptr;
+            BufPtr keep_rows, keep_count;
+            g_timer.start();
+            if (alternation_of_chains(col, pattern, anchored, out.dev, total.get(), &dirty_rows, &dirty_count, keep_rows, keep_count)) {
+                int grid = vm_grid(n < 1 << 20 ? n : 1 << 20);
+                DISPATCH_CAP(cap0, k_vm_bool_rows, grid, smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr, (int)c->image.size(),
+                             device_unicode_flags(), anchored ? 1 : 0, (const int32_t*)dirty_rows, (const unsigned int*)dirty_count, out.dev,
+                             total.get());
+                g_timer.stop();
+                g_last_tier = "bitstream";
+                int matches = (int)read_counter(total.get());
+                g_timer.collect();
+                out.finish();
+                return matches;
+            }
+            g_timer.armed = false;
+        }
         if (plan) {
             int cap = cap_tier((int)c->prog.insts.size());
             int32_t* dirty_rows = nullptr;

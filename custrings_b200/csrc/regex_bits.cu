@@ -447,6 +447,8 @@ __global__ void k_item_bounds(const int32_t* __restrict__ offsets, int n, int fi
 
 const PlanDev& device_plan(const Plan& plan);
 
+bool plan_is_chain(const Plan& plan) { return plan.is_chain; }
+
 // count_re inside the chain kernel (see k_chain64's count mode): the last step loops and every step uses its class
 bool count_in_kernel_ok(const Plan& plan)
 {

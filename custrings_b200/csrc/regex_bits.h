@@ -35,6 +35,7 @@ struct SpanStreams {
     int32_t* counts_out = nullptr;
 };
 bool count_in_kernel_ok(const Plan& plan);
+bool plan_is_chain(const Plan& plan);  // linear chain (k_chain64) rather than a DAG (k_bitstream interpreter)
 bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, const uint8_t* uflags, uint8_t* out,
          unsigned long long* total, int32_t** dirty_rows, unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count,
          SpanStreams* spans = nullptr);

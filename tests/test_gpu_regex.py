@@ -15,6 +15,10 @@ SPAN_PATTERNS = [r"\b\w{4,}\b", r"\d+", r"[a-z]+", r"ab", r"a\d+", r"é+", r"\w+
                  r"\b\d+\b", r"\b\d{2,}\b", r"\b\d{3,}\b", r"\b\d{4,}\b"]
 
 
+# top-level alternations of chains: OR of chain-kernel runs instead of the DAG interpreter
+ALTERNATIONS = [r"\bthe\b|\bfox\b", r"(\bin\b)|(\ba\b)|(\bthe\b)", r"\d+|é", r"^a|b$", r"ab|cd|ef|gh", r"\w+@|\s\d", r"[a-c]x|[|]y|\|z", r"日|😀|é+"]
+
+
 @pytest.fixture(scope="module")
 def cols(oracle):
     from custrings_b200 import nvstrings
@@ -33,7 +37,7 @@ def test_contains_match_count_patterns(cols, tier):
     strs, dev, ref = cols
     lib().custr_set_regex_tier(tier)
     try:
-        pats = [p for p in corpus.PATTERNS if p not in (r"(a|b)*c", r"((a|b)c)*d", "a+*")] + corpus.random_patterns(11, 150) + SPAN_PATTERNS[-14:]
+        pats = [p for p in corpus.PATTERNS if p not in (r"(a|b)*c", r"((a|b)c)*d", "a+*")] + corpus.random_patterns(11, 150) + SPAN_PATTERNS[-14:] + ALTERNATIONS
         for p in pats:
             rc, rn = ref.contains_re(p)
             assert _none_to(False, dev.contains(p)) == rc.tolist(), p
