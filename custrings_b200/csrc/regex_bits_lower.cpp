@@ -21,6 +21,7 @@ struct Plan {
     PlanDev dev;
     bool is_chain = false;
     bool span_ok = false;  // chain whose only loop is a GREEDY loop on the last step (see span_chain)
+    bool chain_has_opt = false;  // some step is optional: only the 64-bit chain kernel understands that
     ChainDev chain;
     std::string text;
 };
@@ -278,14 +279,51 @@ std::shared_ptr<Plan> lower(const rx::Program& prog, bool anchored, const uint8_
         }
     }
     if (P.nends == 0) return nullptr;
-    // ---- linear chain?  (step s fed only by s-1, END only from the last step, unguarded self loops)
+    // ---- linear chain?  Step s is fed by s-1 and, when s-1 is OPTIONAL (x?, x*), by whatever feeds s-1 as well (so the
+    // predecessor set of every step is a contiguous run s-1, s-2, ... possibly ending in START); END hangs off the last
+    // step and possibly off earlier ones (early exits: x{1,3}, trailing x?).  Unguarded self loops; assertions only on
+    // the edges out of START (one common mask) and into END (one common mask).
     {
-        bool chain = P.nsteps <= CHAIN_MAX_STEPS && P.nclasses <= CHAIN_MAX_CLASSES && P.nends == 1 && P.ends[0].src == P.nsteps - 1;
-        for (int s2 = 0; chain && s2 < P.nsteps; ++s2) {
+        bool chain = P.nsteps <= CHAIN_MAX_STEPS && P.nclasses <= CHAIN_MAX_CLASSES;
+        bool opt[MAX_STEPS] = {false};
+        const int N = P.nsteps;
+        auto has_pred = [&](const StepD& st, int src) {
+            for (int q = 0; q < st.npreds; ++q)
+                if (st.preds[q].src == (uint8_t)src) return true;
+            return false;
+        };
+        auto has_end = [&](int src) {
+            for (int q = 0; q < P.nends; ++q)
+                if (P.ends[q].src == src) return true;
+            return false;
+        };
+        // opt[j]: step j+1 is also fed by what feeds step j (step j can be skipped)
+        for (int j = 0; chain && j + 1 < N; ++j) opt[j] = has_pred(P.steps[j + 1], j == 0 ? (int)SRC_START : j - 1);
+        uint8_t start_mask = 0;
+        bool start_mask_set = false;
+        for (int s2 = 0; chain && s2 < N; ++s2) {
             const StepD& st = P.steps[s2];
-            chain = st.npreds == 1 && st.preds[0].src == (s2 == 0 ? SRC_START : s2 - 1) && (!st.self_loop || st.self_mask == 0) &&
-                    (s2 == 0 || st.preds[0].mask == 0);  // assertions only in front of the chain and before END
+            chain = !st.self_loop || st.self_mask == 0;
+            // expected predecessors: s2-1, then further back while the steps in between are optional
+            int expect = 0;
+            for (int j = s2 - 1;; --j) {
+                const int src = j < 0 ? (int)SRC_START : j;
+                ++expect;
+                chain = chain && has_pred(st, src);
+                if (j < 0 || !opt[j]) break;
+            }
+            chain = chain && st.npreds == expect;
+            for (int q = 0; chain && q < st.npreds; ++q) {
+                if (st.preds[q].src == SRC_START) {
+                    if (!start_mask_set) { start_mask = st.preds[q].mask; start_mask_set = true; }
+                    chain = st.preds[q].mask == start_mask;
+                } else
+                    chain = st.preds[q].mask == 0;
+            }
         }
+        // END: any steps may have an edge into it (early exits: x{1,3}, trailing x?), the last one must; one common mask
+        chain = chain && has_end(N - 1);
+        for (int q = 1; chain && q < P.nends; ++q) chain = P.ends[q].mask == P.ends[0].mask;
         if (chain) {
             ChainDev& C = plan->chain;
             memset(&C, 0, sizeof(C));
@@ -294,8 +332,13 @@ std::shared_ptr<Plan> lower(const rx::Program& prog, bool anchored, const uint8_
             C.anchored = P.anchored;
             C.end_mask = P.ends[0].mask;
             C.needs = P.before_needs | P.after_needs;
-            for (int s2 = 0; s2 < P.nsteps; ++s2)
-                C.steps[s2] = ChainStepD{P.steps[s2].cls, P.steps[s2].preds[0].mask, P.steps[s2].self_loop};
+            bool any_opt = false;
+            for (int s2 = 0; s2 < P.nsteps; ++s2) {
+                C.steps[s2] = ChainStepD{P.steps[s2].cls, s2 == 0 ? (uint32_t)start_mask : 0u, P.steps[s2].self_loop, opt[s2] ? 1u : 0u,
+                                         has_end(s2) ? 1u : 0u};
+                any_opt = any_opt || opt[s2] || (has_end(s2) && s2 + 1 < P.nsteps);
+            }
+            plan->chain_has_opt = any_opt;
             for (int k = 0; k < P.nclasses; ++k) {
                 ChainClassD& cc = C.classes[k];
                 const ClassD& src = P.classes[k];
@@ -338,7 +381,7 @@ std::shared_ptr<Plan> lower(const rx::Program& prog, bool anchored, const uint8_
             plan->is_chain = true;
             // span fast path: no loop before the last step, and the last step's loop (if any) must be greedy, i.e. the
             // SPLIT that follows the instruction tries the loop body first (regcomp PLUS, not PLUS_LAZY)
-            bool span_ok = true;
+            bool span_ok = !any_opt;
             for (int s2 = 0; s2 + 1 < P.nsteps; ++s2) span_ok = span_ok && !P.steps[s2].self_loop;
             if (span_ok && P.steps[P.nsteps - 1].self_loop) {
                 const int last = order[P.nsteps - 1];

@@ -49,7 +49,7 @@ struct PlanDev {
 // off the last step.  Covers literals, class sequences, x+, x*, x{n,m}-free tails, leading/trailing assertions.
 constexpr int CHAIN_MAX_STEPS = 8;
 constexpr int CHAIN_MAX_CLASSES = 4;
-struct ChainStepD { uint32_t cls, before, loop; };
+struct ChainStepD { uint32_t cls, before, loop, opt, exit; };  // opt: the step may be skipped (x?, x*); exit: edge into END
 struct ChainClassD {
     uint32_t builtins;   // OR of (1 << AtomKind) for the builtin atoms (AK_WORD .. AK_ANY)
     uint32_t natoms;     // remaining EQ / RANGE atoms

@@ -16,21 +16,25 @@
 // (SPEC 1..4) see the assertion, class and loop flags as literals, so ptxas folds the flag tests, selects and constant-bank reads away (measured on C2:
 // 0.445 -> 0.42 ms with every flag literal; the assertion flags alone are worth 5 %, the class flags 4 %).
 template <int SPEC>
-struct PlanLit {  // SPEC 0: nothing is literal
-    static constexpr bool on = false;
+struct PlanLit {  // SPEC 0: no flag is literal, except that the chain has no optional step and no early exit
+    static constexpr bool on = false, opt = false;
     static constexpr uint32_t needs = 0, end_mask = 0, before0 = 0, builtins = 0;
 };
-template <> struct PlanLit<1> { static constexpr bool on = true; static constexpr uint32_t needs = 0, end_mask = 0, before0 = 0, builtins = 1u << AK_WORD; };
-template <> struct PlanLit<2> { static constexpr bool on = true; static constexpr uint32_t needs = 0, end_mask = 0, before0 = 0, builtins = 1u << AK_DIGIT; };
-template <> struct PlanLit<3> { static constexpr bool on = true; static constexpr uint32_t needs = AS_BOW, end_mask = AS_BOW, before0 = AS_BOW, builtins = 1u << AK_WORD; };
-template <> struct PlanLit<4> { static constexpr bool on = true; static constexpr uint32_t needs = AS_BOW, end_mask = AS_BOW, before0 = AS_BOW, builtins = 1u << AK_DIGIT; };
+template <> struct PlanLit<5> {  // SPEC 5: like 0, for chains WITH optional steps / early exits (x?, x*, x{n,m})
+    static constexpr bool on = false, opt = true;
+    static constexpr uint32_t needs = 0, end_mask = 0, before0 = 0, builtins = 0;
+};
+template <> struct PlanLit<1> { static constexpr bool on = true, opt = false; static constexpr uint32_t needs = 0, end_mask = 0, before0 = 0, builtins = 1u << AK_WORD; };
+template <> struct PlanLit<2> { static constexpr bool on = true, opt = false; static constexpr uint32_t needs = 0, end_mask = 0, before0 = 0, builtins = 1u << AK_DIGIT; };
+template <> struct PlanLit<3> { static constexpr bool on = true, opt = false; static constexpr uint32_t needs = AS_BOW, end_mask = AS_BOW, before0 = AS_BOW, builtins = 1u << AK_WORD; };
+template <> struct PlanLit<4> { static constexpr bool on = true, opt = false; static constexpr uint32_t needs = AS_BOW, end_mask = AS_BOW, before0 = AS_BOW, builtins = 1u << AK_DIGIT; };
 constexpr int CHAIN_SPECS = 4;
 // which specialisation (0 = none) covers this chain
 inline int chain_spec_of(const ChainDev& cd)
 {
     if (cd.nclasses != 1 || cd.anchored || cd.classes[0].natoms != 0 || cd.classes[0].negate) return 0;
-    for (uint32_t s = 0; s < cd.nsteps; ++s)  // the specialisations also fix the loop structure: only the last step loops
-        if ((cd.steps[s].loop != 0) != (s + 1 == cd.nsteps)) return 0;
+    for (uint32_t s = 0; s < cd.nsteps; ++s)  // the specialisations also fix the structure: no optional step, only the last one loops
+        if (cd.steps[s].opt || (cd.steps[s].exit != 0) != (s + 1 == cd.nsteps) || (cd.steps[s].loop != 0) != (s + 1 == cd.nsteps)) return 0;
     const uint32_t b = cd.classes[0].builtins;
     const int kind = b == (1u << AK_WORD) ? 1 : (b == (1u << AK_DIGIT) ? 2 : 0);
     if (!kind) return 0;
@@ -44,6 +48,8 @@ inline int chain_spec_of(const ChainDev& cd)
 #define PV_BEFORE0 (PL::on ? PL::before0 : cd.steps[0].before)
 #define PV_STEP_CLS(s) (PL::on ? 0u : cd.steps[s].cls)
 #define PV_STEP_LOOP(s) (PL::on ? (uint32_t)((s) == NS - 1) : cd.steps[s].loop)
+#define PV_STEP_OPT(s) (PL::opt ? cd.steps[s].opt : 0u)
+#define PV_STEP_EXIT(s) (PL::opt ? cd.steps[s].exit : (uint32_t)((s) == NS - 1))
 #define PV_NCLASSES (PL::on ? 1u : cd.nclasses)
 #define PV_CLS_BUILTINS(k) (PL::on ? PL::builtins : cd.classes[k].builtins)
 #define PV_CLS_NATOMS(k) (PL::on ? 0u : cd.classes[k].natoms)
@@ -313,7 +319,9 @@ __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[N
         as.eold_a = as.lb | shift_down64(nl & nrs, nl_next, L);
         st.last_nl = hi32(nl);
     }
-    u64 P = 0;
+    // Optional steps (x?, x*): the positions ready for step s (`ready`) are also ready for step s+1.  Early exits (x{1,3},
+    // trailing x?): a match may end behind every step that has an edge into END (`done`, "last consumed byte" domain).
+    u64 P = 0, ready = 0, done = 0;
     uint32_t old_prev = 0;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -326,7 +334,9 @@ __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[N
             // the marker of step s-1 moves to the next position; the carry (previous window's stream) is dropped when
             // this window starts inside a character: that marker was not on a final byte
             t = adv64(P, cont0 ? 0u : old_prev, L) & nrs;
+            if (PV_STEP_OPT(s - 1)) t |= ready;
         }
+        ready = t;
         const u64 ck = sel_class64<NCLS>(c, PV_STEP_CLS(s));
         t &= ck & ~cont;
         const uint32_t old = st.last[s];
@@ -340,12 +350,13 @@ __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[N
         st.last[s] = hi32(Z);
         old_prev = old;
         P = Z & fin;
+        if (PV_STEP_EXIT(s)) done |= P;
         if (s == NS - 1 && __builtin_expect(sink.m != nullptr, 0))  // span streams of the last step (span_walk.cuh); out of line: cold for contains_re / match
             store_spans(sink, t,                                                           // M: first character of the last step, lead byte
                         PV_STEP_LOOP(s) ? (ck & nrs) : (ck & cont),                       // K: the match may continue INTO this byte
                         PV_END_MASK ? apply_after64_generic(fin, PV_END_MASK, as) : fin);  // A: a match may end after this byte
     }
-    return PV_END_MASK ? apply_after64(P, PV_END_MASK, as) : P;
+    return PV_END_MASK ? apply_after64(done, PV_END_MASK, as) : done;
 }
 
 // copy of window [ws, ws + 2048) into a ring stage; `dst0` = shared address of this lane's chunk 0 in that stage,
@@ -647,6 +658,17 @@ static void launch_chain64_ns(const ChainDev& cd, const Args& a, int blocks)
     auto k1 = k_chain64<NS, 1>;
     auto k2 = k_chain64<NS, 2>;
     auto k4 = k_chain64<NS, 4>;
+    bool plain = true;  // no optional step, END only behind the last step
+    for (uint32_t s = 0; s < cd.nsteps; ++s) plain = plain && !cd.steps[s].opt && ((cd.steps[s].exit != 0) == (s + 1 == cd.nsteps));
+    if (!plain) {
+        auto o1 = k_chain64<NS, 1, 5>;
+        auto o2 = k_chain64<NS, 2, 5>;
+        auto o4 = k_chain64<NS, 4, 5>;
+        if (cd.nclasses <= 1) LAUNCH(o1, blocks, THREADS, 0, cd, a);
+        else if (cd.nclasses == 2) LAUNCH(o2, blocks, THREADS, 0, cd, a);
+        else LAUNCH(o4, blocks, THREADS, 0, cd, a);
+        return;
+    }
     if constexpr (NS <= 4) {  // shape specialisations exist for the short chains (\w+, \d{2,}, \b\w{4,}\b ...)
         const int spec = g_no_spec ? 0 : chain_spec_of(cd);
         auto s1 = k_chain64<NS, 1, 1>;
