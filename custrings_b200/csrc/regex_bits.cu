@@ -515,7 +515,7 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     if (blocks > cap) blocks = cap;
     if (plan.is_chain && !g_force_generic) {
 #ifndef CUSTR_EXPERIMENT_ONLY_4_1
-        if (g_chain32 && !plan.chain_has_opt) launch_chain(plan.chain, a, blocks);   // 1024-byte windows, 32-bit streams (A/B)
+        if (g_chain32 && !plan.chain_has_opt && plan.chain.nclasses <= 4) launch_chain(plan.chain, a, blocks);   // 1024-byte windows, 32-bit streams (A/B)
         else
 #endif
         {  // 2048-byte windows, 64-bit streams, cp.async ring; grid = resident set (3 CTAs per SM), dynamic items

@@ -48,7 +48,7 @@ struct PlanDev {
 // Linear-chain specialisation (regex_bits.cu k_chain): step s is fed only by step s-1 (step 0 by START), END hangs
 // off the last step.  Covers literals, class sequences, x+, x*, x{n,m}-free tails, leading/trailing assertions.
 constexpr int CHAIN_MAX_STEPS = 8;
-constexpr int CHAIN_MAX_CLASSES = 4;
+constexpr int CHAIN_MAX_CLASSES = 8;
 struct ChainStepD { uint32_t cls, before, loop, opt, exit; };  // opt: the step may be skipped (x?, x*); exit: edge into END
 struct ChainClassD {
     uint32_t builtins;   // OR of (1 << AtomKind) for the builtin atoms (AK_WORD .. AK_ANY)

@@ -664,9 +664,11 @@ static void launch_chain64_ns(const ChainDev& cd, const Args& a, int blocks)
         auto o1 = k_chain64<NS, 1, 5>;
         auto o2 = k_chain64<NS, 2, 5>;
         auto o4 = k_chain64<NS, 4, 5>;
+        auto o8 = k_chain64<NS, 8, 5>;
         if (cd.nclasses <= 1) LAUNCH(o1, blocks, THREADS, 0, cd, a);
         else if (cd.nclasses == 2) LAUNCH(o2, blocks, THREADS, 0, cd, a);
-        else LAUNCH(o4, blocks, THREADS, 0, cd, a);
+        else if (cd.nclasses <= 4) LAUNCH(o4, blocks, THREADS, 0, cd, a);
+        else LAUNCH(o8, blocks, THREADS, 0, cd, a);
         return;
     }
     if constexpr (NS <= 4) {  // shape specialisations exist for the short chains (\w+, \d{2,}, \b\w{4,}\b ...)
@@ -680,9 +682,11 @@ static void launch_chain64_ns(const ChainDev& cd, const Args& a, int blocks)
         if (spec == 3) { LAUNCH(s3, blocks, THREADS, 0, cd, a); return; }
         if (spec == 4) { LAUNCH(s4, blocks, THREADS, 0, cd, a); return; }
     }
+    auto k8 = k_chain64<NS, 8>;
     if (cd.nclasses <= 1) LAUNCH(k1, blocks, THREADS, 0, cd, a);
     else if (cd.nclasses == 2) LAUNCH(k2, blocks, THREADS, 0, cd, a);
-    else LAUNCH(k4, blocks, THREADS, 0, cd, a);
+    else if (cd.nclasses <= 4) LAUNCH(k4, blocks, THREADS, 0, cd, a);
+    else LAUNCH(k8, blocks, THREADS, 0, cd, a);
 }
 #endif
 

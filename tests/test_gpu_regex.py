@@ -16,6 +16,9 @@ SPAN_PATTERNS = [r"\b\w{4,}\b", r"\d+", r"[a-z]+", r"ab", r"a\d+", r"é+", r"\w+
 
 
 # top-level alternations of chains: OR of chain-kernel runs instead of the DAG interpreter
+# chains with optional steps / early exits and with 5..8 classes
+WIDE_CHAINS = [r"colou?r", r"https?://", r"warning", r"abcdefgh", r"qu?ick\s+brown", r"\d{1,3}", r"\d{2,4}:\d\d?", r"ab*c", r"a?b?c", r"x\d{2,4}\b",
+               r"\bjump(s|ed)?", r"la+zy dog", r"[Tt]he quick"]
 ALTERNATIONS = [r"\bthe\b|\bfox\b", r"(\bin\b)|(\ba\b)|(\bthe\b)", r"\d+|é", r"^a|b$", r"ab|cd|ef|gh", r"\w+@|\s\d", r"[a-c]x|[|]y|\|z", r"日|😀|é+"]
 
 
@@ -37,7 +40,7 @@ def test_contains_match_count_patterns(cols, tier):
     strs, dev, ref = cols
     lib().custr_set_regex_tier(tier)
     try:
-        pats = [p for p in corpus.PATTERNS if p not in (r"(a|b)*c", r"((a|b)c)*d", "a+*")] + corpus.random_patterns(11, 150) + SPAN_PATTERNS[-14:] + ALTERNATIONS
+        pats = [p for p in corpus.PATTERNS if p not in (r"(a|b)*c", r"((a|b)c)*d", "a+*")] + corpus.random_patterns(11, 150) + SPAN_PATTERNS[-14:] + ALTERNATIONS + WIDE_CHAINS
         for p in pats:
             rc, rn = ref.contains_re(p)
             assert _none_to(False, dev.contains(p)) == rc.tolist(), p
