@@ -122,6 +122,25 @@ static unsigned long long fetch(unsigned long long* d)
     return h;
 }
 
+// regex.cu: literal `contains` through the bit-stream chain kernel (rows holding a NUL byte are left to the caller)
+bool literal_contains_chain(const custr_column* col, const char* literal, uint8_t* out_dev, unsigned long long* total, int32_t** dirty_rows,
+                            unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count);
+
+// byte-compare `contains` for the listed rows only
+__global__ void __launch_bounds__(FIND_THREADS)
+k_contains_rows(ColView col, const uint8_t* __restrict__ needle, int m, const int32_t* __restrict__ rows, const unsigned int* __restrict__ nrows_ptr,
+                uint8_t* __restrict__ out, unsigned long long* __restrict__ total)
+{
+    const int nrows = (int)*nrows_ptr;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nrows; k += gridDim.x * blockDim.x) {
+        const int i = rows[k];
+        const uint8_t* s = (const uint8_t*)col.chars + col.offsets[i];
+        const bool r = m > 0 && row::find_bytes(s, 0, col.offsets[i + 1] - col.offsets[i], needle, m) >= 0;
+        out[i] = r;
+        if (r) atomicAdd(total, 1ull);
+    }
+}
+
 static int find_family(const custr_column* col, const char* str, int start, int end, int mode, int32_t* out_i, uint8_t* out_b,
                        int devmem, int null_rc)
 {
@@ -142,6 +161,18 @@ static int find_family(const custr_column* col, const char* str, int start, int 
         out.finish();
     } else {
         ResultBuf<uint8_t> out(out_b, n, devmem);
+        if (mode == FM_CONTAINS && m > 0 && col->nbytes >= (1 << 20)) {  // large column: the chain kernel reads every byte once, coalesced
+            int32_t* dirty_rows = nullptr;
+            unsigned int* dirty_count = nullptr;
+            BufPtr keep_rows, keep_count;
+            if (literal_contains_chain(col, str, out.dev, total.get(), &dirty_rows, &dirty_count, keep_rows, keep_count)) {
+                LAUNCH(k_contains_rows, 64, FIND_THREADS, 0, view_of(col), (const uint8_t*)d_needle->ptr, m, (const int32_t*)dirty_rows,
+                       (const unsigned int*)dirty_count, out.dev, total.get());
+                cnt = fetch(total.get());
+                out.finish();
+                return (int)cnt;
+            }
+        }
         LAUNCH(k_find, row_grid(n, FIND_THREADS), FIND_THREADS, 0, view_of(col), (const uint8_t*)d_needle->ptr, m, start, end, mode,
                (int32_t*)nullptr, out.dev, total.get());
         cnt = fetch(total.get());

@@ -817,6 +817,26 @@ static bool alternation_of_chains(const custr_column* col, const char* pattern, 
     return true;
 }
 
+// Literal `contains` through the chain kernel (find.cu): the literal is escaped into a pattern; when it lowers to a chain the
+// boolean result of every row WITHOUT a NUL byte is left in out_dev (*total += hits) and the rows holding one come back in
+// dirty_rows for the caller's own byte-compare kernel (a literal search has plain byte semantics there, unlike the regex VM).
+bool literal_contains_chain(const custr_column* col, const char* literal, uint8_t* out_dev, unsigned long long* total, int32_t** dirty_rows,
+                            unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count)
+{
+    if (g_forced_tier == 1 || bits::g_force_generic || bits::g_chain32) return false;
+    std::string pat;
+    for (const char* p = literal; *p; ++p) {
+        if (strchr("\\.[](){}*+?|^$", *p)) pat.push_back('\\');
+        pat.push_back(*p);
+    }
+    if (pat.empty()) return false;
+    CompiledPtr c = get_compiled(pat.c_str());
+    const std::shared_ptr<bits::Plan>& plan = plan_of(*c, false);
+    if (!plan || !bits::plan_is_chain(*plan) || !cap_tier((int)c->prog.insts.size())) return false;
+    return bits::run(*plan, col, (const uint8_t*)c->dev_image->ptr, device_unicode_flags(), out_dev, total, dirty_rows, dirty_count, keep_rows,
+                     keep_count);
+}
+
 static int bool_search(const custr_column* col, const char* pattern, uint8_t* results, int devmem, bool anchored, const char* who)
 {
     if (!col || !pattern || !results) return fail(CUSTR_ERR_ARG, std::string(who) + ": null argument");

@@ -100,6 +100,29 @@ def test_rsplit_columns_and_records(cols, oracle):
         assert tokens.size() == want_total
 
 
+def test_contains_literal_large_column(oracle):
+    """literal contains on a column large enough (>= 1 MiB) to take the bit-stream chain kernel: regex metacharacters in the
+    literal, multi-byte characters, rows holding NUL bytes (decided by the byte-compare kernel), nulls"""
+    from custrings_b200 import nvstrings
+    rng = random.Random(23)
+    words = ["a.b", "(x)", "c++", "\\d", "é", "日本", "abc", "a b", "x\x00y", "[z]", "q?", "w|v", "^s$", "plain", "{1}"]
+    strs = []
+    for i in range(40000):
+        r = rng.random()
+        if r < 0.02:
+            strs.append(None)
+        elif r < 0.04:
+            strs.append("")
+        else:
+            strs.append(" ".join(rng.choice(words) for _ in range(rng.randrange(1, 12))))
+    dev, ref = nvstrings.to_device(strs), oracle.RefStrings.from_list(strs)
+    assert dev.byte_count() if hasattr(dev, "byte_count") else True
+    for lit in ["a.b", "(x)", "c++", "\\d", "é", "日本", "abc a", "b a", "[z]", "q?", "w|v", "^s$", "{1}", "zzz", "y a", "本 "]:
+        want = ref.contains(lit)[0].tolist()
+        got = [False if v is None else v for v in dev.contains(lit, regex=False)]
+        assert got == want, lit
+
+
 def test_find_from_and_match_strings(cols, oracle):
     from custrings_b200 import nvstrings
     strs, dev, ref = cols
