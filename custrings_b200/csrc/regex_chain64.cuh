@@ -359,6 +359,22 @@ __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[N
     return PV_END_MASK ? apply_after64(done, PV_END_MASK, as) : done;
 }
 
+// the window that holds the end of the buffer (once per column): chunks that exist completely are copied with cp.async, the
+// others are zero-filled and patched with the bytes that exist (plain stores by the lane that will read them back)
+__device__ __noinline__ void ring_issue_tail(uint32_t dst0, const char* __restrict__ chars, int ws, int end, uint32_t lane)
+{
+    for (int k = 0; k < 4; ++k) {
+        const int pos = ws + 64 * (int)lane + 16 * k;
+        const uint32_t dst = dst0 ^ (16u * k);
+        if (pos + 16 <= end) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(chars + pos) : "memory");
+            continue;
+        }
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+        for (int q = pos; q < end; ++q) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst + (uint32_t)(q - pos)), "r"((uint32_t)(uint8_t)chars[q]) : "memory");
+    }
+}
+
 // copy of window [ws, ws + 2048) into a ring stage; `dst0` = shared address of this lane's chunk 0 in that stage,
 // `gsrc` = chars + 64 * lane
 __device__ __forceinline__ void ring_issue(uint32_t dst0, const char* __restrict__ gsrc, const char* __restrict__ chars, int ws, int end, uint32_t lane)
@@ -371,14 +387,7 @@ __device__ __forceinline__ void ring_issue(uint32_t dst0, const char* __restrict
         asm volatile("cp.async.commit_group;" ::: "memory");
         return;
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int pos = ws + 64 * (int)lane + 16 * k;
-        int bytes = end - pos;
-        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-        const char* src = chars + (bytes > 0 ? pos : 0);  // never form an out-of-range address; size 0 = pure zero fill
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 ^ (16u * k)), "l"(src), "r"(bytes) : "memory");
-    }
+    ring_issue_tail(dst0, chars, ws, end, lane);
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
