@@ -178,6 +178,7 @@ k_tokenize64(const __grid_constant__ TokArgs A)
             const uint32_t phase = (uint32_t)(out_a & 15);
             // tokens of my word.  Their offsets are staged in the ring stage this window came from (its bytes now live in
             // registers) and written back coalesced; a window with more tokens than the stage holds stores directly.
+            __syncwarp();  // every lane has read its chunk of this ring stage: it may now be overwritten with token offsets
             const int ntoks = (int)(total >> 16);
             const bool stage_toks = ntoks <= WIN64 / 4;
             const uint32_t tokbuf = wb + (uint32_t)stage * WIN64;
