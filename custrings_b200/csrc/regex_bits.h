@@ -53,6 +53,8 @@ extern bool g_chain32;
 struct ChainDev;
 const ChainDev* span_chain(const Plan& plan);
 
+// Plain host executor of the chain model of a plan (tests/sim only); false when the plan is not a chain
+bool reference_execute_chain(const Plan& plan, const char* chars, const int32_t* offsets, int32_t n, uint8_t* out, uint8_t* dirty);
 // Plain host executor of a plan (tests/sim only): out[i] for every row, dirty[i] = row needs the exact path.
 void reference_execute(const Plan& plan, const char* chars, const int32_t* offsets, const uint8_t* validity, int32_t n,
                        uint8_t* out, uint8_t* dirty);

@@ -435,6 +435,61 @@ const ChainDev* device_chain(const Plan& plan) { return plan.is_chain ? &plan.ch
 const ChainDev* span_chain(const Plan& plan) { return plan.is_chain && plan.span_ok ? &plan.chain : nullptr; }
 
 // ---- plain host executor (tests/sim only) ------------------------------------------------------------------------
+// Plain host executor of the CHAIN model (ChainDev: steps with loop / opt / exit flags, one leading and one trailing
+// assertion mask) for pure-ASCII rows — the model k_chain64 evaluates with bit streams (tests/sim only).  Returns false
+// when the plan is not a chain.  Same conventions as reference_execute below.
+bool reference_execute_chain(const Plan& plan, const char* chars, const int32_t* offsets, int32_t n, uint8_t* out, uint8_t* dirty)
+{
+    if (!plan.is_chain) return false;
+    const ChainDev& C = plan.chain;
+    const AtomD alnum{AK_ALNUM, 0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        const uint8_t* s = (const uint8_t*)chars + offsets[i];
+        const int len = offsets[i + 1] - offsets[i];
+        out[i] = 0;
+        dirty[i] = 0;
+        for (int p = 0; p < len; ++p)
+            if (s[p] >= 0x80 || s[p] == 0) dirty[i] = 1;
+        if (dirty[i]) continue;
+        auto is_al = [&](int p) { return p >= 0 && p < len && atom_has(alnum, s[p]); };
+        auto is_nl = [&](int p) { return p >= 0 && p < len && s[p] == '\n'; };
+        auto holds = [&](uint32_t m, int q) {  // assertions between byte q-1 and byte q (q = len: end of the row)
+            const bool bow = is_al(q) != is_al(q - 1);
+            if ((m & AS_BOW) && !bow) return false;
+            if ((m & AS_NBOW) && bow) return false;
+            if ((m & AS_BOL_CARET) && !(q == 0 || is_nl(q - 1))) return false;
+            if ((m & AS_BOL_A) && q != 0) return false;
+            if ((m & AS_EOL_DOLLAR) && !(q == len || is_nl(q))) return false;
+            if ((m & AS_EOL_Z) && q != len) return false;
+            return true;
+        };
+        // ready[q]: step s may start consuming at byte q; after the step: fin[q] = it has just consumed byte q
+        std::vector<uint8_t> ready(len + 1, 0), fin(len, 0), done(len, 0), next(len + 1, 0);
+        for (int q = 0; q <= len; ++q) ready[q] = (C.anchored ? q == 0 : true) && holds(C.steps[0].before, q);
+        for (uint32_t st = 0; st < C.nsteps; ++st) {
+            const ChainClassD& cc = C.classes[C.steps[st].cls];
+            std::fill(fin.begin(), fin.end(), 0);
+            for (int q = 0; q < len; ++q) {
+                const bool in_class = (cc.ascii[s[q] >> 5] >> (s[q] & 31)) & 1u;
+                bool v = ready[q] && in_class;
+                if (!v && C.steps[st].loop && in_class && q > 0 && fin[q - 1]) v = true;
+                fin[q] = v;
+            }
+            if (C.steps[st].exit)
+                for (int q = 0; q < len; ++q) done[q] |= fin[q];
+            std::fill(next.begin(), next.end(), 0);
+            for (int q = 0; q < len; ++q)
+                if (fin[q]) next[q + 1] = 1;
+            if (C.steps[st].opt)
+                for (int q = 0; q <= len; ++q) next[q] |= ready[q];
+            ready = next;
+        }
+        for (int q = 0; q < len && !out[i]; ++q)
+            if (done[q] && holds(C.end_mask, q + 1)) out[i] = 1;
+    }
+    return true;
+}
+
 void reference_execute(const Plan& plan, const char* chars, const int32_t* offsets, const uint8_t* validity, int32_t n,
                        uint8_t* out, uint8_t* dirty)
 {

@@ -105,6 +105,29 @@ int sim_bits_bool(const char* chars, const int32_t* off, const uint8_t* validity
     return total;
 }
 
+// the CHAIN model (ChainDev with loop / opt / exit flags) executed on the host; -1 when the pattern is not a chain
+int sim_chain_bool(const char* chars, const int32_t* off, const uint8_t* validity, int n, const char* pattern, int anchored, uint8_t* out)
+{
+    Prog p(pattern);
+    std::shared_ptr<bits::Plan> plan = bits::lower(p.prog, anchored != 0, k_flags);
+    if (!plan) return -1;
+    std::vector<uint8_t> dirty(n ? n : 1);
+    if (!bits::reference_execute_chain(*plan, chars, off, n, out, dirty.data())) return -1;
+    ColView col{chars, off, validity, 0, n};
+    L* lists = new L;
+    lists->init();
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        if (dirty[i]) {
+            int len = off[i + 1] - off[i], mb, me;
+            out[i] = col.valid(i) ? (uint8_t)rxdev::vm_find<1024>(p.P, (const uint8_t*)chars + off[i], len, 0, anchored ? 1 : len, mb, me, *lists) : 0;
+        }
+        total += out[i];
+    }
+    delete lists;
+    return total;
+}
+
 // span fast path (chain_spans.cuh) on the host: count_re.  returns -1 when the pattern is not a last-loop chain
 int sim_chain_count(const char* chars, const int32_t* off, const uint8_t* validity, int n, const char* pattern, int32_t* out)
 {

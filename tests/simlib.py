@@ -58,6 +58,17 @@ def bits_bool(chars, offsets, validity, pattern, anchored):
     return out[:n].astype(bool), rc
 
 
+def chain_bool(chars, offsets, validity, pattern, anchored):
+    """the chain model (steps with loop / opt / exit flags) executed on the host; (None, -1) when the pattern is not a chain"""
+    chars, offsets, validity = _cols(chars, offsets, validity)
+    n = len(offsets) - 1
+    out = np.zeros(max(n, 1), np.uint8)
+    rc = lib().sim_chain_bool(_p(chars), _p(offsets), _p(validity), n, pattern.encode() if isinstance(pattern, str) else pattern, int(anchored), _p(out))
+    if rc < 0:
+        return None, -1
+    return out[:n].astype(bool), rc
+
+
 def chain_count(chars, offsets, validity, pattern):
     """span fast path; (None, -1) when the pattern is not a last-loop chain"""
     chars, offsets, validity = _cols(chars, offsets, validity)

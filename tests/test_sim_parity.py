@@ -69,6 +69,26 @@ def test_bitstream_lowering_equals_reference(data):
     assert eligible > 100
 
 
+def test_chain_model_equals_reference(data):
+    """the chain model the 64-bit kernel evaluates (optional steps, early exits, up to 8 classes) gives the reference's
+    answer for every pattern the lowering turns into a chain"""
+    from tests import simlib
+    strs, chars, offsets, validity, ref = data
+    wide = [r"colou?r", r"https?://", r"warning", r"abcdefgh", r"qu?ick\s+brown", r"\d{1,3}", r"\d{2,4}:\d\d?", r"ab*c", r"a?b?c",
+            r"x\d{2,4}\b", r"la+zy dog", r"[Tt]he quick", r"\w+\d?", r"\bthe\b", r"^\w+ ?", r"o?ver$", r"\Bx?y*z"]
+    chains = optional = 0
+    for p in SAFE_PATTERNS + wide + corpus.random_patterns(29, 200):
+        for anchored in (False, True):
+            got, cnt = simlib.chain_bool(chars, offsets, validity, p, anchored)
+            if got is None:
+                continue
+            chains += 1
+            optional += "?" in p or "*" in p or "," in p
+            want, wcnt = ref.match(p) if anchored else ref.contains_re(p)
+            assert np.array_equal(want, got) and wcnt == cnt, (p, anchored)
+    assert chains > 80 and optional > 20, (chains, optional)
+
+
 def test_headline_pattern_is_bitstream_eligible():
     from tests import simlib
     d = simlib.describe(r"\b\w{4,}\b")
