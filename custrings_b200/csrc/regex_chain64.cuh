@@ -12,8 +12,8 @@
 
 // Plan view: how the kernel reads the flags of the chain it executes.  The generic kernels (SPEC = 0) read them from the
 // parameter block: one binary interprets every chain.  For the most common shapes — a run of ONE builtin class (\w or
-// \d) of a minimum length (x+, x{n,}), bare or word-bounded (\b...\b), searched anywhere — ahead-of-time specialisations
-// (SPEC 1..4) see the assertion, class and loop flags as literals, so ptxas folds the flag tests, selects and constant-bank reads away (measured on C2:
+// \d; bare also \s and [a-z]) of a minimum length (x+, x{n,}), bare or word-bounded (\b...\b), searched anywhere —
+// ahead-of-time specialisations (SPEC 1..4, 6, 7) see the assertion, class and loop flags as literals, so ptxas folds the flag tests, selects and constant-bank reads away (measured on C2:
 // 0.445 -> 0.42 ms with every flag literal; the assertion flags alone are worth 5 %, the class flags 4 %).
 template <int SPEC>
 struct PlanLit {  // SPEC 0: no flag is literal, except that the chain has no optional step and no early exit
@@ -28,7 +28,9 @@ template <> struct PlanLit<1> { static constexpr bool on = true, opt = false; st
 template <> struct PlanLit<2> { static constexpr bool on = true, opt = false; static constexpr uint32_t needs = 0, end_mask = 0, before0 = 0, builtins = 1u << AK_DIGIT; };
 template <> struct PlanLit<3> { static constexpr bool on = true, opt = false; static constexpr uint32_t needs = AS_BOW, end_mask = AS_BOW, before0 = AS_BOW, builtins = 1u << AK_WORD; };
 template <> struct PlanLit<4> { static constexpr bool on = true, opt = false; static constexpr uint32_t needs = AS_BOW, end_mask = AS_BOW, before0 = AS_BOW, builtins = 1u << AK_DIGIT; };
-constexpr int CHAIN_SPECS = 4;
+template <> struct PlanLit<6> { static constexpr bool on = true, opt = false; static constexpr uint32_t needs = 0, end_mask = 0, before0 = 0, builtins = 1u << AK_SPACE; };
+template <> struct PlanLit<7> { static constexpr bool on = true, opt = false; static constexpr uint32_t needs = 0, end_mask = 0, before0 = 0, builtins = 1u << AK_LOWER; };
+constexpr int CHAIN_SPECS = 6;
 // which specialisation (0 = none) covers this chain
 inline int chain_spec_of(const ChainDev& cd)
 {
@@ -36,10 +38,14 @@ inline int chain_spec_of(const ChainDev& cd)
     for (uint32_t s = 0; s < cd.nsteps; ++s)  // the specialisations also fix the structure: no optional step, only the last one loops
         if (cd.steps[s].opt || (cd.steps[s].exit != 0) != (s + 1 == cd.nsteps) || (cd.steps[s].loop != 0) != (s + 1 == cd.nsteps)) return 0;
     const uint32_t b = cd.classes[0].builtins;
+    const bool bare = cd.needs == 0 && cd.end_mask == 0 && cd.steps[0].before == 0;
+    const bool word_bounded = cd.needs == AS_BOW && cd.end_mask == AS_BOW && cd.steps[0].before == AS_BOW;
+    if (b == (1u << AK_SPACE)) return bare ? 6 : 0;   // \s+
+    if (b == (1u << AK_LOWER)) return bare ? 7 : 0;   // [a-z]+
     const int kind = b == (1u << AK_WORD) ? 1 : (b == (1u << AK_DIGIT) ? 2 : 0);
     if (!kind) return 0;
-    if (cd.needs == 0 && cd.end_mask == 0 && cd.steps[0].before == 0) return kind;
-    if (cd.needs == AS_BOW && cd.end_mask == AS_BOW && cd.steps[0].before == AS_BOW) return 2 + kind;
+    if (bare) return kind;
+    if (word_bounded) return 2 + kind;
     return 0;
 }
 #define PV_NEEDS (PL::on ? PL::needs : cd.needs)
@@ -522,6 +528,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
                     else if (PV_CLS_NATOMS(k) == 0 && f == (1u << AK_DIGIT)) v = digit;
                     else if (PV_CLS_NATOMS(k) == 0 && f == (1u << AK_ALNUM)) v = alnum;
                     else if (PV_CLS_NATOMS(k) == 0 && f == (1u << AK_SPACE)) v = space;
+                    else if (PV_CLS_NATOMS(k) == 0 && f == (1u << AK_LOWER)) v = p[6] & p[5] & letter5;
                     else v = class_generic64(cd.classes[k], p, letter5, digit, alnum, word, space);
                     if (PV_CLS_NEGATE(k)) v = ~v;
                 }
@@ -686,6 +693,10 @@ static void launch_chain64_ns(const ChainDev& cd, const Args& a, int blocks)
         auto s2 = k_chain64<NS, 1, 2>;
         auto s3 = k_chain64<NS, 1, 3>;
         auto s4 = k_chain64<NS, 1, 4>;
+        auto s6 = k_chain64<NS, 1, 6>;
+        auto s7 = k_chain64<NS, 1, 7>;
+        if (spec == 6) { LAUNCH(s6, blocks, THREADS, 0, cd, a); return; }
+        if (spec == 7) { LAUNCH(s7, blocks, THREADS, 0, cd, a); return; }
         if (spec == 1) { LAUNCH(s1, blocks, THREADS, 0, cd, a); return; }
         if (spec == 2) { LAUNCH(s2, blocks, THREADS, 0, cd, a); return; }
         if (spec == 3) { LAUNCH(s3, blocks, THREADS, 0, cd, a); return; }

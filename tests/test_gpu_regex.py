@@ -12,7 +12,7 @@ SPAN_PATTERNS = [r"\b\w{4,}\b", r"\d+", r"[a-z]+", r"ab", r"a\d+", r"é+", r"\w+
                  r"\W+", r"\s\S+", r"\B\w+", r"l+", r"\w{2,}\b", r"\Aa\w*", r"\d\d?", r"[é-ü]+", r"😀.", r".\b", r"\w+\Z", r"\D{3}", r"_+",
                  # every shape-specialised chain kernel (regex_chain64.cuh SPEC 1..4, NS 1..4)
                  r"\w+", r"\w{2,}", r"\w{3,}", r"\w{4,}", r"\d{2,}", r"\d{3,}", r"\d\d\d\d+", r"\b\w+\b", r"\b\w{2,}\b", r"\b\w{3,}\b",
-                 r"\b\d+\b", r"\b\d{2,}\b", r"\b\d{3,}\b", r"\b\d{4,}\b"]
+                 r"\b\d+\b", r"\b\d{2,}\b", r"\b\d{3,}\b", r"\b\d{4,}\b", r"\s+", r"\s{2,}", r"[a-z]+", r"[a-z]{2,}", r"[a-z]{3,}", r"[a-z]{4,}"]
 
 
 # top-level alternations of chains: OR of chain-kernel runs instead of the DAG interpreter
@@ -40,7 +40,7 @@ def test_contains_match_count_patterns(cols, tier):
     strs, dev, ref = cols
     lib().custr_set_regex_tier(tier)
     try:
-        pats = [p for p in corpus.PATTERNS if p not in (r"(a|b)*c", r"((a|b)c)*d", "a+*")] + corpus.random_patterns(11, 150) + SPAN_PATTERNS[-14:] + ALTERNATIONS + WIDE_CHAINS
+        pats = [p for p in corpus.PATTERNS if p not in (r"(a|b)*c", r"((a|b)c)*d", "a+*")] + corpus.random_patterns(11, 150) + SPAN_PATTERNS[-20:] + ALTERNATIONS + WIDE_CHAINS
         for p in pats:
             rc, rn = ref.contains_re(p)
             assert _none_to(False, dev.contains(p)) == rc.tolist(), p
