@@ -14,7 +14,11 @@ NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nv
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
 
-SOURCES = ["column.cu", "regex.cu", "regex_bits.cu", "regex_bits_lower.cpp", "regex_compile.cpp", "find.cu", "split.cu", "category.cu", "classes.cpp"]
+# (source, extra defines, object name); regex_item.cu is built once per chain-length group so its instantiations compile in parallel
+SOURCES = [("regex_bits.cu", [], None), ("regex_item.cu", ["-DITEM_NS_GROUP=0"], "regex_item_g0"), ("regex_item.cu", ["-DITEM_NS_GROUP=1"], "regex_item_g1"),
+           ("regex_item.cu", ["-DITEM_NS_GROUP=2"], "regex_item_g2"), ("regex_item.cu", ["-DITEM_NS_GROUP=3"], "regex_item_g3"),
+           ("regex.cu", [], None), ("column.cu", [], None), ("find.cu", [], None), ("split.cu", [], None), ("category.cu", [], None),
+           ("regex_bits_lower.cpp", [], None), ("regex_compile.cpp", [], None), ("classes.cpp", [], None)]
 
 
 def _stale(out, deps):
@@ -30,12 +34,13 @@ def _headers():
     return hs
 
 
-def _compile(src, verbose):
+def _compile(item, verbose):
+    src, defines, name = item
     path = os.path.join(CSRC, src)
-    obj = os.path.join(OBJ, src.rsplit(".", 1)[0] + ".o")
+    obj = os.path.join(OBJ, (name or src.rsplit(".", 1)[0]) + ".o")
     if not _stale(obj, [path] + _headers()):
         return obj
-    cmd = [NVCC] + ARCH + COMMON + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+    cmd = [NVCC] + ARCH + COMMON + defines + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -53,7 +58,7 @@ def build(verbose=False, force=False):
     if force:
         shutil.rmtree(OBJ)
         os.makedirs(OBJ)
-    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s[0]))]
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
     if _stale(LIB, objs):

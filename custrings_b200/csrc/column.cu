@@ -42,14 +42,17 @@ DeviceBuf::~DeviceBuf()
 
 int num_sms()
 {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    static std::atomic<int> sms[64];  // per device (custr_set_device may switch devices inside one process)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int v = sms[dev].load(std::memory_order_relaxed);
+    if (!v) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
+        sms[dev].store(v, std::memory_order_relaxed);
     }
-    return sms;
+    return v;
 }
 
 BufPtr upload(const void* host, size_t bytes)
@@ -216,18 +219,29 @@ __global__ void k_clamp_rows(int32_t* idx, int32_t m, int32_t n)
 // ------------------------------------------------------------------------------------------------ helpers
 static inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
+struct WidenLen {
+    __host__ __device__ __forceinline__ long long operator()(int32_t v) const { return (long long)v; }
+};
+
 int64_t scan_lengths_to_offsets(const int32_t* lengths, int32_t* offsets, int32_t n)
 {
-    // offsets[0..n-1] = exclusive scan; offsets[n] = total
-    size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, lengths, offsets, n + 1, g_stream);
-    BufPtr tmp = dev_alloc(tmp_bytes);
-    // lengths must have n+1 readable entries (callers allocate n+1 and zero the last)
-    CUSTR_CUDA(cub::DeviceScan::ExclusiveSum(tmp->ptr, tmp_bytes, lengths, offsets, n + 1, g_stream));
+    // The total is accumulated in 64 bits FIRST (a column that grows past 2 GiB must be rejected, not wrapped: the int32
+    // scan below would otherwise hand the write pass offsets that alias), then offsets[0..n-1] = exclusive scan,
+    // offsets[n] = total.  lengths must have n+1 readable entries (callers allocate n+1 and zero the last).
+    Scratch<long long> wide(1);
+    cub::TransformInputIterator<long long, WidenLen, const int32_t*> it(lengths, WidenLen{});
+    size_t tmp_bytes = 0, tmp2 = 0;
+    cub::DeviceReduce::Sum(nullptr, tmp_bytes, it, wide.get(), n, g_stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, lengths, offsets, n + 1, g_stream);
+    BufPtr tmp = dev_alloc(tmp_bytes > tmp2 ? tmp_bytes : tmp2);
+    CUSTR_CUDA(cub::DeviceReduce::Sum(tmp->ptr, tmp_bytes, it, wide.get(), n, g_stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    int32_t total = 0;
-    CUSTR_CUDA(cudaMemcpyAsync(&total, offsets + n, sizeof(int32_t), cudaMemcpyDeviceToHost, g_stream));
+    long long total = 0;
+    CUSTR_CUDA(cudaMemcpyAsync(&total, wide.get(), sizeof(total), cudaMemcpyDeviceToHost, g_stream));
     CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    if (total > 0x7fffffffLL) throw ArgError{fail(CUSTR_ERR_INVALID, "result exceeds 2 GiB of chars / 2^31 entries (int32 offsets)")};
+    CUSTR_CUDA(cub::DeviceScan::ExclusiveSum(tmp->ptr, tmp2, lengths, offsets, n + 1, g_stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return total;
 }
 

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include <atomic>
+#include <type_traits>
 #include "../../include/custr.h"
 
 namespace custr {
@@ -153,7 +154,10 @@ R guarded(F&& f, R on_arg, R on_cuda)
 {
     try { return f(); }
     catch (const CudaError&) { return on_cuda; }
-    catch (const ArgError&) { return on_arg; }
+    catch (const ArgError& e) {  // integer entry points report the code that was raised (CUSTR_ERR_INVALID stays distinguishable from a null argument)
+        if constexpr (std::is_integral<R>::value) return e.code ? (R)e.code : on_arg;
+        else return on_arg;
+    }
     catch (const std::bad_alloc&) { g_error = "host allocation failed"; return on_cuda; }
 }
 

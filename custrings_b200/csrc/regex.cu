@@ -23,16 +23,25 @@ static const uint8_t k_unicode_flags_host[65536] = {
 #include "unicode_flags.inc"
 };
 const uint8_t* host_unicode_flags() { return k_unicode_flags_host; }
+static int current_device()
+{
+    int dev = 0;
+    CUSTR_CUDA(cudaGetDevice(&dev));
+    return dev;
+}
+// one table per device: after custr_set_device() the kernels must not dereference the first device's copy
 const uint8_t* device_unicode_flags()
 {
-    static std::once_flag once;
-    static uint8_t* d = nullptr;
-    static cudaError_t err = cudaSuccess;
-    std::call_once(once, [] {
-        err = cudaMalloc(&d, 65536);
-        if (err == cudaSuccess) err = cudaMemcpy(d, k_unicode_flags_host, 65536, cudaMemcpyHostToDevice);
-    });
-    if (err != cudaSuccess) CUSTR_CUDA(err);
+    static std::mutex mu;
+    static std::map<int, uint8_t*> tables;
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = tables.find(dev);
+    if (it != tables.end()) return it->second;
+    uint8_t* d = nullptr;
+    CUSTR_CUDA(cudaMalloc(&d, 65536));
+    CUSTR_CUDA(cudaMemcpy(d, k_unicode_flags_host, 65536, cudaMemcpyHostToDevice));
+    tables[dev] = d;
     return d;
 }
 
@@ -73,12 +82,15 @@ struct Compiled {
 };
 using CompiledPtr = std::shared_ptr<Compiled>;
 
+// Entries are keyed by (device, pattern): the program image lives in the memory of the device that was current when it
+// was uploaded.  Both bit-stream plans are built here, under the lock, so a cached entry is immutable once visible.
 static CompiledPtr get_compiled(const char* pattern)
 {
     static std::mutex mu;
     static std::list<std::pair<std::string, CompiledPtr>> lru;
+    const int dev = current_device();
     std::lock_guard<std::mutex> lock(mu);
-    std::string key(pattern);
+    std::string key = std::to_string(dev) + ":" + pattern;
     for (auto it = lru.begin(); it != lru.end(); ++it)
         if (it->first == key) {
             lru.splice(lru.begin(), lru, it);
@@ -88,6 +100,9 @@ static CompiledPtr get_compiled(const char* pattern)
     c->prog = rx::compile(pattern);
     c->image = rx::serialize(c->prog, host_unicode_flags());
     c->dev_image = upload(c->image.data(), c->image.size());
+    c->plan_contains = bits::lower(c->prog, false, host_unicode_flags());
+    c->plan_match = bits::lower(c->prog, true, host_unicode_flags());
+    c->plans_built = true;
     // the image must be resident before another stream/thread uses the cached entry
     CUSTR_CUDA(cudaStreamSynchronize(g_stream));
     lru.emplace_front(key, c);
@@ -788,7 +803,7 @@ static bool alternation_of_chains(const custr_column* col, const char* pattern, 
                                   int32_t** dirty_rows, unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count)
 {
     std::vector<std::string> alts;
-    if (bits::g_force_generic || bits::g_chain32 || !split_top_level(pattern, alts)) return false;
+    if (bits::g_force_generic || !split_top_level(pattern, alts)) return false;
     std::vector<CompiledPtr> progs;
     for (const std::string& a : alts) {
         progs.push_back(get_compiled(a.c_str()));
@@ -823,7 +838,7 @@ static bool alternation_of_chains(const custr_column* col, const char* pattern, 
 bool literal_contains_chain(const custr_column* col, const char* literal, uint8_t* out_dev, unsigned long long* total, int32_t** dirty_rows,
                             unsigned int** dirty_count, BufPtr& keep_rows, BufPtr& keep_count)
 {
-    if (g_forced_tier == 1 || bits::g_force_generic || bits::g_chain32) return false;
+    if (g_forced_tier == 1 || bits::g_force_generic) return false;
     std::string pat;
     for (const char* p = literal; *p; ++p) {
         if (strchr("\\.[](){}*+?|^$", *p)) pat.push_back('\\');
@@ -973,7 +988,7 @@ void custr_set_regex_tier(int tier)
 {
     g_forced_tier = tier == 1 ? 1 : 0;
     bits::g_force_generic = tier == 2;  // 2: bitstream tier, generic DAG interpreter even for chain-shaped plans
-    bits::g_chain32 = tier == 3;        // 3: bitstream tier, 32-bit-stream chain kernel
+    bits::g_chain_win = tier == 3;      // 3: bitstream tier, window-at-a-time chain kernel (k_chain64) also for boolean results
     bits::g_no_spec = tier == 4;        // 4: 64-bit chain kernel without the shape specialisations
 }
 

@@ -43,9 +43,9 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
 // delimiter bytes.  Produces the flat token column (chars + int32 offsets[ntok + 1]).  False = not applicable.
 bool tokenize_flat(const custr_column* col, const uint8_t* delims, int ndelims, BufPtr& out_chars, BufPtr& out_off, int64_t& ntok,
                    int64_t& nbytes);
-extern bool g_force_generic;
-extern bool g_no_spec;
-extern bool g_chain32;
+extern thread_local bool g_force_generic;
+extern thread_local bool g_no_spec;
+extern thread_local bool g_chain_win;
 
 // Non-null when the plan is a linear chain whose only loop is its last step: for those patterns the match SPAN the Pike VM
 // reports (leftmost start, then thread priority) is "leftmost start, longest end that satisfies the trailing assertion",

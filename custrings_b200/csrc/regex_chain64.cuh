@@ -211,21 +211,31 @@ struct NaClasses {
     u64 c[NCLS];
     u64 al;
 };
-template <int NCLS>
+// shared address of byte `rel` (0..63) of this lane's 64 staged bytes.  LAYOUT 0 (k_chain64): `a0` = address of the lane's
+// chunk 0, chunks XOR-swizzled; LAYOUT 1 (k_chain_item, regex_chain_item.cuh): `a0` = stage base + 128 * (lane >> 3), chunk
+// kk of lane o sits at kk * 512 + 128 * (o >> 3) + 16 * ((o + 2 kk) & 7).
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t ring_byte_addr(uint32_t a0, int rel)
+{
+    if (LAYOUT == 0) return (a0 ^ (uint32_t)(rel & 48)) + (uint32_t)(rel & 15);
+    const uint32_t kk = (uint32_t)rel >> 4;
+    return a0 + kk * 512u + 16u * ((lane_id() + 2u * kk) & 7u) + (uint32_t)(rel & 15);
+}
+template <int NCLS, int LAYOUT = 0>
 __device__ __noinline__ NaClasses<NCLS> classify_non_ascii64(const ChainDev& cd, const Args& A, uint32_t my0, int lane_base, u64 na,
                                                              NaClasses<NCLS> r)
 {
     const uint8_t* base = (const uint8_t*)A.chars;
     auto byte_at = [&](int pos) -> uint32_t {
         const int rel = pos - lane_base;
-        if ((unsigned)rel < 64u) return lds8((my0 ^ (uint32_t)(rel & 48)) + (uint32_t)(rel & 15));
+        if ((unsigned)rel < 64u) return lds8(ring_byte_addr<LAYOUT>(my0, rel));
         return pos < A.end ? base[pos] : 0u;
     };
     while (na) {
         const int b = __ffsll((long long)na) - 1;
         if (b < 63) {  // fast path: a 2-byte character (U+0080..U+07FF) that lies inside this lane's 64 bytes
-            const uint32_t lead = lds8((my0 ^ (uint32_t)(b & 48)) + (uint32_t)(b & 15));
-            const uint32_t next = lds8((my0 ^ (uint32_t)((b + 1) & 48)) + (uint32_t)((b + 1) & 15));
+            const uint32_t lead = lds8(ring_byte_addr<LAYOUT>(my0, b));
+            const uint32_t next = lds8(ring_byte_addr<LAYOUT>(my0, b + 1));
             if ((lead & 0xE0u) == 0xC0u && (next & 0xC0u) == 0x80u) {
                 const uint32_t cp = ((lead & 0x1Fu) << 6) | (next & 0x3Fu);
                 const u64 bits = 3ull << b;
@@ -273,7 +283,7 @@ struct SpanSink {
     size_t widx;
     int wp, byte_a, byte_b;
 };
-__device__ __noinline__ void store_spans(const SpanSink s, u64 m, u64 k, u64 a)
+static __device__ __noinline__ void store_spans(const SpanSink s, u64 m, u64 k, u64 a)
 {
     if (s.wp >= s.byte_a && s.wp + 64 <= s.byte_b) {
         s.m[s.widx] = m;
@@ -367,7 +377,7 @@ __device__ __forceinline__ u64 chain_eval64(const ChainDev& cd, const u64 (&c)[N
 
 // the window that holds the end of the buffer (once per column): chunks that exist completely are copied with cp.async, the
 // others are zero-filled and patched with the bytes that exist (plain stores by the lane that will read them back)
-__device__ __noinline__ void ring_issue_tail(uint32_t dst0, const char* __restrict__ chars, int ws, int end, uint32_t lane)
+static __device__ __noinline__ void ring_issue_tail(uint32_t dst0, const char* __restrict__ chars, int ws, int end, uint32_t lane)
 {
     for (int k = 0; k < 4; ++k) {
         const int pos = ws + 64 * (int)lane + 16 * k;
@@ -667,6 +677,7 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
     if (lane == 0 && my_matches) atomicAdd(A.total, my_matches);
 }
 
+#ifndef CUSTR_NO_LAUNCHERS
 #ifndef CUSTR_EXPERIMENT_ONLY_4_1
 template <int NS>
 static void launch_chain64_ns(const ChainDev& cd, const Args& a, int blocks)
@@ -729,3 +740,4 @@ static void launch_chain64(const ChainDev& cd, const Args& a, int blocks)
     }
 #endif
 }
+#endif  // CUSTR_NO_LAUNCHERS

@@ -1,0 +1,384 @@
+// Item-buffered linear-chain kernel (boolean results: contains_re / match / literal contains) — included by regex_item.cu
+// inside namespace custr::bits, after regex_chain64.cuh (whose stream helpers, plan view and UTF-8 classifier it shares).
+//
+// k_chain64 walks the offsets array once per 2 KiB window: ROWSTART scatter, look-ahead byte, row finalisation, NUL
+// bookkeeping — about 190 of its 567 warp-instructions per window (ncu source page, profiles/r2_*).  This kernel takes the
+// row bookkeeping OUT of the window loop.  A work item (a contiguous row range of about 32 KiB of chars, as before) is
+// processed in SEGMENTS of up to SEG_WINS windows whose bit streams live in shared memory for the whole segment:
+//
+//   phase 0   ROWSTART bits of every row start of the segment are scattered into `bits` (red.shared.or), 32 rows per step;
+//   phase A   window loop — per lane: 64 staged bytes -> 8 bit planes -> class streams -> marker chain -> match-end stream
+//             E -> per-row sticky OR  F = spread(E, ~ROWSTART), which REPLACES the window's ROWSTART word in `bits`.
+//             No offsets, no result stores, no look-ahead load in here;
+//   phase B   one pass over the rows that end in the segment: result = bit of F at the row's last byte, 32 rows per step,
+//             every row of the item is written (no pre-clearing memset of the result array).
+//
+// What else changed against k_chain64:
+//   * look-ahead (\b / $ / "last byte of a character" behind the last byte of a window) is DEFERRED instead of loaded: when
+//     no row starts right behind the window, the match-end bit of the window's last position is withheld and decided at the
+//     top of the next window, where the class of the following byte is in registers anyway; it enters the sticky stream
+//     through the carry.  (When a row does start there the look-ahead is "end of row" and nothing is deferred.)
+//   * char staging: every cp.async instruction copies 512 CONTIGUOUS bytes (lane L: 16 bytes at 512 k + 16 L) — 4 global
+//     lines per instruction instead of 16 — into a chunk-major, rotated layout (chunk kk of owner lane o at
+//     kk * 512 + 128 (o >> 3) + 16 ((o + 2 kk) & 7)) that makes both the cp.async writes and the LDS.128 read-back
+//     bank-conflict free with immediate offsets only.
+//   * windows without non-ASCII bytes (warp-uniform test) run a chain body without the UTF-8 terms; windows with them run
+//     the general body.  NUL bytes are only ACCUMULATED per lane; an item that saw one re-checks its rows in phase B (rare).
+#pragma once
+
+constexpr int SEG_WINS = 18;                 // windows per segment: a 32 KiB item, its unaligned head and its last row
+constexpr int SEG_WORDS = SEG_WINS * 32;     // 64-bit stream words per segment
+struct __align__(128) WarpSmItem {
+    char ring[RING_STAGES][WIN64];
+    u64 bits[SEG_WORDS + 16];                // ROWSTART, then F, per window; one extra word: a row start right behind the segment
+};
+constexpr uint32_t ITEM_SM_BITS = RING_STAGES * WIN64;
+constexpr int ITEM_SMEM_BYTES = WARPS * (int)sizeof(WarpSmItem);
+
+template <int NS>
+struct ItemState {  // top words of the previous window's streams (lane 31's copy is the one that is used)
+    uint32_t last[NS];
+    uint32_t last_al, last_nl, last_f;
+    uint32_t pend;  // bit 31: a match may end at the previous window's last position, subject to the look-ahead assertions
+};
+
+static __device__ __noinline__ void ring_issue_item_tail(uint32_t wr, const char* __restrict__ chars, uint32_t ws, uint32_t end, uint32_t lane)
+{
+    for (uint32_t k = 0; k < 4; ++k) {
+        const uint32_t pos = ws + 512u * k + 16u * lane;
+        const uint32_t dst = wr + 128u * k;
+        if (pos + 16u <= end) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(chars + pos) : "memory");
+            continue;
+        }
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+        for (uint32_t q = pos; q < end; ++q) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst + (q - pos)), "r"((uint32_t)(uint8_t)chars[q]) : "memory");
+    }
+}
+// copy of window [ws, ws + 2048) into a ring stage: `wr` = this lane's write address in that stage, `gsrc` = chars + 16 * lane
+__device__ __forceinline__ void ring_issue_item(uint32_t wr, const char* __restrict__ gsrc, const char* __restrict__ chars, uint32_t ws, uint32_t end,
+                                                uint32_t lane)
+{
+    if (ws + WIN64 <= end) {
+        const char* src = gsrc + ws;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wr + 128u * k), "l"(src + 512 * k) : "memory");
+    } else
+        ring_issue_item_tail(wr, chars, ws, end, lane);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// x >> 1 with the bit behind the lane's word taken from `nxt` (low word of the next lane's / next window's stream word)
+__device__ __forceinline__ u64 shift_down64_nb(u64 x, uint32_t nxt) { return mk64(__funnelshift_r(lo32(x), hi32(x), 1), __funnelshift_r(hi32(x), nxt, 1)); }
+
+// Marker chain of one window.  Returns the stream of positions behind which a match may end, BEFORE the zero-width
+// assertions of END are applied.  UTF8 = false: the window holds ASCII bytes only (cont == 0, every byte is a character).
+template <int NS, int NCLS, int SPEC, bool UTF8>
+__device__ __forceinline__ u64 chain_item64(const ChainDev& cd, const u64 (&c)[NCLS], const Assertions64& as, u64 rs, int rounds, u64 cont, uint32_t cont0,
+                                            ItemState<NS>& st, const LaneCtx& L)
+{
+    using PL = PlanLit<SPEC>;
+    const u64 nrs = ~rs;
+    u64 fin = ~0ull;  // last byte of a character (the window's last position: decided by the deferred look-ahead)
+    if (UTF8) fin = ~shift_down64(cont, 0u, L);
+    u64 P = 0, ready = 0, done = 0;
+    uint32_t old_prev = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        u64 t;
+        if (s == 0) {
+            t = PV_ANCHORED ? rs : ~0ull;
+            const uint32_t before = PV_BEFORE0;
+            if (before) t = apply_before64(t, before, as);
+        } else {
+            t = adv64(P, (UTF8 && cont0) ? 0u : old_prev, L) & nrs;
+            if (PV_STEP_OPT(s - 1)) t |= ready;
+        }
+        ready = t;
+        const u64 ck = sel_class64<NCLS>(c, PV_STEP_CLS(s));
+        t &= UTF8 ? (ck & ~cont) : ck;
+        const uint32_t old = st.last[s];
+        u64 Z = t;
+        if (PV_STEP_LOOP(s)) Z = spread64(t, ck & nrs, old, L);
+        else if (UTF8) {
+#pragma unroll 1
+            for (int r = 0; r < rounds; ++r) Z |= adv64(Z, old, L) & cont;
+        }
+        st.last[s] = hi32(Z);
+        old_prev = old;
+        P = UTF8 ? (Z & fin) : Z;
+        if (PV_STEP_EXIT(s)) done |= P;
+    }
+    return done;
+}
+
+template <int NS, int NCLS, int SPEC = 0>
+__global__ void __launch_bounds__(THREADS, 3)
+k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
+{
+    using PL = PlanLit<SPEC>;
+    extern __shared__ __align__(128) unsigned char item_smem[];
+    LaneCtx L;
+    L.lane = lane_id();
+    asm volatile("" : "+r"(L.lane));
+    L.src = (L.lane + 31) & 31;
+    L.is31 = L.lane == 31;
+    const uint32_t lane = L.lane;
+    uint32_t wb = (uint32_t)__cvta_generic_to_shared(item_smem) + (threadIdx.x >> 5) * (uint32_t)sizeof(WarpSmItem);  // this warp's block
+    uint32_t bits0 = wb + ITEM_SM_BITS;
+    uint32_t wr0 = wb + (lane & 3u) * 512u + 16u * (((lane >> 2) + 2u * (lane & 3u)) & 7u);  // my cp.async destination (+ 128 k, + stage)
+    uint32_t rd0 = wb + 128u * (lane >> 3);                                                    // my read-back base (+ chunk terms, + stage)
+    const uint32_t r1 = 512u + 16u * ((lane + 2u) & 7u), r2 = 1024u + 16u * ((lane + 4u) & 7u), r3 = 1536u + 16u * ((lane + 6u) & 7u);
+    const uint32_t r0 = 16u * (lane & 7u);
+    const char* gsrc = A.chars + 16 * (int)lane;
+    asm volatile("" : "+r"(wb), "+r"(bits0), "+r"(wr0), "+r"(rd0));
+    const uint32_t bneed = PV_BUILTIN_UNION | ((PV_NEEDS & (AS_BOW | AS_NBOW)) ? (1u << AK_ALNUM) : 0u);
+    const bool need_nl = (PV_NEEDS & (AS_BOL_CARET | AS_EOL_DOLLAR | AS_EOL_Z)) != 0;
+    const uint32_t uend = (uint32_t)A.end;
+    uint32_t cnt = 0;  // rows with a match finalised by this lane
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(A.item_counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= A.nitems) break;
+        const int ra = __ldg(A.item_bounds + item), rb = __ldg(A.item_bounds + item + 1);
+        if (ra >= rb) continue;
+        const int byte_a = __ldg(A.offsets + ra), byte_b = __ldg(A.offsets + rb);
+        // (an item that holds only empty rows runs the segment loop once with no window: phase B writes its zeros.  A separate
+        // loop + `continue` here makes ptxas give up structured reconvergence for the whole kernel: BRA.DIV guards everywhere)
+        const bool empty_item = byte_a >= byte_b;
+        ItemState<NS> st;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) st.last[s] = 0;
+        st.last_al = st.last_nl = st.last_f = st.pend = 0;
+        u64 zacc = 0;  // NUL bytes seen by this lane in this item
+        uint32_t ws = empty_item ? (uint32_t)byte_a : ((uint32_t)byte_a & ~(uint32_t)(WIN64 - 1));
+        int wins_left = empty_item ? 0 : (int)((((uint32_t)byte_b - 1u) >> 11) - ((uint32_t)byte_a >> 11)) + 1;
+        int krs = ra;   // next offsets index whose ROWSTART bit is not set yet
+        int kfin = ra;  // next row to finalise
+        uint32_t stage = 0;
+        __syncwarp();  // the previous item's reads of the ring and of `bits` are done
+        if (!empty_item) ring_issue_item(wr0, gsrc, A.chars, ws, uend, lane);
+
+        do {
+            const int nw = wins_left < SEG_WINS ? wins_left : SEG_WINS;
+            const uint32_t seg_ws = ws;
+            const uint32_t span = (uint32_t)nw * WIN64;
+            // ---- phase 0: ROWSTART bits of the segment (and of the position right behind it: extra word)
+            for (uint32_t i = 2u * lane; i <= 32u * (uint32_t)nw; i += 64u)
+                asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(bits0 + 8u * i), "r"(0u) : "memory");
+            __syncwarp();
+            for (;;) {
+                const int j = krs + (int)lane;
+                const bool live = j <= rb;
+                const uint32_t rel = live ? (uint32_t)__ldg(A.offsets + j) - seg_ws : 0xffffffffu;
+                if (live && rel <= span) reds_or(bits0 + 4u * (rel >> 5), 1u << (rel & 31));
+                const unsigned m = __ballot_sync(FULL, live && rel < span);
+                krs += __popc(m);
+                if (m != FULL) break;
+            }
+            __syncwarp();
+
+            // ---- phase A: the windows of the segment
+            for (int w = 0; w < nw; ++w, ws += WIN64, stage ^= 1u) {
+                const bool more = (w + 1 < nw) || (wins_left > nw);
+                const uint32_t so = stage * WIN64;
+                if (more) ring_issue_item(wr0 + (so ^ WIN64), gsrc, A.chars, ws + WIN64, uend, lane);  // next window in flight
+                const uint32_t wa = bits0 + 8u * (32u * (uint32_t)w + lane);  // my word of the segment's stream
+                const u64 rs = lds64(wa);
+                const uint32_t rs_nb = lds32(wa + 8u);                                   // low word of the next stream word
+                const bool rs_next = (lds32(bits0 + 256u * (uint32_t)(w + 1)) & 1u) != 0;  // a row starts right behind this window
+                if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                else asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();  // every lane's copies of this window have landed
+                u64 p[8];
+                {
+                    uint32_t pl[8], ph[8];
+                    const uint32_t rb_ = rd0 + so;
+                    const uint4 v0 = lds128(rb_ + r0);
+                    const uint4 v1 = lds128(rb_ + r1);
+                    transpose_planes(v0, v1, pl);
+                    const uint4 v2 = lds128(rb_ + r2);
+                    const uint4 v3 = lds128(rb_ + r3);
+                    transpose_planes(v2, v3, ph);
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) p[b] = mk64(pl[b], ph[b]);
+                }
+                const u64 na = p[7];
+                const u64 letter5 = cls_letter5(p), digit = cls_digit(p);
+                const u64 alnum = (p[6] & letter5) | digit, word = alnum | cls_underscore(p);
+                zacc |= ~(p[0] | p[1] | p[2] | p[3] | p[4] | p[5] | p[6] | p[7]);
+                u64 space = 0;
+                if (bneed & (1u << AK_SPACE)) space = cls_space(p);
+                NaClasses<NCLS> nc;
+                u64 (&c)[NCLS] = nc.c;
+#pragma unroll
+                for (int k = 0; k < NCLS; ++k) {
+                    u64 v = 0;
+                    if (k < (int)PV_NCLASSES) {
+                        const uint32_t f = PV_CLS_BUILTINS(k);
+                        if (PV_CLS_NATOMS(k) == 0 && f == (1u << AK_WORD)) v = word;  // single builtin: inline
+                        else if (PV_CLS_NATOMS(k) == 0 && f == (1u << AK_DIGIT)) v = digit;
+                        else if (PV_CLS_NATOMS(k) == 0 && f == (1u << AK_ALNUM)) v = alnum;
+                        else if (PV_CLS_NATOMS(k) == 0 && f == (1u << AK_SPACE)) v = space;
+                        else if (PV_CLS_NATOMS(k) == 0 && f == (1u << AK_LOWER)) v = p[6] & p[5] & letter5;
+                        else v = class_generic64(cd.classes[k], p, letter5, digit, alnum, word, space);
+                        if (PV_CLS_NEGATE(k)) v = ~v;
+                    }
+                    c[k] = v;
+                }
+                nc.al = alnum;
+                u64 nl = need_nl ? (cls_eq(p, '\n') & ~na) : 0ull;
+                const bool utf8 = __any_sync(FULL, na != 0);
+                u64 cont = 0;
+                uint32_t cont0 = 0;
+                int rounds = 0;
+                if (utf8) {
+                    if (na) nc = classify_non_ascii64<NCLS, 1>(cd, A, rd0 + so, (int)ws + 64 * (int)lane, na, nc);
+                    cont = p[7] & ~p[6];
+                    const u64 lead3 = p[7] & p[6] & p[5];  // lead byte of a 3- or 4-byte character
+                    rounds = 1 + (int)__any_sync(FULL, lead3 != 0) + (int)__any_sync(FULL, (lead3 & p[4]) != 0);
+                    cont0 = __shfl_sync(FULL, lo32(cont), 0) & 1u;
+                }
+                const u64 al = nc.al;
+                const u64 nrs = ~rs;
+
+                // ---- the match end withheld at the previous window's last position: its look-ahead is this window's first byte
+                {
+                    uint32_t ok = st.pend;
+                    const uint32_t em = PV_END_MASK;
+                    if (em & (AS_BOW | AS_NBOW)) {
+                        const uint32_t differ = st.last_al ^ (__shfl_sync(FULL, lo32(al), 0) << 31);  // alnum before / behind the boundary
+                        if (em & AS_BOW) ok &= differ;
+                        if (em & AS_NBOW) ok &= ~differ;
+                    }
+                    if (em & AS_EOL_DOLLAR) ok &= __shfl_sync(FULL, lo32(nl), 0) << 31;  // '$' in the middle of a row: a newline follows
+                    if (em & AS_EOL_Z) ok = 0;
+                    if (utf8 && cont0) ok = 0;  // the window boundary lies inside a character
+                    st.last_f |= ok & 0x80000000u;
+                }
+
+                // ---- zero-width assertion streams (look-ahead behind the window's last position: "end of row", see below)
+                Assertions64 as;
+                as.rs = rs;
+                as.nl = nl;
+                as.bow_b = as.bow_a = as.bolc_b = as.lb = as.eold_a = 0;
+                if (PV_NEEDS & (AS_BOW | AS_NBOW)) {
+                    as.bow_b = al ^ (adv64(al, st.last_al, L) & nrs);
+                    as.bow_a = al ^ shift_down64(al & nrs, 0u, L);
+                    st.last_al = hi32(al);
+                }
+                if (PV_NEEDS & (AS_BOL_CARET | AS_EOL_DOLLAR | AS_EOL_Z)) {
+                    as.bolc_b = rs | (adv64(nl, st.last_nl, L) & nrs);
+                    as.lb = shift_down64_nb(rs, rs_nb);
+                    as.eold_a = as.lb | shift_down64(nl & nrs, 0u, L);
+                    st.last_nl = hi32(nl);
+                }
+                u64 done;
+                if (!utf8) done = chain_item64<NS, NCLS, SPEC, false>(cd, c, as, rs, 0, 0ull, 0u, st, L);
+                else done = chain_item64<NS, NCLS, SPEC, true>(cd, c, as, rs, rounds, cont, cont0, st, L);
+                u64 E = PV_END_MASK ? apply_after64(done, PV_END_MASK, as) : done;
+                // the last position of the window: with a row start right behind it the look-ahead used above ("nothing
+                // follows") is exact; otherwise the bit is withheld and decided by the next window
+                {
+                    u64 d2 = done;  // END assertions that need no look-ahead
+                    if (PV_END_MASK & AS_BOL_CARET) d2 &= nl;
+                    if (PV_END_MASK & AS_BOL_A) d2 = 0;
+                    const uint32_t hold = (L.is31 && !rs_next) ? 0x80000000u : 0u;
+                    st.pend = hi32(d2) & hold;
+                    E &= ~((u64)hold << 32);
+                }
+                // ---- sticky per-row OR of the match ends; it replaces the window's ROWSTART word
+                const u64 F = spread64(E, nrs, st.last_f, L);
+                st.last_f = hi32(F);
+                sts64(wa, lo32(F), hi32(F));
+                __syncwarp();  // ring stage and stream words are free for the next iteration / phase B
+            }
+
+            // ---- phase B: the rows that end inside the segment
+            const bool item_dirty = __any_sync(FULL, zacc != 0);
+            for (;;) {
+                const int j = kfin + (int)lane;
+                bool in = false;
+                uint32_t hit = 0;
+                int o0 = 0, o1 = 0;
+                if (j < rb) {
+                    o0 = __ldg(A.offsets + j);
+                    o1 = __ldg(A.offsets + j + 1);
+                    in = (uint32_t)o1 - seg_ws <= span;
+                }
+                if (in && o1 > o0) {
+                    const uint32_t rel = (uint32_t)o1 - 1u - seg_ws;
+                    hit = (lds32(bits0 + 4u * (rel >> 5)) >> (rel & 31)) & 1u;
+                }
+                if (__builtin_expect(item_dirty, 0)) {  // a NUL byte somewhere in this item: rows holding one go to the exact VM
+                    bool dirty = false;
+                    if (in)
+                        for (int q = o0; q < o1 && !dirty; ++q) dirty = A.chars[q] == 0;
+                    const unsigned dm = __ballot_sync(FULL, dirty);
+                    if (dm) {
+                        unsigned basei = 0;
+                        if (lane == 0) basei = atomicAdd(A.dirty_count, __popc(dm));
+                        basei = __shfl_sync(FULL, basei, 0);
+                        if (dirty) {
+                            A.dirty_rows[basei + __popc(dm & ((1u << lane) - 1))] = j;
+                            hit = 0;
+                        }
+                    }
+                }
+                if (in) {
+                    A.out[j] = (uint8_t)hit;
+                    cnt += hit;
+                }
+                const unsigned m = __ballot_sync(FULL, in);
+                kfin += __popc(m);
+                if (m != FULL) break;
+            }
+            wins_left -= nw;
+            __syncwarp();
+        } while (wins_left > 0);
+    }
+    cnt = __reduce_add_sync(FULL, cnt);
+    if (lane == 0 && cnt) atomicAdd(A.total, (unsigned long long)cnt);
+}
+
+#ifndef ITEM_EXPERIMENT
+template <int NS>
+static void launch_item_ns(const ChainDev& cd, const Args& a, int blocks)
+{
+#define ITEM_LAUNCH(K)                                                                                                   \
+    do {                                                                                                                 \
+        auto kfn = K;                                                                                                    \
+        CUSTR_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES));             \
+        CUSTR_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        LAUNCH(kfn, blocks, THREADS, ITEM_SMEM_BYTES, cd, a);                                                            \
+    } while (0)
+    bool plain = true;  // no optional step, END only behind the last step
+    for (uint32_t s = 0; s < cd.nsteps; ++s) plain = plain && !cd.steps[s].opt && ((cd.steps[s].exit != 0) == (s + 1 == cd.nsteps));
+    if (!plain) {
+        if (cd.nclasses <= 1) ITEM_LAUNCH((k_chain_item<NS, 1, 5>));
+        else if (cd.nclasses == 2) ITEM_LAUNCH((k_chain_item<NS, 2, 5>));
+        else if (cd.nclasses <= 4) ITEM_LAUNCH((k_chain_item<NS, 4, 5>));
+        else ITEM_LAUNCH((k_chain_item<NS, 8, 5>));
+        return;
+    }
+    if constexpr (NS <= 4) {
+        const int spec = g_no_spec ? 0 : chain_spec_of(cd);
+        if (spec == 1) { ITEM_LAUNCH((k_chain_item<NS, 1, 1>)); return; }
+        if (spec == 2) { ITEM_LAUNCH((k_chain_item<NS, 1, 2>)); return; }
+        if (spec == 3) { ITEM_LAUNCH((k_chain_item<NS, 1, 3>)); return; }
+        if (spec == 4) { ITEM_LAUNCH((k_chain_item<NS, 1, 4>)); return; }
+        if (spec == 6) { ITEM_LAUNCH((k_chain_item<NS, 1, 6>)); return; }
+        if (spec == 7) { ITEM_LAUNCH((k_chain_item<NS, 1, 7>)); return; }
+    }
+    if (cd.nclasses <= 1) ITEM_LAUNCH((k_chain_item<NS, 1, 0>));
+    else if (cd.nclasses == 2) ITEM_LAUNCH((k_chain_item<NS, 2, 0>));
+    else if (cd.nclasses <= 4) ITEM_LAUNCH((k_chain_item<NS, 4, 0>));
+    else ITEM_LAUNCH((k_chain_item<NS, 8, 0>));
+#undef ITEM_LAUNCH
+}
+#else
+template <int NS>
+static void launch_item_ns(const ChainDev&, const Args&, int) {}
+#endif

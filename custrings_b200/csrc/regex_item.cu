@@ -1,0 +1,35 @@
+// Item-buffered chain kernel (regex_chain_item.cuh), compiled in four translation units (-DITEM_NS_GROUP=0..3: chains of
+// 1-2, 3-4, 5-6, 7-8 steps) so that the instantiations build in parallel.  Host entry: launch_chain_item() in regex_bits.cu.
+#include "regex_bits.h"
+#include "regex_bits_plan.h"
+#include "regex_vm.cuh"
+#include <cstddef>
+
+#ifndef ITEM_NS_GROUP
+#define ITEM_NS_GROUP 0
+#endif
+
+namespace custr {
+namespace bits {
+
+#include "regex_bits_dev.cuh"
+#define CUSTR_NO_LAUNCHERS
+#include "regex_chain.cuh"
+#include "regex_chain64.cuh"
+#include "regex_chain_item.cuh"
+
+#define ITEM_ENTRY_NAME2(g) launch_chain_item_g##g
+#define ITEM_ENTRY_NAME(g) ITEM_ENTRY_NAME2(g)
+void ITEM_ENTRY_NAME(ITEM_NS_GROUP)(const ChainDev& cd, const Args& a, int blocks)
+{
+#ifdef ITEM_EXPERIMENT  // quick SASS iteration on the headline instantiation (tools/sass_stat.sh)
+    auto kfn = k_chain_item<4, 1, ITEM_EXPERIMENT>;
+    LAUNCH(kfn, blocks, THREADS, ITEM_SMEM_BYTES, cd, a);
+    return;
+#endif
+    if ((int)cd.nsteps <= 2 * ITEM_NS_GROUP + 1) launch_item_ns<2 * ITEM_NS_GROUP + 1>(cd, a, blocks);
+    else launch_item_ns<2 * ITEM_NS_GROUP + 2>(cd, a, blocks);
+}
+
+}  // namespace bits
+}  // namespace custr
