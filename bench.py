@@ -1,21 +1,31 @@
 #!/usr/bin/env python3
 """bench.py — BASELINE.json's headline metric: contains_re(r'\\b\\w{4,}\\b') over the C2 corpus
-(10 M strings / 1 GiB chars per GPU), strings/s.
+(10 M strings / 1 GiB chars per GPU), strings/s — plus the other BASELINE.json configs as `secondary`.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--rows R --bytes B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--rows R --bytes B] [--no-secondary]
 
 * a "step" is one contains_re call over one device-resident column shard (device bool results).
 * N > 1: launched by torchrun, one rank per GPU; every rank owns an independent 10 M-row shard (row sharding,
   no data-path collective => "weak" scaling); the timed region is bracketed by barrier + synchronize and the
-  reported time is the MAX over ranks (all_reduce MAX over NCCL).
+  reported time is the MAX over ranks (all_reduce MAX over NCCL).  `strong` in the same line: the SAME 10 M rows
+  split N ways (what BASELINE.json's "10M strings at 1/2/4/8 B200" literally says).
 * `value`  : whole-job strings/s with inputs resident in HBM (CUDA events).
 * `e2e`    : same metric through the public API from HOST buffers: nvstrings.from_offsets(pinned host) ->
-             contains(devptr) -> device->host copy of the bool results, all inside the timed region.
+             contains(devptr) -> device->host copy of the bool results, all inside the timed region; `h2d_only_ms` is
+             the same host->device copies alone (the PCIe / host-memory ceiling of that path on this box).
 * `roofline`: the dominant kernel's algorithmic bytes (chars + offsets + validity + results) over its
              average device time measured with CUDA events on the launch stream (custr_set_profiling), against the
              measured HBM copy peak in MEASURED_PEAKS.json.
 * `cpu_baseline`: the reference's own CPU build (oracle/_ref) on a bounded sample, 1 thread, rank 0, N=1 only.
-* `--impl reference`: the reference's CPU implementation on all host threads over bounded samples per step.
+* `reference_gpu`: the UNMODIFIED reference CUDA sources built for sm_100 (baseline/_ref, baseline/Makefile) on the same
+             device and column: NVStrings::contains_re by CUDA events, create_from_offsets(devmem=true) excluded.
+* `pandas_cpu`: pandas .str.contains on the box's host, single process (pandas is single-threaded), bounded sample.
+* `secondary`: C3 (replace_re on C2; README split + 7-step replace chain), C4 (nvcategory.from_strings, key exchange over
+             NCCL timed separately when N > 1), C5 (nvtext.tokenize on tweets + utf8 lines), C1 (split(',') on
+             985-rows.csv): ms by CUDA events, algorithmic bytes, roofline fraction, oracle rate and an oracle parity bit
+             on a sample each.
+* `--impl reference`: the reference's CPU implementation on all host threads: persistent worker processes, columns
+             built before the timer, the full column per step.
 """
 import argparse
 import json
@@ -32,6 +42,9 @@ sys.path.insert(0, ROOT)
 
 PATTERN = r"\b\w{4,}\b"
 METRIC = "contains_re strings/sec (10M strings, 1 GiB chars per GPU)"
+# rows of c2_corpus(10 M, 1 GiB, seed 20240917) that match PATTERN, as counted by the UNMODIFIED reference built for the
+# GPU (profiles/r2_reference_gpu_build_c2.jsonl) and by the CPU oracle over the full column (tests/test_gpu_scale.py)
+EXPECTED_MATCHES = {(10_000_000, 1 << 30, 20240917): 5002107}
 
 
 def algorithmic_bytes(n_rows, n_chars):
@@ -95,37 +108,61 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def reference_rate(chars, offsets, validity, rows, procs):
-    """strings/s of the reference CPU build (oracle/_ref) over the first `rows` rows with `procs` processes."""
-    from custrings_b200.workloads import slice_rows
-    import multiprocessing as mp
-    bounds = [rows * i // procs for i in range(procs + 1)]
-    shards = [slice_rows(chars, offsets, validity, bounds[i], bounds[i + 1]) for i in range(procs)]
-    if procs == 1:
-        t0 = time.perf_counter()
-        _ref_worker(shards[0])
-        return rows / (time.perf_counter() - t0)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(procs) as pool:
-        pool.map(_ref_touch, range(procs))  # load the .so in every worker before timing
-        t0 = time.perf_counter()
-        pool.map(_ref_worker, shards)
-        dt = time.perf_counter() - t0
-    return rows / dt
+# ---- reference CPU arm: persistent workers, columns built once, one "go" per step ---------------------------------------
+_SHARDS = None  # set in the parent before forking: list of (chars, offsets, validity, nulls); inherited copy-on-write
 
 
-def _ref_touch(_):
+def _ref_worker_main(idx, conn):
     from oracle import ref
-    ref.lib()
-    return 0
+    c, o, v, nulls = _SHARDS[idx]
+    col = ref.RefStrings.from_arrays(c, o, v, nulls)  # built once, outside every timed region
+    conn.send(("ready", col.size()))
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            break
+        _, cnt = col.contains_re(msg)
+        conn.send(int(cnt))
+    conn.close()
 
 
-def _ref_worker(shard):
-    from oracle import ref
-    c, o, v, nulls = shard
-    col = ref.RefStrings.from_arrays(c, o, v, nulls)
-    _, cnt = col.contains_re(PATTERN)
-    return cnt
+class RefPool:
+    """`procs` forked workers, each holding the reference CPU build's NVStrings over one contiguous row range."""
+
+    def __init__(self, chars, offsets, validity, rows, procs):
+        global _SHARDS
+        import multiprocessing as mp
+        from custrings_b200.workloads import slice_rows
+        from oracle import ref
+        ref.lib()  # the parent maps the oracle library too (the workers inherit the mapping)
+        bounds = [rows * i // procs for i in range(procs + 1)]
+        _SHARDS = [slice_rows(chars, offsets, validity, bounds[i], bounds[i + 1]) for i in range(procs)]
+        ctx = mp.get_context("fork")
+        self.conns, self.procs = [], []
+        for i in range(procs):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_ref_worker_main, args=(i, b), daemon=True)
+            p.start()
+            b.close()
+            self.conns.append(a)
+            self.procs.append(p)
+        for c in self.conns:
+            assert c.recv()[0] == "ready"
+        self.rows = rows
+
+    def step(self, pattern=PATTERN):
+        for c in self.conns:
+            c.send(pattern)
+        return sum(c.recv() for c in self.conns)
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send(None)
+            except Exception:
+                pass
+        for p in self.procs:
+            p.join(timeout=5)
 
 
 def run_reference(args, rank, world):
@@ -137,25 +174,223 @@ def run_reference(args, rank, world):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_oracle.so not built"}))
         return
     cores = os.cpu_count() or 1
-    sample_rows = min(args.rows, max(200_000, 150_000 * cores))
-    chars, offsets, validity, nulls = c2_corpus(sample_rows, int(sample_rows * (args.bytes / args.rows)), seed=20240917)
+    chars, offsets, validity, nulls = c2_corpus(args.rows, args.bytes, seed=20240917)
+    pool = RefPool(chars, offsets, validity, args.rows, cores)
+    matches = 0
     for _ in range(args.warmup):
-        reference_rate(chars, offsets, validity, min(sample_rows, 20_000 * cores), cores)
+        matches = pool.step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        reference_rate(chars, offsets, validity, sample_rows, cores)
+        matches = pool.step()
     dt = time.perf_counter() - t0
-    value = sample_rows * args.steps / dt
-    sample = "first %d rows (%d chars) of the C2 generator per step, %d processes" % (sample_rows, offsets[-1], cores)
+    pool.close()
+    value = args.rows * args.steps / dt
+    sample = "the full column per step (%d rows, %d chars), %d persistent processes, columns built before the timer" % (args.rows, offsets[-1], cores)
+    expected = EXPECTED_MATCHES.get((args.rows, args.bytes, 20240917))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "strings/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C2 contains_re(\\b\\w{4,}\\b), reference CPU build, bounded sample", "pattern": PATTERN,
-                   "rows_per_step": sample_rows},
+        "config": {"workload": "C2 contains_re(\\b\\w{4,}\\b) over %d strings / %d chars, reference CPU build" % (args.rows, int(offsets[-1])),
+                   "pattern": PATTERN, "rows_per_gpu": args.rows, "chars_per_gpu": int(offsets[-1]), "matches_rank0": int(matches),
+                   "matches_verified": (int(matches) == expected) if expected else None},
         "cpu_baseline": {"value": value, "unit": "strings/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "strings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ---- helpers -------------------------------------------------------------------------------------------------------------
+def timed_ms(fn, reps=5, warmup=1):
+    """median / min device time of fn() in ms (CUDA events on the current stream = the library's stream)"""
+    import torch
+    for _ in range(warmup):
+        r = fn()
+        del r
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+        del r
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def col_bytes(col):
+    """(chars, rows) of an nvstrings"""
+    from custrings_b200._lib import lib
+    return int(lib().custr_chars_bytes(col.m_cptr)), col.size()
+
+
+def col_io_bytes(col):
+    """bytes of the Arrow triple of a column: chars + offsets + validity"""
+    c, n = col_bytes(col)
+    return c + 4 * (n + 1) + (n + 7) // 8
+
+
+def roof(alg_bytes, ms, peak):
+    gbs = alg_bytes / (ms / 1e3) / 1e9
+    return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak}
+
+
+def oracle_rate(make_ref, run, rows):
+    """rows/s of the reference CPU build (1 thread) for `run(ref_col)` over a column of `rows` rows"""
+    col = make_ref()
+    t0 = time.perf_counter()
+    out = run(col)
+    dt = time.perf_counter() - t0
+    return out, {"value": rows / dt, "unit": "rows/s", "cores": 1, "kind": "reference", "sample": "%d rows, reference CPU build (oracle/_ref), 1 thread" % rows}
+
+
+def secondary_workloads(args, rank, world, peak, reduce_max):
+    """The other BASELINE.json configs.  Every rank runs its shard; times are the max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from custrings_b200 import nvstrings, nvcategory, nvtext, workloads as W
+    try:
+        from oracle import ref
+        have_ref = ref.available() and rank == 0
+    except Exception:
+        ref, have_ref = None, False
+    out = []
+
+    def entry(name, ms, alg, rows, extra=None):
+        ms = reduce_max(ms)
+        e = {"workload": name, "ms": ms, "rows_per_gpu": rows, "algorithmic_bytes": alg, "roofline": roof(alg, ms, peak),
+             "rows_per_s": world * rows / (ms / 1e3)}
+        if extra:
+            e.update(extra)
+        out.append(e)
+        return e
+
+    # ---- C3b: replace_re(\b\w{4,}\b, '#') over the C2 shard (input B of SURVEY §8d C3)
+    chars, offsets, validity, nulls = args._c2
+    n = args.rows
+    col = nvstrings.from_offsets(chars, offsets, n, validity, nulls)
+    res = col.replace(PATTERN, "#")
+    alg = col_io_bytes(col) + col_io_bytes(res)
+    del res
+    ms, _ = timed_ms(lambda: col.replace(PATTERN, "#"), reps=5)
+    e = entry("C3 replace_re(\\b\\w{4,}\\b,'#') over the C2 shard", ms, alg, n)
+    if have_ref:
+        m = 100_000
+        c, o, v, nn = W.slice_rows(chars, offsets, validity, 0, m)
+        want, e["cpu_baseline"] = oracle_rate(lambda: ref.RefStrings.from_arrays(c, o, v, nn), lambda r: r.replace_re(PATTERN, "#").to_arrays(), m)
+        got = nvstrings.from_offsets(c, o, m, v, nn).replace(PATTERN, "#").to_arrays()
+        e["parity"] = all(np.array_equal(a, b) for a, b in zip(got, want))
+    del col
+
+    # ---- C3a: README chain — split(',') -> column 4 -> 7 x replace(day, str(i)) (regex=True => replace_re)
+    n3 = args.rows
+    c3, o3 = W.c3_readme_rows(n3, seed=7 + rank)
+    col = nvstrings.from_offsets(c3, o3, n3)
+    cols = col.split(",")
+    day = cols[4]
+    alg_split = col_io_bytes(col) + sum(col_io_bytes(c) for c in cols)
+    alg_chain = 0
+    d = day
+    for i, name in enumerate(W.DAYS):
+        nd = d.replace(name, str(i))
+        alg_chain += col_io_bytes(d) + col_io_bytes(nd)
+        d = nd
+    del cols, d, nd
+
+    def chain():
+        d = day
+        for i, name in enumerate(W.DAYS):
+            d = d.replace(name, str(i))
+        return d
+
+    ms_split, _ = timed_ms(lambda: col.split(","), reps=3)
+    ms_chain, _ = timed_ms(chain, reps=5)
+    e = entry("C3 README chain: 7 x replace(day, str(i)) over split(',')[4] of %d rows" % n3, ms_chain, alg_chain, n3,
+              {"split_ms": reduce_max(ms_split), "split_algorithmic_bytes": alg_split, "split_roofline": roof(alg_split, reduce_max(ms_split), peak)})
+    if have_ref:
+        m = 100_000
+        sub_c, sub_o = c3[: int(o3[m])], o3[: m + 1]
+
+        def ref_chain(r):
+            d = r.split(",")[4]
+            for i, name in enumerate(W.DAYS):
+                d = d.replace_re(name, str(i))
+            return d.to_arrays()
+
+        want, e["cpu_baseline"] = oracle_rate(lambda: ref.RefStrings.from_arrays(sub_c, sub_o), ref_chain, m)
+        d = nvstrings.from_offsets(sub_c, sub_o, m).split(",")[4]
+        for i, name in enumerate(W.DAYS):
+            d = d.replace(name, str(i))
+        e["parity"] = all(np.array_equal(a, b) for a, b in zip(d.to_arrays(), want))
+    del col, day
+
+    # ---- C4: nvcategory.from_strings, 12.5 M rows per GPU / 1000 distinct keys (100 M rows over 8 GPUs)
+    n4 = 12_500_000 if args.rows == 10_000_000 else max(1000, args.rows + args.rows // 4)
+    c4, o4, keys, idx = W.c4_category_rows(n4, 1000, seed=11, rank=rank)
+    col = nvstrings.from_offsets(c4, o4, n4)
+    alg = len(c4) + 4 * (n4 + 1) + 4 * n4
+    ms, _ = timed_ms(lambda: nvcategory.from_strings(col), reps=5)
+    extra = {}
+    if world > 1:
+        t = nvcategory.from_strings_sharded(col, timings=True)[1]  # warm-up of the communicator
+        ts = [nvcategory.from_strings_sharded(col, timings=True)[1] for _ in range(3)]
+        extra = {"sharded_build_ms": reduce_max(float(np.median([x["build_ms"] for x in ts]))),
+                 "key_exchange_ms": reduce_max(float(np.median([x["exchange_ms"] for x in ts]))),
+                 "remap_ms": reduce_max(float(np.median([x["remap_ms"] for x in ts]))),
+                 "exchange": ts[0]["how"]}
+    e = entry("C4 nvcategory.from_strings: %d rows per GPU, 1000 distinct keys" % n4, ms, alg, n4, extra)
+    cat = nvcategory.from_strings_sharded(col) if world > 1 else nvcategory.from_strings(col)
+    # invariants on the full shard: keys == the sorted key set, values == the drawn key index
+    vals = torch.empty(n4, dtype=torch.int32, device="cuda")
+    cat.values(devptr=vals.data_ptr())
+    e["parity"] = bool(cat.keys().to_host() == [k.decode() for k in keys] and np.array_equal(vals.cpu().numpy(), idx.astype(np.int32)))
+    if have_ref:
+        m = 200_000
+        want, e["cpu_baseline"] = oracle_rate(lambda: ref.RefStrings.from_arrays(c4[: int(o4[m])], o4[: m + 1]),
+                                              lambda r: ref.RefCategory(r).values(), m)
+        got = nvcategory.from_strings(nvstrings.from_offsets(c4[: int(o4[m])], o4[: m + 1], m))
+        e["parity"] = e["parity"] and bool(np.array_equal(np.array(got.values(), np.int32), np.asarray(want, np.int32)))
+    del col, cat, vals
+
+    # ---- C5: nvtext.tokenize (whitespace) on tweets.csv `text` + one utf8.csv line per 8 tweets, tiled to 512 MiB per GPU
+    total5 = (512 << 20) if args.bytes == (1 << 30) else args.bytes // 2
+    c5, o5, n5 = W.c5_corpus(total5)
+    col = nvstrings.from_offsets(c5, o5, n5)
+    tok = nvtext.tokenize(col)
+    tchars, ntok = col_bytes(tok)
+    alg = len(c5) + 4 * (n5 + 1) + tchars + 4 * (ntok + 1)
+    del tok
+    ms, _ = timed_ms(lambda: nvtext.tokenize(col), reps=5)
+    e = entry("C5 nvtext.tokenize(whitespace): tweets.csv text + 1 utf8.csv line per 8 rows, tiled to %d chars per GPU" % len(c5), ms, alg, n5,
+              {"tokens_per_gpu": ntok, "non_ascii_bytes": int((c5 >= 0x80).sum())})
+    if have_ref:
+        m = 100_000
+        want, e["cpu_baseline"] = oracle_rate(lambda: ref.RefStrings.from_arrays(c5[: int(o5[m])], o5[: m + 1]), lambda r: r.tokenize().to_arrays(), m)
+        got = nvtext.tokenize(nvstrings.from_offsets(c5[: int(o5[m])], o5[: m + 1], m)).to_arrays()
+        e["parity"] = all(np.array_equal(a, b) for a, b in zip(got, want))
+    del col
+
+    # ---- C1: split(',') on data/985-rows.csv (plumbing; pandas .str.split as the CPU reference)
+    lines = W.c1_lines()
+    col = nvstrings.to_device([l.decode("utf-8", "replace") for l in lines])
+    ms, _ = timed_ms(lambda: col.split(","), reps=5)
+    cols = col.split(",")
+    alg = col_io_bytes(col) + sum(col_io_bytes(c) for c in cols)
+    e = entry("C1 split(',') on data/985-rows.csv (%d lines)" % len(lines), ms, alg, len(lines), {"columns": len(cols)})
+    if rank == 0:
+        import pandas as pd
+        t0 = time.perf_counter()
+        exp = pd.Series([l.decode("utf-8", "replace") for l in lines]).str.split(",", expand=True)
+        e["pandas_ms"] = 1e3 * (time.perf_counter() - t0)
+        got = [c.to_host() for c in cols]
+        e["parity_pandas"] = bool(len(cols) == exp.shape[1] and all(got[k] == [None if v is None or v != v else v for v in exp[k].tolist()] for k in range(len(cols))))
+    if have_ref:
+        want, e["cpu_baseline"] = oracle_rate(lambda: ref.RefStrings.from_list([l.decode("utf-8", "replace") for l in lines]),
+                                              lambda r: [c.to_list() for c in r.split(",")], len(lines))
+        e["parity"] = bool([[None if v is None else v.decode() for v in c] for c in want] == [c.to_host() for c in cols])
+    return out
 
 
 def main():
@@ -169,6 +404,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--tier", type=int, default=0, help="0 auto, 1 force the exact Pike VM")
+    ap.add_argument("--no-secondary", action="store_true", help="only the headline workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -182,7 +418,7 @@ def main():
     import torch.distributed as dist
     from custrings_b200 import nvstrings
     from custrings_b200._lib import lib
-    from custrings_b200.workloads import c2_corpus
+    from custrings_b200.workloads import c2_corpus, slice_rows
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (custrings_b200 has no CPU fallback)")
@@ -208,10 +444,23 @@ def main():
     L.custr_set_stream(torch.cuda.current_stream().cuda_stream)
     L.custr_set_regex_tier(args.tier)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- synthetic shard of this rank (different seed per rank: independent rows, same distribution)
     t_gen = time.perf_counter()
     chars, offsets, validity, nulls = c2_corpus(args.rows, args.bytes, seed=20240917 + rank)
     t_gen = time.perf_counter() - t_gen
+    args._c2 = (chars, offsets, validity, nulls)
     n = args.rows
     h_chars = torch.from_numpy(chars).pin_memory()
     h_off = torch.from_numpy(offsets).pin_memory()
@@ -224,15 +473,13 @@ def main():
     def step():
         return L.custr_contains_re(col.m_cptr, PATTERN.encode(), d_res.data_ptr(), 1)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # clocks / throttle reasons are sampled from the warm-up on, through the device-resident timed region and the
     # end-to-end region (a single nvidia-smi query takes longer than the 20-step timed region itself)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_first = time.perf_counter()
+    matches = step()  # includes the host regex compile + program upload + the column's work-item index
+    t_first = time.perf_counter() - t_first
     for _ in range(args.warmup):
         matches = step()
     tier = L.custr_last_regex_tier().decode()
@@ -269,29 +516,88 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_matches = int(h_res.sum().item())
+    # the same host->device copies alone: what PCIe / host memory allow on this box with every rank copying at once
+    d_chars = torch.empty_like(h_chars, device="cuda")
+    d_off = torch.empty_like(h_off, device="cuda")
+    d_val = torch.empty_like(h_val, device="cuda")
+
+    def h2d_only():
+        d_chars.copy_(h_chars, non_blocking=True)
+        d_off.copy_(h_off, non_blocking=True)
+        d_val.copy_(h_val, non_blocking=True)
+        h_res.copy_(d_res, non_blocking=True)
+        torch.cuda.synchronize()
+
+    h2d_only()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        h2d_only()
+    barrier()
+    h2d_s = time.perf_counter() - t0
+    del d_chars, d_off, d_val
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    times = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    elapsed_ms, e2e_ms, h2d_ms = reduce_max(elapsed_ms), reduce_max(e2e_s * 1e3), reduce_max(h2d_s * 1e3)
+
+    # ---- strong scaling: the SAME 10 M rows (seed 20240917) split N ways
+    strong = None
     if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms = times.tolist()
+        base = (chars, offsets, validity, nulls) if rank == 0 else c2_corpus(args.rows, args.bytes, seed=20240917)
+        lo, hi = n * rank // world, n * (rank + 1) // world
+        sc, so, sv, sn = slice_rows(base[0], base[1], base[2], lo, hi)
+        scol = nvstrings.from_offsets(sc, so, hi - lo, sv, sn)
+        s_res = torch.empty(hi - lo, dtype=torch.uint8, device="cuda")
+        for _ in range(args.warmup):
+            sm_ = L.custr_contains_re(scol.m_cptr, PATTERN.encode(), s_res.data_ptr(), 1)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            L.custr_contains_re(scol.m_cptr, PATTERN.encode(), s_res.data_ptr(), 1)
+        ev1.record()
+        barrier()
+        s_ms = reduce_max(ev0.elapsed_time(ev1))
+        tot = torch.tensor([float(sm_)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot)
+        strong = {"value": n * args.steps / (s_ms / 1e3), "unit": "strings/s", "ms_per_step": s_ms / args.steps, "rows_total": n,
+                  "rows_per_gpu": n // world, "matches_total": int(tot.item()),
+                  "matches_verified": EXPECTED_MATCHES.get((args.rows, args.bytes, 20240917)) == int(tot.item()),
+                  "note": "per-call fixed cost (launch, counter reset, match-count readback) does not shrink with the shard"}
+        del scol, s_res, base
+
+    peak, peak_src = hbm_peak()
+    secondary = None
+    if not args.no_secondary:
+        del col
+        col = None
+        try:
+            secondary = secondary_workloads(args, rank, world, peak, reduce_max)
+        except Exception as e:  # the secondary workloads must never take the headline line down
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            secondary = [{"workload": "secondary workloads failed", "error": "%s: %s" % (type(e).__name__, e)}]
+            if world > 1:
+                raise
 
     if rank == 0:
         value = world * n * args.steps / (elapsed_ms / 1e3)
         e2e_value = world * n * args.e2e_steps / (e2e_ms / 1e3)
-        peak, peak_src = hbm_peak()
         k_ms = float(np.mean(kernel_ms))
         alg = algorithmic_bytes(n, int(offsets[-1]))
         achieved = alg / (k_ms / 1e3) / 1e9
+        expected = EXPECTED_MATCHES.get((args.rows, args.bytes, 20240917))
+        if expected is not None and int(matches) != expected:
+            raise SystemExit("bench.py: contains_re found %d matching rows on rank 0, the reference finds %d" % (matches, expected))
         traffic = None
-        try:  # dram read+write of the dominant kernel from the committed ncu --set full capture (same workload)
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        try:  # dram read+write of the dominant kernel from the committed ncu --set full capture (same workload); NOT measured in this run
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
                 tj = json.load(f)
             if tier == "bitstream" and args.rows == 10_000_000 and args.bytes == 1 << 30:
                 traffic = tj["traffic"]
         except Exception:
             pass
+        h2d_bytes = int(chars.nbytes + offsets.nbytes + validity.nbytes)
         line = {
             "metric": METRIC, "value": value, "unit": "strings/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -299,27 +605,72 @@ def main():
             "config": {"workload": "C2 contains_re(\\b\\w{4,}\\b) over %d strings / %d chars per GPU" % (n, int(offsets[-1])),
                        "pattern": PATTERN, "rows_per_gpu": n, "chars_per_gpu": int(offsets[-1]), "sharding": "contiguous row ranges, no collective",
                        "l2": "inputs (1 GiB) larger than the 126 MB L2, no flush needed", "regex_tier": tier,
-                       "matches_rank0": int(matches), "datagen_s": round(t_gen, 1)},
-            "e2e": {"value": e2e_value, "unit": "strings/s", "h2d_bytes_per_step": int(chars.nbytes + offsets.nbytes + validity.nbytes),
-                    "d2h_bytes_per_step": int(n), "steps": args.e2e_steps, "matches_rank0": e2e_matches},
+                       "matches_rank0": int(matches), "matches_verified": (int(matches) == expected) if expected else None,
+                       "first_call_ms": 1e3 * t_first, "datagen_s": round(t_gen, 1)},
+            "e2e": {"value": e2e_value, "unit": "strings/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": int(n), "steps": args.e2e_steps, "matches_rank0": e2e_matches, "ms_per_step": e2e_ms / args.e2e_steps,
+                    "h2d_only_ms": h2d_ms / args.e2e_steps, "h2d_gbs_per_gpu": h2d_bytes / (h2d_ms / args.e2e_steps / 1e3) / 1e9},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": "profiles/r2_traffic.json (ncu --set full capture of the same workload, not this run)" if traffic else None,
                          "kernel_ms": k_ms, "algorithmic_bytes": alg, "peak_source": peak_src,
-                         "kernel": "bits::k_chain64<4,1,3> (+ memset, + k_vm_bool_rows for rows holding NUL)" if tier == "bitstream" else "k_vm_bool<32>"},
+                         "kernel": "bits::k_chain_item<4,1,3> (+ k_vm_bool_rows for rows holding NUL)" if tier == "bitstream" else "k_vm_bool<32>"},
             "clocks": sampler.summary(),
         }
+        if strong:
+            line["strong"] = strong
+        if secondary is not None:
+            line["secondary"] = secondary
         if world == 1:
             try:
                 from oracle import ref
                 if ref.available():
                     rows = min(args.cpu_sample_rows, n)
-                    rate = reference_rate(chars, offsets, validity, rows, 1)
+                    c, o, v, nn = slice_rows(chars, offsets, validity, 0, rows)
+                    rc = ref.RefStrings.from_arrays(c, o, v, nn)
+                    t0 = time.perf_counter()
+                    rc.contains_re(PATTERN)
+                    rate = rows / (time.perf_counter() - t0)
                     line["cpu_baseline"] = {"value": rate, "unit": "strings/s", "cores": 1, "kind": "reference",
-                                            "sample": "first %d rows of the same column, reference CPU build (oracle/_ref), 1 thread" % rows}
+                                            "sample": "first %d rows of the same column, reference CPU build (oracle/_ref), 1 thread, column built before the timer" % rows}
                 else:
                     line["cpu_baseline"] = {"value": None, "unit": "strings/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
             except Exception as e:  # the baseline must never break the bench line
                 line["cpu_baseline"] = {"value": None, "unit": "strings/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
+            try:  # the reference's own CUDA path on this GPU and this column
+                from baseline import ref_gpu
+                if ref_gpu.available():
+                    dc, do, dv = (torch.from_numpy(x).cuda() for x in (chars, offsets, validity))
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    rg = ref_gpu.RefGpuStrings.from_device(dc, do, n, dv, nulls)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    create_ms = e0.elapsed_time(e1)
+                    rmatches = rg.contains_re(PATTERN, d_res)
+                    med, best = timed_ms(lambda: rg.contains_re(PATTERN, d_res), reps=5, warmup=0)
+                    line["reference_gpu"] = {"value": n / (med / 1e3), "unit": "strings/s", "ms": med, "ms_best": best, "matches": int(rmatches),
+                                             "create_from_offsets_devmem_ms": create_ms,
+                                             "what": "unmodified reference CUDA sources built for sm_100 (baseline/Makefile; RMM shim = cudaMallocAsync), "
+                                                     "NVStrings::contains_re by CUDA events on this GPU, same column; create_from_offsets excluded"}
+                    rg.free()
+                    del dc, do, dv
+                else:
+                    line["reference_gpu"] = {"unavailable": "baseline/_ref/libref_gpu.so not built (make -C baseline)"}
+            except Exception as e:
+                line["reference_gpu"] = {"unavailable": "failed: %s" % e}
+            try:  # pandas .str on the host, single process
+                import pandas as pd
+                rows = min(1_000_000, n)
+                ser = pd.Series([bytes(chars[offsets[i]:offsets[i + 1]]).decode("utf-8") if (validity[i >> 3] >> (i & 7)) & 1 else None for i in range(rows)])
+                t0 = time.perf_counter()
+                hits = int(ser.str.contains(PATTERN, regex=True).fillna(False).sum())
+                dt = time.perf_counter() - t0
+                line["pandas_cpu"] = {"value": rows / dt, "unit": "strings/s", "cores": 1, "host_cores": os.cpu_count(), "hits": hits,
+                                      "sample": "pandas %s Series.str.contains(regex=True) on the first %d rows, single process; Python's re treats "
+                                                "'_' as a word character for \\b, so its hit count differs from the reference's on ~0.1 %% of rows" % (pd.__version__, rows)}
+            except Exception as e:
+                line["pandas_cpu"] = {"unavailable": "failed: %s" % e}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

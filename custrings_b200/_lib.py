@@ -23,11 +23,13 @@ _SIGNATURES = {
     "custr_launch_count": (cl, []),
     "custr_last_regex_tier": (cp, []),
     "custr_set_regex_tier": (None, [ci]),
+    "custr_set_item_kib": (None, [ci]),
     "custr_set_profiling": (None, [ci]),
     "custr_last_kernel_ms": (C.c_float, []),
     "custr_create_from_offsets": (vp, [vp, ci, vp, vp, ci, ci]),
     "custr_adopt_device": (vp, [vp, ci, vp, vp, ci]),
     "custr_create_from_array": (vp, [vp, cu]),
+    "custr_create_from_index": (vp, [vp, cu, ci, ci]),
     "custr_column_free": (None, [vp]),
     "custr_size": (cu, [vp]),
     "custr_chars_bytes": (cl, [vp]),
@@ -78,6 +80,10 @@ _SIGNATURES = {
     "custr_category_values_cptr": (vp, [vp]),
     "custr_category_remap_to_union": (vp, [vp, vp]),
     "custr_category_merge": (vp, [vp, ci, ci]),
+    "custr_comm_unique_id": (ci, [vp]),
+    "custr_comm_create": (vp, [ci, ci, vp]),
+    "custr_comm_destroy": (None, [vp]),
+    "custr_category_create_sharded": (vp, [vp, vp, vp]),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)

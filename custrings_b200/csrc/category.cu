@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "rowops.cuh"
 #include <cub/cub.cuh>
+#include <algorithm>
+#include <mutex>
 
 namespace custr {
 
@@ -224,6 +226,13 @@ __global__ void k_remap_values(const int32_t* __restrict__ in, const int32_t* __
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = map[in[i]];
+}
+
+// byte length of every key, -1 for the null key (payload of the sharded key exchange)
+__global__ void k_key_lengths(ColView keys, int32_t* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < keys.n) out[i] = keys.valid(i) ? keys.offsets[i + 1] - keys.offsets[i] : -1;
 }
 
 static inline int row_grid(int n)
@@ -483,13 +492,40 @@ custr_category* custr_category_merge(const custr_category* const* cats, int32_t 
                 const int32_t n1 = k1->n, n2 = k2->n;
                 maps[1] = dev_alloc(sizeof(int32_t) * (size_t)(n2 ? n2 : 1));
                 std::vector<int32_t> h_map((size_t)n2), fresh;
+                // k1 may itself be the result of a merge_category (keys appended, NOT sorted; its null key anywhere), so it is
+                // never binary-searched directly: the lookup goes through a sorted view of k1 (a category built over k1's keys:
+                // sorted distinct keys + values[i] = rank of k1[i]) and the rank is mapped back to k1's own index.
+                std::vector<int32_t> rank_to_k1;
+                std::unique_ptr<custr_category, void (*)(custr_category*)> sorted1(nullptr, [](custr_category* c) { custr_category_free(c); });
+                if (n1 && n2) {
+                    sorted1.reset(build_category(k1));
+                    std::vector<int32_t> rank((size_t)n1);
+                    CUSTR_CUDA(cudaMemcpyAsync(rank.data(), sorted1->values_buf->ptr, sizeof(int32_t) * (size_t)n1, cudaMemcpyDeviceToHost, g_stream));
+                    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+                    rank_to_k1.assign((size_t)sorted1->keys->n, -1);
+                    for (int32_t i = n1 - 1; i >= 0; --i) rank_to_k1[(size_t)rank[i]] = i;  // first occurrence wins
+                }
                 if (n2) {
-                    LAUNCH(k_lookup_keys, (n2 + 255) / 256, 256, 0, view_of(k2), view_of(k1), (int32_t*)maps[1]->ptr);
+                    if (sorted1) LAUNCH(k_lookup_keys, (n2 + 255) / 256, 256, 0, view_of(k2), view_of(sorted1->keys), (int32_t*)maps[1]->ptr);
+                    else CUSTR_CUDA(cudaMemsetAsync(maps[1]->ptr, 0xff, sizeof(int32_t) * (size_t)n2, g_stream));
                     CUSTR_CUDA(cudaMemcpyAsync(h_map.data(), maps[1]->ptr, sizeof(int32_t) * (size_t)n2, cudaMemcpyDeviceToHost, g_stream));
                     CUSTR_CUDA(cudaStreamSynchronize(g_stream));
                 }
-                for (int32_t i = 0; i < n2; ++i)   // key sets are small (dictionary entries, not rows): host bookkeeping
-                    if (h_map[i] < 0) { h_map[i] = n1 + (int32_t)fresh.size(); fresh.push_back(i); }
+                // the new keys are appended in SORTED order (the reference picks them out of the sorted keys2 + keys1 sequence,
+                // NVCategory.cu:1262-1290), which is k2's own order only while k2 is a freshly built, sorted key set
+                std::vector<int32_t> order2((size_t)n2);
+                for (int32_t i = 0; i < n2; ++i) order2[(size_t)i] = i;
+                if (n2 > 1) {
+                    std::unique_ptr<custr_category, void (*)(custr_category*)> sorted2(build_category(k2), [](custr_category* c) { custr_category_free(c); });
+                    std::vector<int32_t> rank2((size_t)n2);
+                    CUSTR_CUDA(cudaMemcpyAsync(rank2.data(), sorted2->values_buf->ptr, sizeof(int32_t) * (size_t)n2, cudaMemcpyDeviceToHost, g_stream));
+                    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+                    std::stable_sort(order2.begin(), order2.end(), [&](int32_t a, int32_t b) { return rank2[(size_t)a] < rank2[(size_t)b]; });
+                }
+                for (int32_t i : order2) {  // key sets are small (dictionary entries, not rows): host bookkeeping
+                    if (h_map[(size_t)i] >= 0) h_map[(size_t)i] = rank_to_k1[(size_t)h_map[(size_t)i]];
+                    else { h_map[(size_t)i] = n1 + (int32_t)fresh.size(); fresh.push_back(i); }
+                }
                 if (n2) CUSTR_CUDA(cudaMemcpyAsync(maps[1]->ptr, h_map.data(), sizeof(int32_t) * (size_t)n2, cudaMemcpyHostToDevice, g_stream));
                 std::unique_ptr<custr_column> added(custr_gather(k2, fresh.data(), (int32_t)fresh.size(), 0));
                 if (!added) throw ArgError{CUSTR_ERR_INVALID};
@@ -513,6 +549,178 @@ custr_category* custr_category_merge(const custr_category* const* cats, int32_t 
             out->has_null_key = out->keys->nulls > 0;
             CUSTR_CUDA(cudaStreamSynchronize(g_stream));
             return guard.release();
+        },
+        (custr_category*)nullptr, (custr_category*)nullptr);
+}
+
+// ---- multi-GPU: row-sharded dictionary build with the key exchange over NCCL ------------------------------
+// The only collective of the whole path.  NCCL is bound at run time (dlopen of libnccl.so.2: inside a torch process that is
+// the library torch already loaded, otherwise the system one), so libcustr.so itself has no hard dependency on it.
+}  // extern "C"
+#include <dlfcn.h>
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#else
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+typedef int ncclDataType_t;
+enum { ncclUint8 = 1, ncclInt32 = 2, ncclInt64 = 4 };
+#endif
+namespace {
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+const NcclApi& nccl()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+        api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather;
+    });
+    return api;
+}
+void nccl_check(ncclResult_t r, const char* what)
+{
+    if (r != 0) {
+        const NcclApi& a = nccl();
+        throw custr::ArgError{custr::fail(CUSTR_ERR_CUDA, std::string(what) + ": " + (a.GetErrorString ? a.GetErrorString(r) : "NCCL error"))};
+    }
+}
+}  // namespace
+struct custr_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+};
+extern "C" {
+
+int custr_comm_unique_id(void* id128)
+{
+    return guarded(
+        [&]() -> int {
+            if (!id128) return fail(CUSTR_ERR_ARG, "comm_unique_id: null argument");
+            if (!nccl().ok) return fail(CUSTR_ERR_CUDA, "NCCL library (libnccl.so.2) not found");
+            ncclUniqueId id;
+            nccl_check(nccl().GetUniqueId(&id), "ncclGetUniqueId");
+            memcpy(id128, &id, sizeof(id));
+            return CUSTR_OK;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
+custr_comm* custr_comm_create(int rank, int world, const void* id128)
+{
+    return guarded(
+        [&]() -> custr_comm* {
+            if (!id128 || world < 1 || rank < 0 || rank >= world) throw ArgError{fail(CUSTR_ERR_ARG, "comm_create: bad argument")};
+            if (!nccl().ok) throw ArgError{fail(CUSTR_ERR_CUDA, "NCCL library (libnccl.so.2) not found")};
+            ncclUniqueId id;
+            memcpy(&id, id128, sizeof(id));
+            std::unique_ptr<custr_comm> c(new custr_comm);
+            c->rank = rank;
+            c->world = world;
+            nccl_check(nccl().CommInitRank(&c->comm, world, id, rank), "ncclCommInitRank");
+            return c.release();
+        },
+        (custr_comm*)nullptr, (custr_comm*)nullptr);
+}
+
+void custr_comm_destroy(custr_comm* c)
+{
+    if (!c) return;
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    delete c;
+}
+
+// Every rank: dictionary of its own rows -> all-gather of (key count, key bytes), then of the max-padded key lengths and key
+// bytes (two ncclAllGather over NVLink; K keys x ~16 B per rank: latency-bound) -> union column of every rank's keys -> global
+// sorted key set + remap of the local values (create_from_categories math, NVCategory.cu:430-514).  Every rank returns the
+// same keys; values index into them.  timings_ms (optional, 3 floats): local build, key exchange, union + remap.
+custr_category* custr_category_create_sharded(custr_comm* comm, const custr_column* col, float* timings_ms)
+{
+    return guarded(
+        [&]() -> custr_category* {
+            if (!comm || !col) throw ArgError{fail(CUSTR_ERR_ARG, "category_create_sharded: null argument")};
+            cudaEvent_t ev[4];
+            for (auto& e : ev) CUSTR_CUDA(cudaEventCreate(&e));
+            struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); } } evg{ev};
+            CUSTR_CUDA(cudaEventRecord(ev[0], g_stream));
+            std::unique_ptr<custr_category, void (*)(custr_category*)> local(build_category(col), [](custr_category* c) { custr_category_free(c); });
+            CUSTR_CUDA(cudaEventRecord(ev[1], g_stream));
+            const int world = comm->world;
+            const custr_column* lk = local->keys;
+            const int32_t k = lk->n;
+            // (1) sizes
+            long long h_meta[2] = {k, lk->nbytes};
+            Scratch<long long> d_meta(2), d_metas(2 * (size_t)world);
+            CUSTR_CUDA(cudaMemcpyAsync(d_meta.get(), h_meta, sizeof(h_meta), cudaMemcpyHostToDevice, g_stream));
+            nccl_check(nccl().AllGather(d_meta.get(), d_metas.get(), 2, ncclInt64, comm->comm, g_stream), "ncclAllGather(sizes)");
+            std::vector<long long> metas(2 * (size_t)world);
+            CUSTR_CUDA(cudaMemcpyAsync(metas.data(), d_metas.get(), sizeof(long long) * metas.size(), cudaMemcpyDeviceToHost, g_stream));
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            long long max_k = 1, max_b = 1, tot_k = 0, tot_b = 0;
+            for (int r = 0; r < world; ++r) {
+                max_k = std::max(max_k, metas[2 * r]);
+                max_b = std::max(max_b, metas[2 * r + 1]);
+                tot_k += metas[2 * r];
+                tot_b += metas[2 * r + 1];
+            }
+            if (tot_b > 0x7fffffffLL || tot_k > 0x7fffffffLL) throw ArgError{fail(CUSTR_ERR_INVALID, "category_create_sharded: key union exceeds 2 GiB")};
+            // (2) payload: lengths (-1 = the null key) and key bytes, max-padded
+            Scratch<int32_t> d_len((size_t)max_k), d_lens((size_t)max_k * world);
+            Scratch<uint8_t> d_chr((size_t)max_b), d_chrs((size_t)max_b * world);
+            if (k) LAUNCH(k_key_lengths, (k + 255) / 256, 256, 0, view_of(lk), (int32_t*)d_len.get());
+            if (lk->nbytes) CUSTR_CUDA(cudaMemcpyAsync(d_chr.get(), lk->chars + lk->first_off, (size_t)lk->nbytes, cudaMemcpyDeviceToDevice, g_stream));
+            nccl_check(nccl().AllGather(d_len.get(), d_lens.get(), (size_t)max_k, ncclInt32, comm->comm, g_stream), "ncclAllGather(key lengths)");
+            nccl_check(nccl().AllGather(d_chr.get(), d_chrs.get(), (size_t)max_b, ncclUint8, comm->comm, g_stream), "ncclAllGather(key bytes)");
+            std::vector<int32_t> lens((size_t)max_k * world);
+            std::vector<uint8_t> chrs((size_t)max_b * world);
+            CUSTR_CUDA(cudaMemcpyAsync(lens.data(), d_lens.get(), sizeof(int32_t) * lens.size(), cudaMemcpyDeviceToHost, g_stream));
+            CUSTR_CUDA(cudaMemcpyAsync(chrs.data(), d_chrs.get(), chrs.size(), cudaMemcpyDeviceToHost, g_stream));
+            CUSTR_CUDA(cudaEventRecord(ev[2], g_stream));
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            // (3) union column of every rank's keys in rank order (a few thousand dictionary entries: host bookkeeping)
+            std::vector<char> all_chars((size_t)(tot_b ? tot_b : 1));
+            std::vector<int32_t> all_off((size_t)tot_k + 1, 0);
+            std::vector<uint8_t> all_valid((size_t)(tot_k + 7) / 8 + 1, 0);
+            size_t row = 0, pos = 0;
+            int nulls = 0;
+            for (int r = 0; r < world; ++r) {
+                size_t src = 0;
+                for (long long i = 0; i < metas[2 * r]; ++i, ++row) {
+                    const int32_t len = lens[(size_t)r * max_k + i];
+                    if (len < 0) ++nulls;
+                    else {
+                        all_valid[row >> 3] |= (uint8_t)(1u << (row & 7));
+                        memcpy(all_chars.data() + pos, chrs.data() + (size_t)r * max_b + src, (size_t)len);
+                        pos += (size_t)len;
+                        src += (size_t)len;
+                    }
+                    all_off[row + 1] = (int32_t)pos;
+                }
+            }
+            std::unique_ptr<custr_column> all_keys(custr_create_from_offsets(all_chars.data(), (int32_t)tot_k, all_off.data(), all_valid.data(), nulls, 0));
+            if (!all_keys) throw ArgError{CUSTR_ERR_INVALID};
+            custr_category* out = custr_category_remap_to_union(local.get(), all_keys.get());
+            if (!out) throw ArgError{CUSTR_ERR_INVALID};
+            CUSTR_CUDA(cudaEventRecord(ev[3], g_stream));
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            if (timings_ms)
+                for (int i = 0; i < 3; ++i) CUSTR_CUDA(cudaEventElapsedTime(&timings_ms[i], ev[i], ev[i + 1]));
+            return out;
         },
         (custr_category*)nullptr, (custr_category*)nullptr);
 }

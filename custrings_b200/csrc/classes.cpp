@@ -39,6 +39,12 @@ NVStrings* NVStrings::create_from_array(const char** strs, unsigned int count)
 {
     return new NVStrings(checked(custr_create_from_array(strs, count)));
 }
+NVStrings* NVStrings::create_from_index(std::pair<const char*, size_t>* strs, unsigned int count, bool devmem, sorttype stype)
+{
+    static_assert(sizeof(std::pair<const char*, size_t>) == 16, "pair layout");
+    // bad device pointers surface as std::invalid_argument("nvstrings::create_from_index bad_device_ptr"), NVStrings.cu:98-99
+    return new NVStrings(checked(custr_create_from_index(strs, count, devmem, (int)stype)));
+}
 NVStrings* NVStrings::create_from_offsets(const char* strs, int count, const int* offsets, const unsigned char* nullbitmask, int nulls,
                                           bool devmem)
 {

@@ -7,6 +7,10 @@
 #include "common.cuh"
 #include "device_utils.cuh"
 #include <cub/cub.cuh>
+#include <thrust/sort.h>
+#include <thrust/sequence.h>
+#include <thrust/execution_policy.h>
+#include <thrust/system/cuda/execution_policy.h>
 
 namespace custr {
 
@@ -215,6 +219,62 @@ __global__ void k_clamp_rows(int32_t* idx, int32_t m, int32_t n)
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m && (idx[i] < 0 || idx[i] >= n)) idx[i] = 0;
 }
+
+// ---- create_from_index (NVStrings.cu:88-107, NVStringsImpl.cu:209-325): (device pointer, byte length) pairs -> column
+struct IndexPair { const char* ptr; size_t len; };  // layout of std::pair<const char*, size_t> / thrust::pair
+__global__ void k_index_lengths(const IndexPair* __restrict__ pairs, int32_t n, const int32_t* __restrict__ order, int32_t* __restrict__ lengths,
+                                uint8_t* __restrict__ valid, int* __restrict__ too_long)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const IndexPair p = pairs[order ? order[i] : i];
+    if (p.ptr && p.len > 0x7fffffffULL) *too_long = 1;
+    lengths[i] = p.ptr ? (int32_t)p.len : 0;
+    valid[i] = p.ptr != nullptr;
+}
+// one warp per 32 rows: short rows are copied by their own lane, long rows by the whole warp (coalesced)
+__global__ void k_index_copy(const IndexPair* __restrict__ pairs, int32_t n, const int32_t* __restrict__ order, const int32_t* __restrict__ offsets,
+                             char* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const char* src = nullptr;
+    int len = 0, dst = 0;
+    if (i < n) {
+        const IndexPair p = pairs[order ? order[i] : i];
+        src = p.ptr;
+        len = p.ptr ? (int)p.len : 0;
+        dst = offsets[i];
+    }
+    unsigned big = __ballot_sync(0xffffffffu, len > 64);
+    if (len <= 64)
+        for (int k = 0; k < len; ++k) out[dst + k] = src[k];
+    while (big) {
+        const int l = __ffs(big) - 1;
+        big &= big - 1;
+        const char* s = (const char*)__shfl_sync(0xffffffffu, (unsigned long long)src, l);
+        const int n_ = __shfl_sync(0xffffffffu, len, l), d = __shfl_sync(0xffffffffu, dst, l);
+        for (int k = lane; k < n_; k += 32) out[d + k] = s[k];
+    }
+}
+// sort order for create_from_index's `stype` (NVStringsImpl.cu:255-268): null < non-null, then by length and / or bytes
+struct IndexLess {
+    const IndexPair* pairs;
+    int stype;
+    __device__ bool operator()(int32_t a, int32_t b) const
+    {
+        const IndexPair l = pairs[a], r = pairs[b];
+        if (!l.ptr || !r.ptr) return r.ptr != nullptr;
+        int diff = 0;
+        if (stype & 1) diff = (int)(unsigned int)(l.len - r.len);
+        if (diff == 0 && (stype & 2)) {
+            const size_t m = l.len < r.len ? l.len : r.len;
+            for (size_t k = 0; k < m && diff == 0; ++k) diff = (int)(uint8_t)l.ptr[k] - (int)(uint8_t)r.ptr[k];
+            if (diff == 0) diff = l.len < r.len ? -1 : (l.len > r.len ? 1 : 0);
+        }
+        return diff < 0;
+    }
+};
 
 // ------------------------------------------------------------------------------------------------ helpers
 static inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
@@ -466,6 +526,55 @@ custr_column* custr_create_from_array(const char* const* strs, uint32_t count)
             for (uint32_t i = 0; i < count; ++i)
                 if (strs[i]) memcpy(chars.data() + off[i], strs[i], off[i + 1] - off[i]);
             return create_from_offsets_impl(chars.data(), (int32_t)count, off.data(), val.data(), nulls, 0, false);
+        },
+        (custr_column*)nullptr, (custr_column*)nullptr);
+}
+
+// NVStrings::create_from_index (NVStrings.cu:88-107): `pairs` = count (pointer, byte length) pairs laid out like
+// std::pair<const char*, size_t>, in device memory when devmem != 0 else on the host; the POINTERS always address device memory
+// (the reference dereferences them in device code either way, NVStringsImpl.cu:232-238,272-279).  Null pointer = null row.
+// stype: 0 none, 1 length, 2 name, 3 both (NVStrings::sorttype).  A bad device pointer is reported as CUSTR_ERR_INVALID with the
+// reference's message ("nvstrings::create_from_index bad_device_ptr"); like there, the CUDA context is unusable afterwards.
+custr_column* custr_create_from_index(const void* pairs, uint32_t count, int devmem, int stype)
+{
+    return guarded(
+        [&]() -> custr_column* {
+            if (count && !pairs) throw ArgError{fail(CUSTR_ERR_ARG, "create_from_index: null array")};
+            if (count > 0x7fffffffu) throw ArgError{fail(CUSTR_ERR_ARG, "create_from_index: too many rows")};
+            const int32_t n = (int32_t)count;
+            BufPtr staged;
+            const IndexPair* d_pairs = (const IndexPair*)pairs;
+            if (!devmem && n) { staged = upload(pairs, sizeof(IndexPair) * (size_t)n); d_pairs = (const IndexPair*)staged->ptr; }
+            BufPtr order;
+            if (stype && n > 1) {
+                order = dev_alloc(sizeof(int32_t) * (size_t)n);
+                thrust::sequence(thrust::cuda::par.on(g_stream), (int32_t*)order->ptr, (int32_t*)order->ptr + n);
+                thrust::sort(thrust::cuda::par.on(g_stream), (int32_t*)order->ptr, (int32_t*)order->ptr + n, IndexLess{d_pairs, stype});
+                g_launches.fetch_add(2, std::memory_order_relaxed);
+            }
+            const int32_t* d_order = order ? (const int32_t*)order->ptr : nullptr;
+            Scratch<int32_t> lens((size_t)n + 1);
+            Scratch<uint8_t> ok((size_t)n + 1);
+            Scratch<int> too_long(1);
+            CUSTR_CUDA(cudaMemsetAsync(lens.get() + n, 0, sizeof(int32_t), g_stream));
+            CUSTR_CUDA(cudaMemsetAsync(too_long.get(), 0, sizeof(int), g_stream));
+            if (n) LAUNCH(k_index_lengths, blocks_for(n, 256), 256, 0, d_pairs, n, d_order, lens.get(), ok.get(), too_long.get());
+            int h_long = 0;
+            CUSTR_CUDA(cudaMemcpyAsync(&h_long, too_long.get(), sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+            BufPtr off = dev_alloc(sizeof(int32_t) * (size_t)(n + 1));
+            int64_t total = scan_lengths_to_offsets(lens.get(), (int32_t*)off->ptr, n);  // syncs
+            if (h_long) throw ArgError{fail(CUSTR_ERR_INVALID, "create_from_index: a string is longer than 2 GiB")};
+            BufPtr chars = dev_alloc((size_t)total);
+            if (n && total) {
+                LAUNCH(k_index_copy, blocks_for(n, 256), 256, 0, d_pairs, n, d_order, (const int32_t*)off->ptr, (char*)chars->ptr);
+                const cudaError_t e = cudaStreamSynchronize(g_stream);
+                if (e == cudaErrorIllegalAddress) throw ArgError{fail(CUSTR_ERR_INVALID, "nvstrings::create_from_index bad_device_ptr")};
+                CUSTR_CUDA(e);
+            }
+            BufPtr val = dev_alloc((n + 7) / 8 + 1);
+            pack_bits(ok.get(), (uint8_t*)val->ptr, n);
+            const int32_t nulls = count_zero_bits((const uint8_t*)val->ptr, 0, n);
+            return make_column(chars, off, val, n, nulls, total);
         },
         (custr_column*)nullptr, (custr_column*)nullptr);
 }

@@ -984,6 +984,8 @@ extern "C" {
 const char* custr_last_regex_tier(void) { return g_last_tier; }
 void custr_set_profiling(int on) { g_profile = on; }
 float custr_last_kernel_ms(void) { return g_last_kernel_ms; }
+// A/B: size of a work item of the chain / tokenize kernels in KiB (default 32)
+void custr_set_item_kib(int kib) { bits::g_item_bytes = (kib >= 8 && kib <= 1024 ? kib : 32) * 1024; }
 void custr_set_regex_tier(int tier)
 {
     g_forced_tier = tier == 1 ? 1 : 0;

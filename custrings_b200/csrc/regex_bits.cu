@@ -35,6 +35,7 @@ struct Plan {
 
 thread_local bool g_no_spec = false;        // A/B switch: never use the shape-specialised chain kernels
 thread_local bool g_force_generic = false;  // A/B switch: run chain-shaped plans on the generic interpreter kernel
+int g_item_bytes = 32 * 1024;              // size of a work item of the chain / tokenize kernels (bytes of chars; A/B: custr_set_item_kib)
 thread_local bool g_chain_win = false;      // A/B switch: boolean results from k_chain64 (window at a time) instead of k_chain_item
 
 #include "regex_bits_dev.cuh"
@@ -213,15 +214,15 @@ k_bitstream(const __grid_constant__ PlanDev plan, const Args A)
 
 // item_bounds[t] = first row r with offsets[r] >= first + t*ITEM_BYTES, for t = 0..nitems (bounds[nitems] = n): one coalesced
 // pass over the offsets instead of two dependent binary searches at the head of every work item
-__global__ void k_item_bounds(const int32_t* __restrict__ offsets, int n, int first, int nitems, int32_t* __restrict__ bounds)
+__global__ void k_item_bounds(const int32_t* __restrict__ offsets, int n, int first, int nitems, int item_bytes, int32_t* __restrict__ bounds)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // row index 0..n (offsets has n+1 entries)
     if (i > n) return;
     const long long cur = (long long)offsets[i] - first;
     const long long prev = i == 0 ? -1 : (long long)offsets[i - 1] - first;
     // boundaries t with prev < t*ITEM <= cur get row i
-    long long t_lo = prev < 0 ? 0 : prev / ITEM_BYTES + 1;
-    long long t_hi = cur / ITEM_BYTES;
+    long long t_lo = prev < 0 ? 0 : prev / item_bytes + 1;
+    long long t_hi = cur / item_bytes;
     if (t_hi > nitems) t_hi = nitems;
     for (long long t = t_lo; t <= t_hi; ++t) bounds[t] = i;
     if (i == n) {  // boundaries past the last offset (only bounds[nitems] when the span is not a multiple of the item size)
@@ -238,7 +239,7 @@ static const int32_t* ensure_item_bounds(const custr_column* col, const int32_t*
     std::lock_guard<std::mutex> lock(mu);
     if (!col->item_bounds || col->item_bounds_count != nitems) {
         BufPtr b = dev_alloc(sizeof(int32_t) * (size_t)(nitems + 2));
-        LAUNCH(k_item_bounds, (col->n + 1 + 255) / 256, 256, 0, offsets, col->n, first, nitems, (int32_t*)b->ptr);
+        LAUNCH(k_item_bounds, (col->n + 1 + 255) / 256, 256, 0, offsets, col->n, first, nitems, g_item_bytes, (int32_t*)b->ptr);
         CUSTR_CUDA(cudaStreamSynchronize(g_stream));
         col->item_bounds = b;
         col->item_bounds_count = nitems;
@@ -303,7 +304,9 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     a.n = n;
     a.first = col->first_off;
     a.end = col->first_off + (int32_t)col->nbytes;
-    a.nitems = (int)((col->nbytes + ITEM_BYTES - 1) / ITEM_BYTES);
+    // (the DAG interpreter searches its own 32 KiB items; the chain kernels take theirs from the column's item index)
+    const int item_bytes = (plan.is_chain && !g_force_generic) ? g_item_bytes : ITEM_BYTES;
+    a.nitems = (int)((col->nbytes + item_bytes - 1) / item_bytes);
     a.out = out;
     a.total = total;
     a.dirty_rows = *dirty_rows;
@@ -360,7 +363,7 @@ bool tokenize_flat(const custr_column* col, const uint8_t* delims, int ndelims, 
     a.n = n;
     a.first = col->first_off;
     a.end = col->first_off + (int32_t)col->nbytes;
-    a.nitems = (int)((col->nbytes + ITEM_BYTES - 1) / ITEM_BYTES);
+    a.nitems = (int)((col->nbytes + g_item_bytes - 1) / g_item_bytes);
     a.whitespace = delims ? 0u : 1u;
     a.ndelims = delims ? (uint32_t)ndelims : 0u;
     for (int k = 0; k < ndelims && delims; ++k) a.delims[k] = delims[k];

@@ -46,6 +46,7 @@ bool tokenize_flat(const custr_column* col, const uint8_t* delims, int ndelims, 
 extern thread_local bool g_force_generic;
 extern thread_local bool g_no_spec;
 extern thread_local bool g_chain_win;
+extern int g_item_bytes;
 
 // Non-null when the plan is a linear chain whose only loop is its last step: for those patterns the match SPAN the Pike VM
 // reports (leftmost start, then thread priority) is "leftmost start, longest end that satisfies the trailing assertion",

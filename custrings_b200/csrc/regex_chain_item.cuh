@@ -48,7 +48,7 @@ static __device__ __noinline__ void ring_issue_item_tail(uint32_t wr, const char
         const uint32_t pos = ws + 512u * k + 16u * lane;
         const uint32_t dst = wr + 128u * k;
         if (pos + 16u <= end) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(chars + pos) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(chars + pos) : "memory");
             continue;
         }
         asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
@@ -62,7 +62,7 @@ __device__ __forceinline__ void ring_issue_item(uint32_t wr, const char* __restr
     if (ws + WIN64 <= end) {
         const char* src = gsrc + ws;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wr + 128u * k), "l"(src + 512 * k) : "memory");
+        for (int k = 0; k < 4; ++k) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(wr + 128u * k), "l"(src + 512 * k) : "memory");
     } else
         ring_issue_item_tail(wr, chars, ws, end, lane);
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -74,8 +74,8 @@ __device__ __forceinline__ u64 shift_down64_nb(u64 x, uint32_t nxt) { return mk6
 // Marker chain of one window.  Returns the stream of positions behind which a match may end, BEFORE the zero-width
 // assertions of END are applied.  UTF8 = false: the window holds ASCII bytes only (cont == 0, every byte is a character).
 template <int NS, int NCLS, int SPEC, bool UTF8>
-__device__ __forceinline__ u64 chain_item64(const ChainDev& cd, const u64 (&c)[NCLS], const Assertions64& as, u64 rs, int rounds, u64 cont, uint32_t cont0,
-                                            ItemState<NS>& st, const LaneCtx& L)
+__device__ __forceinline__ u64 chain_item64(const ChainDev& cd, const u64 (&c)[NCLS], const Assertions64& as, u64 rs, int rounds, u64 cont, u64 lead,
+                                            uint32_t cont0, ItemState<NS>& st, const LaneCtx& L)
 {
     using PL = PlanLit<SPEC>;
     const u64 nrs = ~rs;
@@ -101,8 +101,13 @@ __device__ __forceinline__ u64 chain_item64(const ChainDev& cd, const u64 (&c)[N
         u64 Z = t;
         if (PV_STEP_LOOP(s)) Z = spread64(t, ck & nrs, old, L);
         else if (UTF8) {
+            // a marker on the lead byte of a multi-byte character moves to the character's last byte, one round per
+            // continuation byte of the longest character of the window — only when some marker of this step sits on such a
+            // lead byte, or one is still travelling in from the previous window (warp-uniform test: usually neither)
+            if (__any_sync(FULL, (t & lead) != 0 || (cont0 && L.is31 && (old & 0x80000000u)))) {
 #pragma unroll 1
-            for (int r = 0; r < rounds; ++r) Z |= adv64(Z, old, L) & cont;
+                for (int r = 0; r < rounds; ++r) Z |= adv64(Z, old, L) & cont;
+            }
         }
         st.last[s] = hi32(Z);
         old_prev = old;
@@ -110,6 +115,23 @@ __device__ __forceinline__ u64 chain_item64(const ChainDev& cd, const u64 (&c)[N
         if (PV_STEP_EXIT(s)) done |= P;
     }
     return done;
+}
+
+// phase B of an item that saw a NUL byte: does THIS row hold one?  Such rows are appended to the work list of the exact VM
+// kernel and report no hit here.  Called by the whole warp (cold path).
+static __device__ __noinline__ uint32_t item_dirty_row(const Args& A, bool in, int o0, int o1, int row, uint32_t hit, uint32_t lane)
+{
+    bool dirty = false;
+    if (in)
+        for (int q = o0; q < o1 && !dirty; ++q) dirty = A.chars[q] == 0;
+    const unsigned dm = __ballot_sync(FULL, dirty);
+    if (dm) {
+        unsigned basei = 0;
+        if (lane == 0) basei = atomicAdd(A.dirty_count, __popc(dm));
+        basei = __shfl_sync(FULL, basei, 0);
+        if (dirty) A.dirty_rows[basei + __popc(dm & ((1u << lane) - 1))] = row;
+    }
+    return dirty ? 0u : hit;
 }
 
 template <int NS, int NCLS, int SPEC = 0>
@@ -135,6 +157,8 @@ k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A
     const uint32_t bneed = PV_BUILTIN_UNION | ((PV_NEEDS & (AS_BOW | AS_NBOW)) ? (1u << AK_ALNUM) : 0u);
     const bool need_nl = (PV_NEEDS & (AS_BOL_CARET | AS_EOL_DOLLAR | AS_EOL_Z)) != 0;
     const uint32_t uend = (uint32_t)A.end;
+    uint32_t top31 = L.is31 ? 0x80000000u : 0u;  // the window's last position: top bit of lane 31's stream words
+    asm volatile("" : "+r"(top31));
     uint32_t cnt = 0;  // rows with a match finalised by this lane
 
     for (;;) {
@@ -155,6 +179,12 @@ k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A
         u64 zacc = 0;  // NUL bytes seen by this lane in this item
         uint32_t ws = empty_item ? (uint32_t)byte_a : ((uint32_t)byte_a & ~(uint32_t)(WIN64 - 1));
         int wins_left = empty_item ? 0 : (int)((((uint32_t)byte_b - 1u) >> 11) - ((uint32_t)byte_a >> 11)) + 1;
+        // the item's slice of the offsets array is read twice (phase 0 and phase B), 32 consecutive entries per lane and step:
+        // touch all of its lines now, in parallel, so that those loads are cache hits instead of one DRAM latency per step
+        for (int j0 = ra; j0 <= rb; j0 += 1024) {
+            const int j = j0 + 32 * (int)lane;
+            if (j <= rb) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.offsets + j));
+        }
         int krs = ra;   // next offsets index whose ROWSTART bit is not set yet
         int kfin = ra;  // next row to finalise
         uint32_t stage = 0;
@@ -169,14 +199,16 @@ k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A
             for (uint32_t i = 2u * lane; i <= 32u * (uint32_t)nw; i += 64u)
                 asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(bits0 + 8u * i), "r"(0u) : "memory");
             __syncwarp();
-            for (;;) {
+            for (;;) {  // two rows per lane and step; rel = 0xffffffff marks "no such row" (a real one is < 2^31)
                 const int j = krs + (int)lane;
-                const bool live = j <= rb;
-                const uint32_t rel = live ? (uint32_t)__ldg(A.offsets + j) - seg_ws : 0xffffffffu;
-                if (live && rel <= span) reds_or(bits0 + 4u * (rel >> 5), 1u << (rel & 31));
-                const unsigned m = __ballot_sync(FULL, live && rel < span);
-                krs += __popc(m);
-                if (m != FULL) break;
+                uint32_t rel0 = 0xffffffffu, rel1 = 0xffffffffu;
+                if (j <= rb) rel0 = (uint32_t)__ldg(A.offsets + j) - seg_ws;
+                if (j + 32 <= rb) rel1 = (uint32_t)__ldg(A.offsets + j + 32) - seg_ws;
+                if (rel0 <= span) reds_or(bits0 + ((rel0 >> 3) & ~3u), 1u << (rel0 & 31));
+                if (rel1 <= span) reds_or(bits0 + ((rel1 >> 3) & ~3u), 1u << (rel1 & 31));
+                const unsigned m0 = __ballot_sync(FULL, rel0 < span), m1 = __ballot_sync(FULL, rel1 < span);
+                krs += __popc(m0) + __popc(m1);
+                if (m1 != FULL) break;
             }
             __syncwarp();
 
@@ -206,9 +238,10 @@ k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A
                     for (int b = 0; b < 8; ++b) p[b] = mk64(pl[b], ph[b]);
                 }
                 const u64 na = p[7];
-                const u64 letter5 = cls_letter5(p), digit = cls_digit(p);
+                const u64 nz5 = p[4] | p[3] | p[2] | p[1] | p[0];
+                const u64 letter5 = nz5 & ~(p[4] & p[3] & (p[2] | (p[1] & p[0]))), digit = cls_digit(p);  // low five bits in 1..26
                 const u64 alnum = (p[6] & letter5) | digit, word = alnum | cls_underscore(p);
-                zacc |= ~(p[0] | p[1] | p[2] | p[3] | p[4] | p[5] | p[6] | p[7]);
+                zacc |= ~(nz5 | p[5] | p[6] | p[7]);
                 u64 space = 0;
                 if (bneed & (1u << AK_SPACE)) space = cls_space(p);
                 NaClasses<NCLS> nc;
@@ -276,8 +309,8 @@ k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A
                     st.last_nl = hi32(nl);
                 }
                 u64 done;
-                if (!utf8) done = chain_item64<NS, NCLS, SPEC, false>(cd, c, as, rs, 0, 0ull, 0u, st, L);
-                else done = chain_item64<NS, NCLS, SPEC, true>(cd, c, as, rs, rounds, cont, cont0, st, L);
+                if (!utf8) done = chain_item64<NS, NCLS, SPEC, false>(cd, c, as, rs, 0, 0ull, 0ull, 0u, st, L);
+                else done = chain_item64<NS, NCLS, SPEC, true>(cd, c, as, rs, rounds, cont, p[7] & p[6], cont0, st, L);
                 u64 E = PV_END_MASK ? apply_after64(done, PV_END_MASK, as) : done;
                 // the last position of the window: with a row start right behind it the look-ahead used above ("nothing
                 // follows") is exact; otherwise the bit is withheld and decided by the next window
@@ -285,7 +318,7 @@ k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A
                     u64 d2 = done;  // END assertions that need no look-ahead
                     if (PV_END_MASK & AS_BOL_CARET) d2 &= nl;
                     if (PV_END_MASK & AS_BOL_A) d2 = 0;
-                    const uint32_t hold = (L.is31 && !rs_next) ? 0x80000000u : 0u;
+                    const uint32_t hold = rs_next ? 0u : top31;
                     st.pend = hi32(d2) & hold;
                     E &= ~((u64)hold << 32);
                 }
@@ -298,42 +331,34 @@ k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A
 
             // ---- phase B: the rows that end inside the segment
             const bool item_dirty = __any_sync(FULL, zacc != 0);
-            for (;;) {
+            for (;;) {  // two rows per lane and step
                 const int j = kfin + (int)lane;
-                bool in = false;
-                uint32_t hit = 0;
-                int o0 = 0, o1 = 0;
+                int oa0 = 0, oa1 = 0, ob0 = 0, ob1 = 0;
+                uint32_t rela = 0xffffffffu, relb = 0xffffffffu;  // (end of the row) - (segment start); 0xffffffff: no such row
                 if (j < rb) {
-                    o0 = __ldg(A.offsets + j);
-                    o1 = __ldg(A.offsets + j + 1);
-                    in = (uint32_t)o1 - seg_ws <= span;
+                    oa0 = __ldg(A.offsets + j);
+                    oa1 = __ldg(A.offsets + j + 1);
+                    rela = (uint32_t)oa1 - seg_ws;
                 }
-                if (in && o1 > o0) {
-                    const uint32_t rel = (uint32_t)o1 - 1u - seg_ws;
-                    hit = (lds32(bits0 + 4u * (rel >> 5)) >> (rel & 31)) & 1u;
+                if (j + 32 < rb) {
+                    ob0 = __ldg(A.offsets + j + 32);
+                    ob1 = __ldg(A.offsets + j + 33);
+                    relb = (uint32_t)ob1 - seg_ws;
                 }
+                const bool ina = rela <= span, inb = relb <= span;
+                uint32_t hita = 0, hitb = 0;
+                if (ina && oa1 > oa0) hita = (lds32(bits0 + (((rela - 1u) >> 3) & ~3u)) >> ((rela - 1u) & 31)) & 1u;
+                if (inb && ob1 > ob0) hitb = (lds32(bits0 + (((relb - 1u) >> 3) & ~3u)) >> ((relb - 1u) & 31)) & 1u;
                 if (__builtin_expect(item_dirty, 0)) {  // a NUL byte somewhere in this item: rows holding one go to the exact VM
-                    bool dirty = false;
-                    if (in)
-                        for (int q = o0; q < o1 && !dirty; ++q) dirty = A.chars[q] == 0;
-                    const unsigned dm = __ballot_sync(FULL, dirty);
-                    if (dm) {
-                        unsigned basei = 0;
-                        if (lane == 0) basei = atomicAdd(A.dirty_count, __popc(dm));
-                        basei = __shfl_sync(FULL, basei, 0);
-                        if (dirty) {
-                            A.dirty_rows[basei + __popc(dm & ((1u << lane) - 1))] = j;
-                            hit = 0;
-                        }
-                    }
+                    hita = item_dirty_row(A, ina, oa0, oa1, j, hita, lane);
+                    hitb = item_dirty_row(A, inb, ob0, ob1, j + 32, hitb, lane);
                 }
-                if (in) {
-                    A.out[j] = (uint8_t)hit;
-                    cnt += hit;
-                }
-                const unsigned m = __ballot_sync(FULL, in);
-                kfin += __popc(m);
-                if (m != FULL) break;
+                if (ina) A.out[j] = (uint8_t)hita;
+                if (inb) A.out[j + 32] = (uint8_t)hitb;
+                cnt += hita + hitb;
+                const unsigned ma = __ballot_sync(FULL, ina), mb = __ballot_sync(FULL, inb);
+                kfin += __popc(ma) + __popc(mb);
+                if (mb != FULL) break;
             }
             wins_left -= nw;
             __syncwarp();

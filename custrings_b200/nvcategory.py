@@ -2,8 +2,8 @@
 (from_strings :78, keys :242, values :364, keys_size, size), over libcustr.so's C-ABI.
 
 Multi-GPU: from_strings_sharded() builds the local dictionary of a row shard, all-gathers the
-distinct keys of every rank with torch.distributed (NCCL over NVLink on GPUs, gloo in CPU tests of the host
-logic) and remaps the local values onto the global sorted key set.
+distinct keys of every rank (ncclAllGather over NVLink inside libcustr.so's host C++; torch.distributed tensor collectives
+with gloo in the CPU tests of the host logic) and remaps the local values onto the global sorted key set.
 """
 import ctypes as C
 
@@ -34,20 +34,6 @@ def to_device(strs):
 def from_offsets(sbuf, obuf, scount, nbuf=None, ncount=0, bdevmem=False):
     """reference nvcategory.py:37 -> NVCategory.cu:359-370"""
     return from_strings(_nvs.from_offsets(sbuf, obuf, scount, nbuf, ncount, bdevmem))
-
-
-def gather_keys_host(local_keys, group=None):
-    """All-gather the key strings of every rank (host lists; the payload is K keys x ~16 B per rank, i.e.
-    latency-bound).  Returns the concatenated list in rank order."""
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return list(local_keys)
-    out = [None] * dist.get_world_size(group)
-    dist.all_gather_object(out, list(local_keys), group=group)
-    merged = []
-    for part in out:
-        merged.extend(part)
-    return merged
 
 
 def exchange_key_arrays(chars, offsets, valid, group=None, device=None):
@@ -102,13 +88,50 @@ def gather_keys_device(keys, group=None):
     return _nvs.from_offsets(chars if chars.size else np.zeros(1, np.uint8), offs, len(offs) - 1, np.packbits(valid, bitorder="little"), nulls)
 
 
-def from_strings_sharded(strs, group=None):
+_COMMS = {}  # (id(group) or None) -> custr_comm handle of this process
+
+
+def _comm(group=None):
+    """NCCL communicator of libcustr.so for `group` (created once per process and group): rank 0 draws the unique id,
+    torch.distributed only carries its 128 bytes to the other ranks."""
+    import torch
+    import torch.distributed as dist
+    key = id(group) if group is not None else None
+    if key not in _COMMS:
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            check_rc(lib().custr_comm_unique_id(buf), "comm_unique_id")
+        t = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+        _COMMS[key] = check_handle(lib().custr_comm_create(rank, world, ident), "comm_create")
+    return _COMMS[key]
+
+
+def from_strings_sharded(strs, group=None, timings=False):
     """Row-sharded dictionary build: `strs` is THIS rank's contiguous row range.  Every rank returns a category whose
-    keys() is the global sorted key set and whose values() index into it."""
+    keys() is the global sorted key set and whose values() index into it.  On GPUs (NCCL backend) the whole exchange runs in
+    host C++ inside libcustr.so (custr_category_create_sharded: ncclAllGather of the ranks' distinct keys); with the gloo
+    backend (CPU tests of the host logic) the keys travel through torch collectives (exchange_key_arrays).
+    timings=True: returns (category, {build_ms, exchange_ms, remap_ms, how})."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 and dist.get_backend(group) == "nccl":
+        t = (C.c_float * 3)()
+        h = lib().custr_category_create_sharded(_comm(group), strs.m_cptr, t)
+        cat = nvcategory(check_handle(h, "from_strings_sharded"))
+        info = {"build_ms": t[0], "exchange_ms": t[1], "remap_ms": t[2], "how": "ncclAllGather x3 inside libcustr.so (sizes, key lengths, key bytes)"}
+        return (cat, info) if timings else cat
+    import time
+    t0 = time.perf_counter()
     local = from_strings(strs)
+    t1 = time.perf_counter()
     all_keys = gather_keys_device(local.keys(), group)
+    t2 = time.perf_counter()
     h = lib().custr_category_remap_to_union(local.m_cptr, all_keys.m_cptr)
-    return nvcategory(check_handle(h, "from_strings_sharded"))
+    cat = nvcategory(check_handle(h, "from_strings_sharded"))
+    info = {"build_ms": 1e3 * (t1 - t0), "exchange_ms": 1e3 * (t2 - t1), "remap_ms": 1e3 * (time.perf_counter() - t2), "how": "torch.distributed tensor collectives"}
+    return (cat, info) if timings else cat
 
 
 def from_categories(cats):

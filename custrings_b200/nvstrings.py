@@ -64,6 +64,14 @@ def from_device_view(chars, offsets, scount, validity=None, ncount=0, keepalive=
     return s
 
 
+def from_index(pairs, count, bdevmem=True, stype=0):
+    """NVStrings::create_from_index (NVStrings.h:98): `pairs` = address of `count` (device pointer, byte length) entries
+    laid out like std::pair<const char*, size_t> (int | numpy uint64[count, 2] | torch tensor); bdevmem: the pair ARRAY is
+    in device memory.  stype: 0 none, 1 length, 2 name, 3 both.  This is how cuDF / nvtext hand string views in."""
+    h = lib().custr_create_from_index(as_ptr(pairs), count, 1 if bdevmem else 0, stype)
+    return nvstrings(check_handle(h, "from_index"))
+
+
 def from_strings(*args):
     """Concatenate nvstrings instances into one.  reference nvstrings.py:27"""
     cols = []

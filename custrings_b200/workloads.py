@@ -69,3 +69,138 @@ def slice_rows(chars, offsets, validity, lo, hi):
     n = hi - lo
     v = np.unpackbits(validity, bitorder="little")[lo:hi]
     return c, (off - off[0]).astype(np.int32), np.packbits(v, bitorder="little"), int(n - v.sum())
+
+
+# ---- the other BASELINE.json configs -------------------------------------------------------------------
+import gzip as _gzip
+import io as _io
+import os as _os
+
+_DATA = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "tests", "golden", "data")
+
+
+def _fixture(name):
+    """bytes of one of the reference's sample data files (tests/golden/data/*.gz, made by tools/make_fixtures.py)"""
+    with _gzip.open(_os.path.join(_DATA, name + ".gz"), "rb") as f:
+        return f.read()
+
+
+def pack_rows(rows):
+    """list of bytes / None -> (chars uint8[], offsets int32[n+1], validity uint8[(n+7)//8], nulls)"""
+    n = len(rows)
+    lens = np.fromiter((0 if r is None else len(r) for r in rows), np.int64, n)
+    offsets = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    chars = np.frombuffer(b"".join(r for r in rows if r), np.uint8).copy() if offsets[-1] else np.zeros(0, np.uint8)
+    valid = np.fromiter((r is not None for r in rows), bool, n)
+    return chars, offsets.astype(np.int32), np.packbits(valid, bitorder="little"), int(n - valid.sum())
+
+
+def c1_lines():
+    """C1: data/985-rows.csv cut at '\\r' (header + 985 rows, every line holds exactly 11 commas), empties dropped"""
+    return [l for l in _fixture("985-rows.csv").split(b"\r") if l]
+
+
+def tile_rows(rows, total_bytes):
+    """Round-robin tiling of `rows` (list of bytes) up to `total_bytes` chars -> (chars, offsets, n).  Vectorised: the
+    pool is packed once and whole copies of it are repeated; the last copy is cut at a row boundary."""
+    chars0, off0, _, _ = pack_rows(rows)
+    per = int(off0[-1])
+    reps = total_bytes // per
+    tail_rows = int(np.searchsorted(off0, total_bytes - reps * per, side="right")) - 1
+    n = reps * len(rows) + tail_rows
+    chars = np.empty(reps * per + int(off0[tail_rows]), np.uint8)
+    if reps:
+        chars[: reps * per].reshape(reps, per)[:] = chars0
+    chars[reps * per:] = chars0[: int(off0[tail_rows])]
+    lens0 = np.diff(off0.astype(np.int64))
+    lens = np.concatenate([np.tile(lens0, reps), lens0[:tail_rows]])
+    offsets = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    return chars, offsets.astype(np.int32), n
+
+
+def c5_rows():
+    """C5 row pool: the `text` column of data/tweets.csv (pandas parses the embedded quotes / newlines) with one line of
+    data/utf8.csv (cut at '\\r') after every 8 tweets, so that multi-byte UTF-8 is actually exercised (tweets.csv holds
+    only 163 non-ASCII bytes)."""
+    import pandas as pd
+    tweets = [t.encode("utf-8") for t in pd.read_csv(_io.BytesIO(_fixture("tweets.csv")))["text"].astype(str)]
+    utf8 = [l for l in _fixture("utf8.csv").split(b"\r") if l.strip()]
+    rows, u = [], 0
+    for i, t in enumerate(tweets):
+        rows.append(t)
+        if i % 8 == 7:
+            rows.append(utf8[u % len(utf8)])
+            u += 1
+    return rows
+
+
+def c5_corpus(total_bytes=512 << 20):
+    """C5 shard: c5_rows() tiled to `total_bytes` chars (512 MiB per GPU = 4 GiB over 8 GPUs)"""
+    return tile_rows(c5_rows(), total_bytes)
+
+
+DAYS = ("Sun", "Mon", "Tues", "Wed", "Thur", "Fri", "Sat")
+
+
+def c3_readme_rows(n=10_000_000, seed=7):
+    """C3 input A (README): n rows "%.2f,%.2f,{Female|Male},{Yes|No},{day},{Lunch|Dinner},%d" -> (chars, offsets)"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pools = [
+        np.array([b"%.2f" % v for v in np.arange(3.07, 50.81, 0.01)], object),
+        np.array([b"%.2f" % v for v in np.arange(1.0, 10.0, 0.01)], object),
+        np.array([b"Female", b"Male"], object), np.array([b"Yes", b"No"], object),
+        np.array([d.encode() for d in DAYS], object), np.array([b"Lunch", b"Dinner"], object),
+        np.array([b"%d" % v for v in range(1, 7)], object),
+    ]
+    # a vocabulary of complete rows would be too small; build rows from per-field byte tables instead
+    fields = []
+    for p in pools:
+        idx = rng.integers(0, len(p), size=n)
+        width = max(len(x) for x in p)
+        tab = np.zeros((len(p), width), np.uint8)
+        ln = np.zeros(len(p), np.int64)
+        for i, x in enumerate(p):
+            tab[i, : len(x)] = np.frombuffer(x, np.uint8)
+            ln[i] = len(x)
+        fields.append((tab, ln, idx))
+    row_len = sum(ln[idx] for _, ln, idx in fields) + (len(fields) - 1)
+    offsets = np.zeros(n + 1, np.int64)
+    np.cumsum(row_len, out=offsets[1:])
+    chars = np.full(int(offsets[-1]), ord(","), np.uint8)
+    pos = offsets[:-1].copy()
+    for k, (tab, ln, idx) in enumerate(fields):
+        l = ln[idx]
+        for j in range(tab.shape[1]):
+            sel = l > j
+            chars[pos[sel] + j] = tab[idx[sel], j]
+        pos += l + 1
+    return chars, offsets.astype(np.int32)
+
+
+def c4_category_rows(n=12_500_000, nkeys=1000, seed=11, rank=0):
+    """C4 shard: n rows drawn uniformly from `nkeys` distinct keys ([a-z0-9], length U{8..24}); the key set depends only on
+    `seed`, the draw also on `rank` -> (chars, offsets, keys list)"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    alphabet = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz0123456789", np.uint8)
+    keys = set()
+    while len(keys) < nkeys:
+        keys.add(alphabet[rng.integers(0, 36, size=int(rng.integers(8, 25)))].tobytes())
+    keys = sorted(keys)
+    rng2 = np.random.Generator(np.random.PCG64(seed * 1000 + 1 + rank))
+    idx = rng2.integers(0, nkeys, size=n)
+    width = 24
+    tab = np.zeros((nkeys, width), np.uint8)
+    ln = np.zeros(nkeys, np.int64)
+    for i, k in enumerate(keys):
+        tab[i, : len(k)] = np.frombuffer(k, np.uint8)
+        ln[i] = len(k)
+    l = ln[idx]
+    offsets = np.zeros(n + 1, np.int64)
+    np.cumsum(l, out=offsets[1:])
+    chars = np.empty(int(offsets[-1]), np.uint8)
+    for j in range(width):
+        sel = l > j
+        chars[offsets[:-1][sel] + j] = tab[idx[sel], j]
+    return chars, offsets.astype(np.int32), keys, idx

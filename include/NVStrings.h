@@ -22,8 +22,11 @@ class NVStrings {
     friend class NVText;
 
 public:
-    // reference NVStrings.h:86,116 / NVStrings.cu:74-119
+    enum sorttype { none = 0, length = 1, name = 2 };  // reference NVStrings.h:55-59 (may be OR-ed)
+    // reference NVStrings.h:86,98,116 / NVStrings.cu:74-119
     static NVStrings* create_from_array(const char** strs, unsigned int count);
+    // (pointer, byte length) pairs; the pointers address device memory, devmem says where the pair array lives (:98)
+    static NVStrings* create_from_index(std::pair<const char*, size_t>* strs, unsigned int count, bool devmem = true, sorttype stype = none);
     static NVStrings* create_from_offsets(const char* strs, int count, const int* offsets, const unsigned char* nullbitmask = 0,
                                           int nulls = 0, bool devmem = true);
     static void destroy(NVStrings* inst);  // :156

@@ -46,8 +46,11 @@ long long custr_launch_count(void);
 /* name of the regex execution tier used by the last regex call on this thread ("bitstream", "pikevm") */
 const char* custr_last_regex_tier(void);
 /* force a tier for A/B testing: 0 = auto, 1 = exact Pike VM only, 2 = bitstream generic interpreter kernel,
- * 3 = bitstream 32-bit-stream chain kernel, 4 = 64-bit chain kernel without the shape specialisations */
+ * 3 = boolean results from the window-at-a-time chain kernel (k_chain64) instead of the item-buffered one,
+ * 4 = chain kernels without the shape specialisations */
 void custr_set_regex_tier(int tier);
+/* tuning / A-B switch: size of a work item of the chain and tokenize kernels in KiB of chars (default 32) */
+void custr_set_item_kib(int kib);
 /* when on, regex calls bracket their dominant kernel(s) with CUDA events on the launch stream;
  * custr_last_kernel_ms() returns that device time for the last call on this thread (-1 if none) */
 void custr_set_profiling(int on);
@@ -63,6 +66,10 @@ custr_column* custr_create_from_offsets(const char* chars, int32_t count, const 
 custr_column* custr_adopt_device(const char* chars, int32_t count, const int32_t* offsets, const uint8_t* validity, int32_t nulls);
 /* Host array of NUL-terminated strings, NULL entries = null rows. */
 custr_column* custr_create_from_array(const char* const* strs, uint32_t count);
+/* NVStrings::create_from_index (NVStrings.h:98, NVStrings.cu:88-107): `pairs` = count {const char* ptr; size_t bytes;} entries
+ * (the layout of std::pair<const char*,size_t>), in device memory when devmem != 0 else on the host; ptr always addresses
+ * DEVICE memory, ptr == NULL is a null row.  stype = NVStrings::sorttype (0 none, 1 length, 2 name, 3 both). */
+custr_column* custr_create_from_index(const void* pairs, uint32_t count, int devmem, int stype);
 void     custr_column_free(custr_column* col);
 uint32_t custr_size(const custr_column* col);
 int64_t  custr_chars_bytes(const custr_column* col);     /* bytes in the chars buffer                      */
@@ -164,6 +171,19 @@ custr_category* custr_category_remap_to_union(const custr_category* cat, const c
  * inputs): NVCategory::merge_category :1223-1336 — keys = the first input's keys followed by the second's new keys, the first
  * values unchanged. */
 custr_category* custr_category_merge(const custr_category* const* cats, int32_t ncats, int sorted);
+
+/* ---- multi-GPU NVCategory: the one collective of the hot path.  One process per GPU; the column is sharded
+ *      by contiguous row range.  custr_comm wraps an NCCL communicator (libnccl.so.2 bound at run time): rank 0 obtains a
+ *      128-byte unique id, the launcher hands it to every rank (MPI / torch.distributed / a file), every rank creates its
+ *      communicator.  custr_category_create_sharded = local NVCategory build (NVCategory.cu:327-356) -> ncclAllGather of
+ *      every rank's distinct keys over NVLink -> global sorted key set + remap of the local values (create_from_categories
+ *      math, NVCategory.cu:430-514).  Every rank returns the same keys; values index into them.  timings_ms: NULL or
+ *      float[3] = {local build, key exchange, union + remap} in ms (CUDA events on the call's stream). ---- */
+typedef struct custr_comm custr_comm;
+int custr_comm_unique_id(void* id128);
+custr_comm* custr_comm_create(int rank, int world, const void* id128);
+void custr_comm_destroy(custr_comm* comm);
+custr_category* custr_category_create_sharded(custr_comm* comm, const custr_column* local_rows, float* timings_ms);
 
 #ifdef __cplusplus
 }

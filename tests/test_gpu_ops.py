@@ -197,6 +197,13 @@ def test_category_merge(oracle):
         same(dev[i].merge_and_remap(dev[j]), ref[i].merge_and_remap(ref[j]))
         same(dev[i].merge_category(dev[j]), ref[i].merge_category(ref[j]))
     same(nvcategory.from_categories(dev[:4]), oracle.RefCategory.from_categories(ref[:4]))
+    # chained merge_category: the left operand's keys are then NOT sorted (appended keys; a null key that only the right side
+    # had ends up last) — existing keys must still be found
+    for a, b, c in ((0, 1, 2), (4, 1, 0), (2, 0, 1), (3, 1, 1), (4, 0, 4)):
+        d_ab, r_ab = dev[a].merge_category(dev[b]), ref[a].merge_category(ref[b])
+        same(d_ab.merge_category(dev[c]), r_ab.merge_category(ref[c]))
+        same(d_ab.merge_and_remap(dev[c]), r_ab.merge_and_remap(ref[c]))
+        same(dev[c].merge_category(d_ab), ref[c].merge_category(r_ab))
 
 
 def test_tokenize_bitstream_large(oracle):
@@ -285,3 +292,43 @@ def test_c3_readme_day_of_week_chain(oracle):
     finally:
         lib().custr_set_regex_tier(0)
     assert dev2.to_host() == dev.to_host()
+
+
+def test_create_from_index(oracle):
+    """NVStrings::create_from_index: (device pointer, length) pairs, host or device pair array, null pointers, the sort types
+    (reference NVStrings.cu:88-107, NVStringsImpl.cu:209-325; expected order re-derived from the reference's comparator)"""
+    import torch
+    from custrings_b200 import nvstrings
+    rng = random.Random(5)
+    words = ["", "a", "é", "zz", "hello world", "x" * 70, "日本語", "B", "b" * 200, "aa"]
+    rows = [rng.choice(words + [None]) for _ in range(3000)]
+    blob = b"".join((r or "").encode() for r in rows) + b"\0" * 16
+    d_blob = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
+    base = d_blob.data_ptr()
+    pairs = np.zeros((len(rows), 2), np.uint64)
+    pos = 0
+    for i, r in enumerate(rows):
+        if r is not None:
+            b = r.encode()
+            pairs[i] = (base + pos, len(b))
+            pos += len(b)
+    host = nvstrings.from_index(pairs, len(rows), bdevmem=False)
+    assert host.to_host() == rows
+    d_pairs = torch.from_numpy(pairs.view(np.int64)).cuda()
+    dev = nvstrings.from_index(d_pairs, len(rows), bdevmem=True)
+    assert dev.to_host() == rows
+
+    def key(stype):
+        def k(r):
+            if r is None:
+                return (0, 0, b"")
+            b = r.encode()
+            return (1, len(b) if stype & 1 else 0, b if stype & 2 else b"")
+        return k
+
+    for stype in (1, 2, 3):
+        got = nvstrings.from_index(d_pairs, len(rows), bdevmem=True, stype=stype).to_host()
+        want = sorted(rows, key=key(stype))
+        assert [key(stype)(g) for g in got] == [key(stype)(w) for w in want]
+        assert sorted(got, key=lambda r: (r is not None, r or "")) == sorted(rows, key=lambda r: (r is not None, r or ""))
+    assert nvstrings.from_index(0, 0).size() == 0

@@ -18,12 +18,14 @@ ap.add_argument("--pattern", default=r"\b\w{4,}\b")
 ap.add_argument("--reps", type=int, default=30)
 ap.add_argument("--rows", type=int, default=10_000_000)
 ap.add_argument("--bytes", type=int, default=1 << 30)
+ap.add_argument("--item-kib", type=int, default=32)
 a = ap.parse_args()
 chars, offsets, validity, nulls = c2_corpus(a.rows, a.bytes)
 col = nvstrings.from_offsets(chars, offsets, a.rows, validity, nulls)
 res = torch.empty(a.rows, dtype=torch.uint8, device="cuda")
 L = lib()
 L.custr_set_profiling(1)
+L.custr_set_item_kib(a.item_kib)
 tiers = [int(t) for t in a.tiers.split(",")]
 times = {t: [] for t in tiers}
 for rep in range(a.reps + 3):
