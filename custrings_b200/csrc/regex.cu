@@ -142,6 +142,7 @@ static const bits::ChainDev* span_plan(Compiled& c)
     return c.plan_contains ? bits::span_chain(*c.plan_contains) : nullptr;
 }
 
+// list capacity tier of the Pike-VM kernels; 0 = no in-thread tier fits: lists in the global scratch arena (Lists<0>)
 static int cap_tier(int ninsts)
 {
     if (ninsts <= 32) return 32;
@@ -149,6 +150,7 @@ static int cap_tier(int ninsts)
     if (ninsts <= 1024) return 1024;
     return 0;
 }
+constexpr int VM_MAX_INSTS = 65535;  // instruction ids are 16 bits in the lists
 
 // ---- kernels ---------------------------------------------------------------------------------------------
 constexpr int VM_THREADS = 128;
@@ -703,20 +705,49 @@ static inline int vm_grid(int n)
     return want < cap ? (want > 0 ? want : 1) : cap;
 }
 
+// Programs beyond the largest in-thread tier: the launch is bracketed by an arena of global scratch (one slice per resident
+// thread), the grid is capped so that the arena stays below 4 GiB, and the call is serialised (the arena descriptor is a
+// device global).  The reference sizes the same scratch per ROW (regexec.cpp:81-95).
+struct VmArenaLaunch {
+    BufPtr buf;
+    std::unique_lock<std::mutex> lock;
+    int nblocks = 0;
+};
+static VmArenaLaunch vm_arena_for(int ninsts, int want_blocks)
+{
+    static std::mutex mu;
+    VmArenaLaunch a;
+    a.lock = std::unique_lock<std::mutex>(mu);
+    const size_t per = (rxdev::vm_arena_bytes_per_thread(ninsts) + 15) & ~(size_t)15;
+    size_t threads = (size_t)want_blocks * VM_THREADS;
+    const size_t cap = ((size_t)4 << 30) / per;
+    if (threads > cap) threads = cap < VM_THREADS ? VM_THREADS : cap / VM_THREADS * VM_THREADS;
+    a.nblocks = (int)(threads / VM_THREADS);
+    a.buf = dev_alloc(per * threads);
+    rxdev::VmArena h{(uint8_t*)a.buf->ptr, per, ninsts};
+    CUSTR_CUDA(cudaMemcpyToSymbolAsync(rxdev::g_vm_arena, &h, sizeof(h), 0, cudaMemcpyHostToDevice, g_stream));
+    return a;
+}
 #define DISPATCH_CAP(cap, KERNEL, grid, smem, ...)                                         \
     do {                                                                                   \
         if ((cap) == 32) LAUNCH(KERNEL<32>, grid, VM_THREADS, smem, __VA_ARGS__);          \
         else if ((cap) == 256) LAUNCH(KERNEL<256>, grid, VM_THREADS, smem, __VA_ARGS__);   \
-        else LAUNCH(KERNEL<1024>, grid, VM_THREADS, smem, __VA_ARGS__);                    \
+        else if ((cap) == 1024) LAUNCH(KERNEL<1024>, grid, VM_THREADS, smem, __VA_ARGS__); \
+        else {                                                                             \
+            VmArenaLaunch arena__ = vm_arena_for(g_dispatch_ninsts, grid);                 \
+            LAUNCH(KERNEL<0>, arena__.nblocks, VM_THREADS, smem, __VA_ARGS__);                \
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));                                   \
+        }                                                                                  \
     } while (0)
+static thread_local int g_dispatch_ninsts = 0;  // instruction count of the program being dispatched (set by check_cap)
 
 static int check_cap(const Compiled& c, const char* who)
 {
-    int cap = cap_tier((int)c.prog.insts.size());
-    if (!cap)
-        throw ArgError{fail(CUSTR_ERR_INVALID, std::string(who) + ": number of instructions (" +
-                                                   std::to_string(c.prog.insts.size()) + ") exceeds available memory")};
-    return cap;
+    const int n = (int)c.prog.insts.size();
+    if (n > VM_MAX_INSTS)  // the reference's wording (count.cu:76-84), at a far larger limit
+        throw ArgError{fail(CUSTR_ERR_INVALID, std::string(who) + ": number of instructions (" + std::to_string(n) + ") exceeds available memory")};
+    g_dispatch_ninsts = n;
+    return cap_tier(n);
 }
 
 static int smem_for(const Compiled& c) { return (int)c.image.size() <= SMEM_PROG_MAX ? (int)((c.image.size() + 15) & ~15ull) : 0; }
@@ -859,8 +890,18 @@ static int bool_search(const custr_column* col, const char* pattern, uint8_t* re
     if (n == 0) return 0;
     CompiledPtr c = get_compiled(pattern);
     ResultBuf<uint8_t> out(results, n, devmem);
-    Scratch<unsigned long long> total(1);
-    CUSTR_CUDA(cudaMemsetAsync(total.get(), 0, 8, g_stream));
+    // match total of the paths that do not bring their own counter block (allocated and cleared on first use)
+    struct LazyTotal {
+        std::unique_ptr<Scratch<unsigned long long>> s;
+        unsigned long long* get()
+        {
+            if (!s) {
+                s.reset(new Scratch<unsigned long long>(1));
+                CUSTR_CUDA(cudaMemsetAsync(s->get(), 0, 8, g_stream));
+            }
+            return s->get();
+        }
+    } total;
     bool done = false;
     if (g_forced_tier != 1) {
         if (!c->plans_built) {
@@ -893,22 +934,29 @@ static int bool_search(const custr_column* col, const char* pattern, uint8_t* re
             int cap = cap_tier((int)c->prog.insts.size());
             int32_t* dirty_rows = nullptr;
             unsigned int* dirty_count = nullptr;
-            BufPtr keep_rows, keep_count;
+            // one zeroed 16-byte block: [match total u64][dirty-row count u32][work-item counter u32]
+            BufPtr keep_rows, keep_count = dev_alloc(16);
+            CUSTR_CUDA(cudaMemsetAsync(keep_count->ptr, 0, 16, g_stream));
+            unsigned long long* d_total = (unsigned long long*)keep_count->ptr;
             g_timer.start();
-            if (cap && bits::run(*plan, col, (const uint8_t*)c->dev_image->ptr, device_unicode_flags(), out.dev, total.get(), &dirty_rows,
+            if (cap && bits::run(*plan, col, (const uint8_t*)c->dev_image->ptr, device_unicode_flags(), out.dev, d_total, &dirty_rows,
                                  &dirty_count, keep_rows, keep_count)) {
-                // rows with non-ASCII / NUL bytes: exact VM over the work list (usually a few % of the rows)
-                int grid = vm_grid(n < 1 << 20 ? n : 1 << 20);
-                DISPATCH_CAP(cap, k_vm_bool_rows, grid, smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
-                             (int)c->image.size(), device_unicode_flags(), anchored ? 1 : 0, (const int32_t*)dirty_rows,
-                             (const unsigned int*)dirty_count, out.dev, total.get());
                 g_timer.stop();
                 g_last_tier = "bitstream";
                 done = true;
-                int matches = (int)read_counter(total.get());  // also keeps the work list alive until the kernels finish
+                struct { unsigned long long total; unsigned int dirty, items; } h{};
+                CUSTR_CUDA(cudaMemcpyAsync(&h, keep_count->ptr, 16, cudaMemcpyDeviceToHost, g_stream));
+                CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+                if (h.dirty) {  // rows holding a NUL byte: exact VM over the work list (rare: no launch at all otherwise)
+                    int grid = vm_grid(n < 1 << 20 ? n : 1 << 20);
+                    DISPATCH_CAP(cap, k_vm_bool_rows, grid, smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,
+                                 (int)c->image.size(), device_unicode_flags(), anchored ? 1 : 0, (const int32_t*)dirty_rows,
+                                 (const unsigned int*)dirty_count, out.dev, d_total);
+                    h.total = read_counter(d_total);
+                }
                 g_timer.collect();
                 out.finish();
-                return matches;
+                return (int)h.total;
             }
             g_timer.armed = false;
         }
@@ -1318,14 +1366,16 @@ custr_column* custr_replace_re_multi(const custr_column* col, const char* const*
             if (n == 0) return custr_create_from_offsets(nullptr, 0, nullptr, nullptr, 0, 0);
             std::vector<CompiledPtr> progs;
             std::vector<const uint8_t*> imgs;
-            int cap = 32;
+            int cap = 32, max_insts = 0;
             for (int t = 0; t < npatterns; ++t) {
                 if (!patterns[t]) throw ArgError{fail(CUSTR_ERR_INVALID, "replace_re: null pattern")};
                 progs.push_back(get_compiled(patterns[t]));
-                int k = check_cap(*progs.back(), "replace_re");
-                if (k > cap) cap = k;
+                check_cap(*progs.back(), "replace_re");
+                max_insts = std::max(max_insts, (int)progs.back()->prog.insts.size());
                 imgs.push_back((const uint8_t*)progs.back()->dev_image->ptr);
             }
+            cap = cap_tier(max_insts);  // one list size for all programs: the largest one's tier
+            g_dispatch_ninsts = max_insts;
             BufPtr d_imgs = upload(imgs.data(), imgs.size() * sizeof(void*));
             MultiProgs mp{(const uint8_t* const*)d_imgs->ptr, npatterns};
             Scratch<int32_t> lens((size_t)n + 1);

@@ -293,10 +293,17 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     if (counts) CUSTR_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n, g_stream));
     else if (!use_item) CUSTR_CUDA(cudaMemsetAsync(out, 0, (size_t)n, g_stream));
     keep_rows = dev_alloc(sizeof(int32_t) * (size_t)(n ? n : 1));
-    keep_count = dev_alloc(2 * sizeof(unsigned int));  // [0] dirty-row count, [1] work-item counter
-    CUSTR_CUDA(cudaMemsetAsync(keep_count->ptr, 0, 2 * sizeof(unsigned int), g_stream));
+    // counters: [0] dirty-row count, [1] work-item counter.  A caller may hand in a zeroed 16-byte block whose first 8 bytes
+    // are its match total (one allocation, one memset and one read-back per call instead of two of each)
+    unsigned int* counters;
+    if (keep_count && keep_count->bytes >= 16) counters = (unsigned int*)keep_count->ptr + 2;
+    else {
+        keep_count = dev_alloc(2 * sizeof(unsigned int));
+        CUSTR_CUDA(cudaMemsetAsync(keep_count->ptr, 0, 2 * sizeof(unsigned int), g_stream));
+        counters = (unsigned int*)keep_count->ptr;
+    }
     *dirty_rows = (int32_t*)keep_rows->ptr;
-    *dirty_count = (unsigned int*)keep_count->ptr;
+    *dirty_count = counters;
     if (col->nbytes == 0) return true;
     Args a;
     a.chars = col->chars;
@@ -311,7 +318,7 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     a.total = total;
     a.dirty_rows = *dirty_rows;
     a.dirty_count = *dirty_count;
-    a.item_counter = (unsigned int*)keep_count->ptr + 1;
+    a.item_counter = counters + 1;
     a.item_bounds = nullptr;
     a.prog_img = prog_img;
     a.uflags = uflags;

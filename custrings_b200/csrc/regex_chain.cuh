@@ -15,6 +15,7 @@
 struct LaneCtx {
     uint32_t lane, src;  // src = lane-1 (mod 32): source lane of an advance
     bool is31;
+    uint32_t m31;        // 1 in lane 31, else 0 (arithmetic select on the FMA pipe)
 };
 
 __device__ __forceinline__ uint32_t adv_rot(uint32_t x, uint32_t last_x, const LaneCtx& L)

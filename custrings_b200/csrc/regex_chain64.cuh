@@ -70,18 +70,48 @@ __device__ __forceinline__ uint32_t lo32(u64 x) { return (uint32_t)x; }
 __device__ __forceinline__ uint32_t hi32(u64 x) { return (uint32_t)(x >> 32); }
 __device__ __forceinline__ u64 mk64(uint32_t lo, uint32_t hi) { return ((u64)hi << 32) | lo; }
 
+// (hi << 1) | (lo >> 31) on the FMA pipe: hi * 2 + mulhi(lo, 2).  The ALU pipe (LOP3 / SHF / PRMT / ISETP, one warp
+// instruction every other cycle) is what bounds the chain kernels; IMAD / IMAD.HI issue on the FMA pipe, which idles.
+__device__ __forceinline__ uint32_t funnel1_fma(uint32_t lo, uint32_t hi)
+{
+#ifdef CUSTR_SHIFTS_ON_ALU
+    return __funnelshift_l(lo, hi, 1);
+#else
+    uint32_t t, r;
+    asm("mul.hi.u32 %0, %1, 2;" : "=r"(t) : "r"(lo));
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(r) : "r"(hi), "r"(t));
+    return r;
+#endif
+}
 // move every bit one position up; bit 0 of lane 0 comes from the previous window (top word kept in last_hi)
 __device__ __forceinline__ u64 adv64(u64 x, uint32_t last_hi, const LaneCtx& L)
 {
+#ifdef CUSTR_SHIFTS_ON_ALU
     uint32_t v = L.is31 ? last_hi : hi32(x);
+#else
+    // lane 31 hands the PREVIOUS window's top word to lane 0: v = hi + is31 * (last_hi - hi), an IMAD instead of a SEL
+    uint32_t v = hi32(x) + L.m31 * (last_hi - hi32(x));
+#endif
     uint32_t up = __shfl_sync(FULL, v, L.src);
-    return mk64(__funnelshift_l(up, lo32(x), 1), __funnelshift_l(lo32(x), hi32(x), 1));
+    return mk64(funnel1_fma(up, lo32(x)), funnel1_fma(lo32(x), hi32(x)));
+}
+// (lo >> 1) | (hi << 31), also on the FMA pipe: hi * 2^31 + mulhi(lo, 2^31)
+__device__ __forceinline__ uint32_t funnel1r_fma(uint32_t lo, uint32_t hi)
+{
+#ifdef CUSTR_SHIFTS_ON_ALU
+    return __funnelshift_r(lo, hi, 1);
+#else
+    uint32_t t, r;
+    asm("mul.hi.u32 %0, %1, 0x80000000;" : "=r"(t) : "r"(lo));
+    asm("mad.lo.u32 %0, %1, 0x80000000, %2;" : "=r"(r) : "r"(hi), "r"(t));
+    return r;
+#endif
 }
 __device__ __forceinline__ u64 shift_down64(u64 x, uint32_t next_bit, const LaneCtx& L)
 {
     uint32_t dn = __shfl_down_sync(FULL, lo32(x), 1);
     if (L.is31) dn = next_bit;
-    return mk64(__funnelshift_r(lo32(x), hi32(x), 1), __funnelshift_r(hi32(x), dn, 1));
+    return mk64(funnel1r_fma(lo32(x), hi32(x)), funnel1r_fma(hi32(x), dn));
 }
 // R[p] = Q[p] | (R[p-1] & K[p]) over the 2048 positions of the window; R[-1] = top bit of last_hi
 __device__ __forceinline__ u64 spread64(u64 q, u64 k, uint32_t last_hi, const LaneCtx& L)
@@ -418,6 +448,8 @@ k_chain64(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
     asm volatile("" : "+r"(L.lane));
     L.src = (L.lane + 31) & 31;
     L.is31 = L.lane == 31;
+    L.m31 = L.lane == 31 ? 1u : 0u;
+    asm volatile("" : "+r"(L.m31));
     const uint32_t lane = L.lane;
     uint32_t wb = (uint32_t)__cvta_generic_to_shared(&sm[threadIdx.x >> 5]);  // this warp's block
     uint32_t my0 = wb + ring_lane_offset(lane);                                // my chunk 0 in stage 0

@@ -69,7 +69,7 @@ __device__ __forceinline__ void ring_issue_item(uint32_t wr, const char* __restr
 }
 
 // x >> 1 with the bit behind the lane's word taken from `nxt` (low word of the next lane's / next window's stream word)
-__device__ __forceinline__ u64 shift_down64_nb(u64 x, uint32_t nxt) { return mk64(__funnelshift_r(lo32(x), hi32(x), 1), __funnelshift_r(hi32(x), nxt, 1)); }
+__device__ __forceinline__ u64 shift_down64_nb(u64 x, uint32_t nxt) { return mk64(funnel1r_fma(lo32(x), hi32(x)), funnel1r_fma(hi32(x), nxt)); }
 
 // Marker chain of one window.  Returns the stream of positions behind which a match may end, BEFORE the zero-width
 // assertions of END are applied.  UTF8 = false: the window holds ASCII bytes only (cont == 0, every byte is a character).
@@ -145,6 +145,8 @@ k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A
     asm volatile("" : "+r"(L.lane));
     L.src = (L.lane + 31) & 31;
     L.is31 = L.lane == 31;
+    L.m31 = L.lane == 31 ? 1u : 0u;
+    asm volatile("" : "+r"(L.m31));
     const uint32_t lane = L.lane;
     uint32_t wb = (uint32_t)__cvta_generic_to_shared(item_smem) + (threadIdx.x >> 5) * (uint32_t)sizeof(WarpSmItem);  // this warp's block
     uint32_t bits0 = wb + ITEM_SM_BITS;

@@ -96,6 +96,72 @@ struct Lists {
     }
 };
 
+// CAP == 0: programs with more instructions than the largest in-thread tier (1024).  The lists live in a global scratch
+// arena — one slice per RESIDENT thread, bound by init() from the arena registered for the launch (the reference allocates
+// 2 x Relist::alloc_size(insts) per ROW instead, regexec.cpp:81-95, count.cu:92-100).  Same operations, pointers instead of
+// arrays.  Device only.
+struct VmArena {
+    uint8_t* base;
+    unsigned long long stride;  // bytes per thread
+    int ninsts;
+};
+#ifdef __CUDACC__
+static __device__ VmArena g_vm_arena;  // per translation unit; only regex.cu's kernels (and its host code) use it
+#endif
+CUSTR_HD size_t vm_arena_bytes_per_thread(int ninsts)
+{
+    const size_t n = (size_t)((ninsts + 31) & ~31);
+    // per list: id u16[n] + beg i32[n] + endp i32[n] + mask u32[n/32]; two lists, two Lists objects (plain + group tracking)
+    return 2 * 2 * (2 * n + 4 * n + 4 * n + n / 8) + 64;
+}
+template <bool GROUPS>
+struct Lists<0, GROUPS> {
+    uint16_t* id[2];
+    int32_t* beg[2];
+    int32_t* endp[2];
+    uint32_t* mask[2];
+    int size[2];
+    int nwords;
+
+    CUSTR_HD void init()
+    {
+#ifdef __CUDA_ARCH__
+        const VmArena a = g_vm_arena;
+        const size_t n = (size_t)((a.ninsts + 31) & ~31);
+        const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        uint8_t* p = a.base + tid * a.stride + (GROUPS ? a.stride / 2 : 0);  // the two Lists objects of a thread get one half each
+        p = (uint8_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+        nwords = (int)(n / 32);
+        for (int k = 0; k < 2; ++k) {
+            beg[k] = (int32_t*)p; p += 4 * n;
+            endp[k] = (int32_t*)p; p += 4 * n;
+            mask[k] = (uint32_t*)p; p += n / 8;
+            id[k] = (uint16_t*)p; p += 2 * n;
+            for (int w = 0; w < nwords; ++w) mask[k][w] = 0;
+            size[k] = 0;
+        }
+#endif
+    }
+    CUSTR_HD void reset(int k)
+    {
+        for (int i = 0; i < size[k]; ++i) {
+            int v = id[k][i];
+            mask[k][v >> 5] &= ~(1u << (v & 31));
+        }
+        size[k] = 0;
+    }
+    CUSTR_HD void activate(int k, int inst, int b, int e = -1)
+    {
+        uint32_t bit = 1u << (inst & 31);
+        if (mask[k][inst >> 5] & bit) return;
+        mask[k][inst >> 5] |= bit;
+        id[k][size[k]] = (uint16_t)inst;
+        beg[k][size[k]] = b;
+        if (GROUPS) endp[k][size[k]] = e;
+        ++size[k];
+    }
+};
+
 // Search row bytes s[0..n) starting at byte offset `begin`; new threads are seeded at offset `off` only while
 // off < seed_limit (n for an unanchored search; begin+1 for "match only here": reference `end = begin+1`).
 // On success mbeg/mend are the byte offsets of the winning match.

@@ -75,6 +75,8 @@ k_tokenize64(const __grid_constant__ TokArgs A)
     asm volatile("" : "+r"(L.lane));
     L.src = (L.lane + 31) & 31;
     L.is31 = L.lane == 31;
+    L.m31 = L.lane == 31 ? 1u : 0u;
+    asm volatile("" : "+r"(L.m31));
     const uint32_t lane = L.lane;
     WarpSmTok& W = sm[threadIdx.x >> 5];
     uint32_t wb = (uint32_t)__cvta_generic_to_shared(&W);

@@ -174,3 +174,24 @@ def test_count_replace_span_streams(oracle):
             want = ref.replace_re(p, repl, mx).to_list()
             assert oracle.unpack(*dev.replace(p, repl, mx).to_arrays()) == want, (p, repl, mx, lib().custr_last_regex_tier())
     assert used >= 15 and counted >= 8, (used, counted)
+
+
+def test_large_programs_beyond_1024_instructions(oracle):
+    """Programs with more instructions than the largest in-thread list tier run from the global scratch arena (the reference
+    sizes global scratch per row for them, regexec.cpp:81-95): the 108 / 113-character patterns of the reference's
+    python/tests/test_regex.py:256-273 and patterns of 1100-3000 instructions, all checked against the oracle."""
+    from custrings_b200 import nvstrings
+    base = "hello @abc @def world The quick brown @fox jumps over the lazy @dog hello http://www.world.com I'm here @home"
+    rows = [base, "1234567890" * 11, "abcdefghijklmnopqrstuvwxyz" * 6, base + " zzzz", "", None, ("ab" * 700) + "c", "x" + "ab" * 1500 + "cd"]
+    dev = nvstrings.to_device(rows)
+    ref = oracle.RefStrings.from_list(rows)
+    pats = [base, base + " zzzz", "ab" * 600, "(ab){550}c", "a?" * 400 + "b" * 400, "[a-c]{1200}", "ab" * 1400 + "c?d"]
+    for p in pats:
+        want, _ = ref.contains_re(p)
+        assert dev.contains(p) == [None if r is None else bool(w) for r, w in zip(rows, want)], p[:40]
+        wantm, _ = ref.match(p)
+        assert dev.match(p) == [None if r is None else bool(w) for r, w in zip(rows, wantm)], p[:40]
+    for p in ("ab" * 600, "(ab){550}"):
+        wantc, _ = ref.count_re(p)
+        assert dev.count(p) == [None if r is None else int(w) for r, w in zip(rows, wantc)], p[:40]
+        assert oracle.unpack(*dev.replace(p, "#").to_arrays()) == oracle.unpack(*ref.replace_re(p, "#").to_arrays())
