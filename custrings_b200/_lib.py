@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcustr.so")
+LIB_PATH = os.environ.get("CUSTR_LIB") or os.path.join(_HERE, "libcustr.so")  # CUSTR_LIB: A/B variant builds (tools/build_variant.py)
 _lib = None
 
 vp, ci, cu, cp, cl = C.c_void_p, C.c_int, C.c_uint, C.c_char_p, C.c_longlong
@@ -24,6 +24,9 @@ _SIGNATURES = {
     "custr_last_regex_tier": (cp, []),
     "custr_set_regex_tier": (None, [ci]),
     "custr_set_item_kib": (None, [ci]),
+    "custr_set_jit": (None, [ci, cl]),
+    "custr_jit_launch_count": (cl, []),
+    "custr_jit_note": (cp, []),
     "custr_set_profiling": (None, [ci]),
     "custr_last_kernel_ms": (C.c_float, []),
     "custr_create_from_offsets": (vp, [vp, ci, vp, vp, ci, ci]),

@@ -18,7 +18,31 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 SOURCES = [("regex_bits.cu", [], None), ("regex_item.cu", ["-DITEM_NS_GROUP=0"], "regex_item_g0"), ("regex_item.cu", ["-DITEM_NS_GROUP=1"], "regex_item_g1"),
            ("regex_item.cu", ["-DITEM_NS_GROUP=2"], "regex_item_g2"), ("regex_item.cu", ["-DITEM_NS_GROUP=3"], "regex_item_g3"),
            ("regex.cu", [], None), ("column.cu", [], None), ("find.cu", [], None), ("split.cu", [], None), ("category.cu", [], None),
-           ("regex_bits_lower.cpp", [], None), ("regex_compile.cpp", [], None), ("classes.cpp", [], None)]
+           ("regex_jit.cu", [], None), ("regex_bits_lower.cpp", [], None), ("regex_compile.cpp", [], None), ("classes.cpp", [], None)]
+# kernel headers embedded into the library for the run-time compiled plan kernels (regex_jit.cu); "cstdint" / "cuda_runtime.h"
+# are stand-ins: NVRTC has no host headers
+JIT_HEADERS = ["device_utils.cuh", "regex_bits_plan.h", "regex_bits_dev.cuh", "regex_chain.cuh", "regex_chain64.cuh", "regex_chain_item.cuh"]
+JIT_STANDINS = {
+    "cstdint": "typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t; typedef unsigned short uint16_t; "
+               "typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t; "
+               "typedef unsigned long uintptr_t; typedef unsigned long size_t;\n",
+    "cuda_runtime.h": "\n",
+}
+
+
+def _embed_jit_headers():
+    out = os.path.join(OBJ, "jit_headers.inc")
+    srcs = [os.path.join(CSRC, h) for h in JIT_HEADERS]
+    if not _stale(out, srcs + [os.path.abspath(__file__)]):
+        return
+    parts = []
+    for name, text in list(JIT_STANDINS.items()) + [(h, open(os.path.join(CSRC, h)).read()) for h in JIT_HEADERS]:
+        chunks = [text[i:i + 8000] for i in range(0, len(text), 8000)] or [""]  # string literals have a length limit: concatenate
+        lit = "\n".join('R"CUSTRJIT(%s)CUSTRJIT"' % c for c in chunks)
+        parts.append('{"%s",\n%s},\n' % (name, lit))
+    with open(out, "w") as f:
+        f.write("".join(parts))
+
 
 
 def _stale(out, deps):
@@ -58,6 +82,7 @@ def build(verbose=False, force=False):
     if force:
         shutil.rmtree(OBJ)
         os.makedirs(OBJ)
+    _embed_jit_headers()
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s[0]))]
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose), srcs))

@@ -1034,12 +1034,22 @@ void custr_set_profiling(int on) { g_profile = on; }
 float custr_last_kernel_ms(void) { return g_last_kernel_ms; }
 // A/B: size of a work item of the chain / tokenize kernels in KiB (default 32)
 void custr_set_item_kib(int kib) { bits::g_item_bytes = (kib >= 8 && kib <= 1024 ? kib : 32) * 1024; }
+// run-time compiled plan kernels (regex_jit.cu): mode 0 never, 1 = large columns whose plan has no ahead-of-time shape
+// (default), 2 = always; min_bytes > 0 also sets the column size from which mode 1 compiles
+void custr_set_jit(int mode, long long min_bytes)
+{
+    bits::g_jit_mode = mode < 0 || mode > 2 ? 1 : mode;
+    if (min_bytes > 0) bits::g_jit_min_bytes = min_bytes;
+}
+long long custr_jit_launch_count(void) { return bits::g_jit_launches.load(); }
+const char* custr_jit_note(void) { return bits::jit_last_note(); }
 void custr_set_regex_tier(int tier)
 {
     g_forced_tier = tier == 1 ? 1 : 0;
     bits::g_force_generic = tier == 2;  // 2: bitstream tier, generic DAG interpreter even for chain-shaped plans
     bits::g_chain_win = tier == 3;      // 3: bitstream tier, window-at-a-time chain kernel (k_chain64) also for boolean results
-    bits::g_no_spec = tier == 4;        // 4: 64-bit chain kernel without the shape specialisations
+    bits::g_no_spec = tier == 4 || tier == 5;  // 4: no ahead-of-time shape specialisation (the plan's run-time compiled kernel instead, when available)
+    bits::g_no_jit = tier == 5;                // 5: neither: the generic ahead-of-time kernels that interpret the plan
 }
 
 int custr_regex_describe(const char* pattern, char* buf, size_t buflen)

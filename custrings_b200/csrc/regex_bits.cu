@@ -255,6 +255,10 @@ void launch_chain_item_g0(const ChainDev& cd, const Args& a, int blocks);
 void launch_chain_item_g1(const ChainDev& cd, const Args& a, int blocks);
 void launch_chain_item_g2(const ChainDev& cd, const Args& a, int blocks);
 void launch_chain_item_g3(const ChainDev& cd, const Args& a, int blocks);
+bool jit_launch_chain_item(const ChainDev& cd, const Args& a, int blocks);  // regex_jit.cu
+std::atomic<long long> g_jit_launches{0};
+thread_local bool g_no_jit = false;        // A/B switch (tier 5): ahead-of-time kernels only
+long long g_jit_min_bytes = 64ll << 20;    // smallest column (bytes of chars) that is worth a run-time compilation
 static void launch_chain_item(const ChainDev& cd, const Args& a, int blocks)
 {
     if (cd.nsteps <= 2) launch_chain_item_g0(cd, a, blocks);
@@ -346,8 +350,18 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
         a.item_bounds = ensure_item_bounds(col, a.offsets, a.first, a.nitems);  // once per column (it is immutable)
         const int resident = num_sms() * 3;
         if (blocks > resident) blocks = resident;
-        if (use_item) launch_chain_item(plan.chain, a, blocks);
-        else launch_chain64(plan.chain, a, blocks);
+        if (use_item) {
+            // the plan's own run-time compiled kernel (regex_jit.cu) when no ahead-of-time shape covers the plan and the
+            // column is large enough to repay ~0.6 s of NVRTC on first use; else / on any failure the ahead-of-time kernels
+            const ChainDev& cd = plan.chain;
+            bool plain = true;
+            for (uint32_t s = 0; s < cd.nsteps; ++s) plain = plain && !cd.steps[s].opt && ((cd.steps[s].exit != 0) == (s + 1 == cd.nsteps));
+            const bool aot_shape = !g_no_spec && plain && cd.nsteps <= 4 && chain_spec_of(cd) != 0;
+            const bool want_jit = !g_no_jit && (g_jit_mode == 2 || (g_jit_mode == 1 && !aot_shape && col->nbytes >= (int64_t)g_jit_min_bytes));
+            if (want_jit && jit_launch_chain_item(cd, a, blocks)) g_jit_launches.fetch_add(1, std::memory_order_relaxed);
+            else launch_chain_item(cd, a, blocks);
+        } else
+            launch_chain64(plan.chain, a, blocks);
         return true;
     }
 #ifndef CUSTR_EXPERIMENT_ONLY_4_1

@@ -47,6 +47,11 @@ extern thread_local bool g_force_generic;
 extern thread_local bool g_no_spec;
 extern thread_local bool g_chain_win;
 extern int g_item_bytes;
+extern thread_local bool g_no_jit;
+extern int g_jit_mode;               // 0 never, 1 large columns without an ahead-of-time shape (default), 2 always
+extern long long g_jit_min_bytes;
+extern std::atomic<long long> g_jit_launches;
+const char* jit_last_note();
 
 // Non-null when the plan is a linear chain whose only loop is its last step: for those patterns the match SPAN the Pike VM
 // reports (leftmost start, then thread priority) is "leftmost start, longest end that satisfies the trailing assertion",

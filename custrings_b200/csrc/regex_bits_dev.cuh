@@ -82,12 +82,28 @@ __device__ __forceinline__ void transpose_planes(const uint4& lo, const uint4& h
     uint32_t b0 = lo.y, b1 = lo.w, b2 = hi.y, b3 = hi.w;  // words 1,3,5,7 -> y = 4..7
     uint32_t t0 = __byte_perm(a0, a1, 0x5140), t1 = __byte_perm(a0, a1, 0x7362);
     uint32_t t2 = __byte_perm(a2, a3, 0x5140), t3 = __byte_perm(a2, a3, 0x7362);
-    p[0] = __byte_perm(t0, t2, 0x5410); p[1] = __byte_perm(t0, t2, 0x7632);
-    p[2] = __byte_perm(t1, t3, 0x5410); p[3] = __byte_perm(t1, t3, 0x7632);
+    // second level (16-bit halves of two words exchanged): lo = lo16(x) | y << 16, hi = x >> 16 | hi16(y) << 16: two PRMT.
+    // -DCUSTR_HALFSWAP_FMA does it as 5 instructions on the FMA pipe (with h = x >> 16: lo = x + (y - h) * 65536 mod 2^32,
+    // hi = h + (y >> 16) * 65536): measured slower (0.345 vs 0.339 ms on C2), the kernel is short of issue slots, not only of
+    // ALU slots
+#ifndef CUSTR_HALFSWAP_FMA
+#define HALF_SWAP(X, Y, LO, HI) { LO = __byte_perm(X, Y, 0x5410); HI = __byte_perm(X, Y, 0x7632); }
+#else
+#define HALF_SWAP(X, Y, LO, HI)                                                                  \
+    {                                                                                            \
+        uint32_t h_, d_, yh_;                                                                    \
+        asm("mul.hi.u32 %0, %1, 65536;" : "=r"(h_) : "r"(X));                                    \
+        asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(d_) : "r"(h_), "r"(Y));                  \
+        asm("mul.hi.u32 %0, %1, 65536;" : "=r"(yh_) : "r"(Y));                                   \
+        asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(LO) : "r"(d_), "r"(X));                       \
+        asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(HI) : "r"(yh_), "r"(h_));                     \
+    }
+#endif
+    HALF_SWAP(t0, t2, p[0], p[1]) HALF_SWAP(t1, t3, p[2], p[3])
     t0 = __byte_perm(b0, b1, 0x5140); t1 = __byte_perm(b0, b1, 0x7362);
     t2 = __byte_perm(b2, b3, 0x5140); t3 = __byte_perm(b2, b3, 0x7362);
-    p[4] = __byte_perm(t0, t2, 0x5410); p[5] = __byte_perm(t0, t2, 0x7632);
-    p[6] = __byte_perm(t1, t3, 0x5410); p[7] = __byte_perm(t1, t3, 0x7632);
+    HALF_SWAP(t0, t2, p[4], p[5]) HALF_SWAP(t1, t3, p[6], p[7])
+#undef HALF_SWAP
     // one delta swap = 2 shifts + 2 bit-selects: (a & m) | (x & ~m) is a single LOP3 (LUT 0xE2) — ptxas does not
     // find it on its own when m and ~m are both immediates
 #define DELTA_SWAP(A, B, S, M)                                                                              \

@@ -68,12 +68,17 @@ __device__ __forceinline__ bool na_char_matches(const ChainClassD& cd, const Arg
     switch (cd.na_kind) {
     case NA_ALWAYS: return true;
     case NA_CHAR_EQ: return ch == cd.na_arg;
+#ifdef CUSTR_JIT  // run-time compiled kernels are only built for plans whose classes carry their inline definition
+    case NA_CLASS: return na_class_inline(cd, A.uflags, ch);
+    case NA_NCLASS: return !na_class_inline(cd, A.uflags, ch);
+#else
     case NA_CLASS:
         return cd.na_inline ? na_class_inline(cd, A.uflags, ch)
                             : rxdev::class_match(rxdev::bind_program(A.prog_img, A.uflags), (int)cd.na_arg, ch);
     case NA_NCLASS:
         return !(cd.na_inline ? na_class_inline(cd, A.uflags, ch)
                               : rxdev::class_match(rxdev::bind_program(A.prog_img, A.uflags), (int)cd.na_arg, ch));
+#endif
     default: return false;
     }
 }

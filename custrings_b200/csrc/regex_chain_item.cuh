@@ -134,9 +134,8 @@ static __device__ __noinline__ uint32_t item_dirty_row(const Args& A, bool in, i
     return dirty ? 0u : hit;
 }
 
-template <int NS, int NCLS, int SPEC = 0>
-__global__ void __launch_bounds__(THREADS, 3)
-k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
+template <int NS, int NCLS, int SPEC>
+__device__ __forceinline__ void chain_item_body(const ChainDev& cd, const Args& A)
 {
     using PL = PlanLit<SPEC>;
     extern __shared__ __align__(128) unsigned char item_smem[];
@@ -163,14 +162,36 @@ k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A
     asm volatile("" : "+r"(top31));
     uint32_t cnt = 0;  // rows with a match finalised by this lane
 
+    // Work items are handed out dynamically (one atomicAdd each).  The NEXT item's index, row bounds and byte bounds are
+    // fetched while the current item is being processed (the chain atomic -> item_bounds -> offsets is three dependent
+    // memory latencies, ~7 % of an item's time when it sits at the top of the item)
+    int nxt_item = 0, nxt_ra = 0, nxt_rb = 0, nxt_ba = 0, nxt_bb = 0;
+    if (lane == 0) nxt_item = (int)atomicAdd(A.item_counter, 1u);
+    nxt_item = __shfl_sync(FULL, nxt_item, 0);
+    if (nxt_item < A.nitems) {
+        nxt_ra = __ldg(A.item_bounds + nxt_item);
+        nxt_rb = __ldg(A.item_bounds + nxt_item + 1);
+        nxt_ba = __ldg(A.offsets + nxt_ra);
+        nxt_bb = __ldg(A.offsets + nxt_rb);
+    }
     for (;;) {
-        int item = 0;
-        if (lane == 0) item = (int)atomicAdd(A.item_counter, 1u);
-        item = __shfl_sync(FULL, item, 0);
+        const int item = nxt_item;
         if (item >= A.nitems) break;
-        const int ra = __ldg(A.item_bounds + item), rb = __ldg(A.item_bounds + item + 1);
-        if (ra >= rb) continue;
-        const int byte_a = __ldg(A.offsets + ra), byte_b = __ldg(A.offsets + rb);
+        const int ra = nxt_ra, rb = nxt_rb;
+        const int byte_a = nxt_ba, byte_b = nxt_bb;
+        int fetched = 0;  // lane 0: index of the item after this one (requested now, looked at after phase 0)
+        if (lane == 0) fetched = (int)atomicAdd(A.item_counter, 1u);
+        int prefetch_stage = 0;  // 0: index requested, 1: row bounds requested, 2: byte bounds requested
+        if (ra >= rb) {  // no rows (cannot happen with the item index of k_item_bounds, kept for safety): just move on
+            nxt_item = __shfl_sync(FULL, fetched, 0);
+            if (nxt_item < A.nitems) {
+                nxt_ra = __ldg(A.item_bounds + nxt_item);
+                nxt_rb = __ldg(A.item_bounds + nxt_item + 1);
+                nxt_ba = __ldg(A.offsets + nxt_ra);
+                nxt_bb = __ldg(A.offsets + nxt_rb);
+            }
+            continue;
+        }
         // (an item that holds only empty rows runs the segment loop once with no window: phase B writes its zeros.  A separate
         // loop + `continue` here makes ptxas give up structured reconvergence for the whole kernel: BRA.DIV guards everywhere)
         const bool empty_item = byte_a >= byte_b;
@@ -201,18 +222,32 @@ k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A
             for (uint32_t i = 2u * lane; i <= 32u * (uint32_t)nw; i += 64u)
                 asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(bits0 + 8u * i), "r"(0u) : "memory");
             __syncwarp();
-            for (;;) {  // two rows per lane and step; rel = 0xffffffff marks "no such row" (a real one is < 2^31)
-                const int j = krs + (int)lane;
-                uint32_t rel0 = 0xffffffffu, rel1 = 0xffffffffu;
-                if (j <= rb) rel0 = (uint32_t)__ldg(A.offsets + j) - seg_ws;
-                if (j + 32 <= rb) rel1 = (uint32_t)__ldg(A.offsets + j + 32) - seg_ws;
-                if (rel0 <= span) reds_or(bits0 + ((rel0 >> 3) & ~3u), 1u << (rel0 & 31));
-                if (rel1 <= span) reds_or(bits0 + ((rel1 >> 3) & ~3u), 1u << (rel1 & 31));
-                const unsigned m0 = __ballot_sync(FULL, rel0 < span), m1 = __ballot_sync(FULL, rel1 < span);
-                krs += __popc(m0) + __popc(m1);
-                if (m1 != FULL) break;
+            {   // two rows per lane and step; the next step's offsets are in flight while this one is scattered;
+                // rel = 0xffffffff marks "no such row" (a real one is < 2^31)
+                int j = krs + (int)lane;
+                int oa = j <= rb ? __ldg(A.offsets + j) : 0, ob = j + 32 <= rb ? __ldg(A.offsets + j + 32) : 0;
+                for (;;) {
+                    const int na = j + 64 <= rb ? __ldg(A.offsets + j + 64) : 0, nb = j + 96 <= rb ? __ldg(A.offsets + j + 96) : 0;
+                    const uint32_t rel0 = j <= rb ? (uint32_t)oa - seg_ws : 0xffffffffu, rel1 = j + 32 <= rb ? (uint32_t)ob - seg_ws : 0xffffffffu;
+                    if (rel0 <= span) reds_or(bits0 + ((rel0 >> 3) & ~3u), 1u << (rel0 & 31));
+                    if (rel1 <= span) reds_or(bits0 + ((rel1 >> 3) & ~3u), 1u << (rel1 & 31));
+                    const unsigned m0 = __ballot_sync(FULL, rel0 < span), m1 = __ballot_sync(FULL, rel1 < span);
+                    krs += __popc(m0) + __popc(m1);
+                    if (m1 != FULL) break;
+                    j += 64;
+                    oa = na;
+                    ob = nb;
+                }
             }
             __syncwarp();
+            if (prefetch_stage == 0) {  // the next item's index has arrived by now: request its row bounds
+                nxt_item = __shfl_sync(FULL, fetched, 0);
+                if (nxt_item < A.nitems) {
+                    nxt_ra = __ldg(A.item_bounds + nxt_item);
+                    nxt_rb = __ldg(A.item_bounds + nxt_item + 1);
+                }
+                prefetch_stage = 1;
+            }
 
             // ---- phase A: the windows of the segment
             for (int w = 0; w < nw; ++w, ws += WIN64, stage ^= 1u) {
@@ -248,6 +283,8 @@ k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A
                 if (bneed & (1u << AK_SPACE)) space = cls_space(p);
                 NaClasses<NCLS> nc;
                 u64 (&c)[NCLS] = nc.c;
+                if constexpr (PL::jit) classes_literal64<PL, NCLS>(c, p, letter5, digit, alnum, word, space);
+                else
 #pragma unroll
                 for (int k = 0; k < NCLS; ++k) {
                     u64 v = 0;
@@ -332,35 +369,42 @@ k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A
             }
 
             // ---- phase B: the rows that end inside the segment
+            if (prefetch_stage == 1) {  // ... and now its byte bounds (they are back when phase B is through)
+                if (nxt_item < A.nitems) {
+                    nxt_ba = __ldg(A.offsets + nxt_ra);
+                    nxt_bb = __ldg(A.offsets + nxt_rb);
+                }
+                prefetch_stage = 2;
+            }
             const bool item_dirty = __any_sync(FULL, zacc != 0);
-            for (;;) {  // two rows per lane and step
-                const int j = kfin + (int)lane;
+            {   // two rows per lane and step, the next step's offsets in flight
+                int j = kfin + (int)lane;
                 int oa0 = 0, oa1 = 0, ob0 = 0, ob1 = 0;
-                uint32_t rela = 0xffffffffu, relb = 0xffffffffu;  // (end of the row) - (segment start); 0xffffffff: no such row
-                if (j < rb) {
-                    oa0 = __ldg(A.offsets + j);
-                    oa1 = __ldg(A.offsets + j + 1);
-                    rela = (uint32_t)oa1 - seg_ws;
+                if (j < rb) { oa0 = __ldg(A.offsets + j); oa1 = __ldg(A.offsets + j + 1); }
+                if (j + 32 < rb) { ob0 = __ldg(A.offsets + j + 32); ob1 = __ldg(A.offsets + j + 33); }
+                for (;;) {
+                    int na0 = 0, na1 = 0, nb0 = 0, nb1 = 0;
+                    if (j + 64 < rb) { na0 = __ldg(A.offsets + j + 64); na1 = __ldg(A.offsets + j + 65); }
+                    if (j + 96 < rb) { nb0 = __ldg(A.offsets + j + 96); nb1 = __ldg(A.offsets + j + 97); }
+                    // (end of the row) - (segment start); 0xffffffff: no such row
+                    const uint32_t rela = j < rb ? (uint32_t)oa1 - seg_ws : 0xffffffffu, relb = j + 32 < rb ? (uint32_t)ob1 - seg_ws : 0xffffffffu;
+                    const bool ina = rela <= span, inb = relb <= span;
+                    uint32_t hita = 0, hitb = 0;
+                    if (ina && oa1 > oa0) hita = (lds32(bits0 + (((rela - 1u) >> 3) & ~3u)) >> ((rela - 1u) & 31)) & 1u;
+                    if (inb && ob1 > ob0) hitb = (lds32(bits0 + (((relb - 1u) >> 3) & ~3u)) >> ((relb - 1u) & 31)) & 1u;
+                    if (__builtin_expect(item_dirty, 0)) {  // a NUL byte somewhere in this item: rows holding one go to the exact VM
+                        hita = item_dirty_row(A, ina, oa0, oa1, j, hita, lane);
+                        hitb = item_dirty_row(A, inb, ob0, ob1, j + 32, hitb, lane);
+                    }
+                    if (ina) A.out[j] = (uint8_t)hita;
+                    if (inb) A.out[j + 32] = (uint8_t)hitb;
+                    cnt += hita + hitb;
+                    const unsigned ma = __ballot_sync(FULL, ina), mb = __ballot_sync(FULL, inb);
+                    kfin += __popc(ma) + __popc(mb);
+                    if (mb != FULL) break;
+                    j += 64;
+                    oa0 = na0; oa1 = na1; ob0 = nb0; ob1 = nb1;
                 }
-                if (j + 32 < rb) {
-                    ob0 = __ldg(A.offsets + j + 32);
-                    ob1 = __ldg(A.offsets + j + 33);
-                    relb = (uint32_t)ob1 - seg_ws;
-                }
-                const bool ina = rela <= span, inb = relb <= span;
-                uint32_t hita = 0, hitb = 0;
-                if (ina && oa1 > oa0) hita = (lds32(bits0 + (((rela - 1u) >> 3) & ~3u)) >> ((rela - 1u) & 31)) & 1u;
-                if (inb && ob1 > ob0) hitb = (lds32(bits0 + (((relb - 1u) >> 3) & ~3u)) >> ((relb - 1u) & 31)) & 1u;
-                if (__builtin_expect(item_dirty, 0)) {  // a NUL byte somewhere in this item: rows holding one go to the exact VM
-                    hita = item_dirty_row(A, ina, oa0, oa1, j, hita, lane);
-                    hitb = item_dirty_row(A, inb, ob0, ob1, j + 32, hitb, lane);
-                }
-                if (ina) A.out[j] = (uint8_t)hita;
-                if (inb) A.out[j + 32] = (uint8_t)hitb;
-                cnt += hita + hitb;
-                const unsigned ma = __ballot_sync(FULL, ina), mb = __ballot_sync(FULL, inb);
-                kfin += __popc(ma) + __popc(mb);
-                if (mb != FULL) break;
             }
             wins_left -= nw;
             __syncwarp();
@@ -370,7 +414,21 @@ k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A
     if (lane == 0 && cnt) atomicAdd(A.total, (unsigned long long)cnt);
 }
 
-#ifndef ITEM_EXPERIMENT
+template <int NS, int NCLS, int SPEC = 0>
+__global__ void __launch_bounds__(THREADS, 3)
+k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
+{
+    chain_item_body<NS, NCLS, SPEC>(cd, A);
+}
+#ifdef CUSTR_JIT  // the one kernel of a run-time compiled module (regex_jit.cpp): the plan's own view, PlanLit<100>
+extern "C" __global__ void __launch_bounds__(THREADS, 3)
+custr_jit_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
+{
+    chain_item_body<CUSTR_JIT_NS, CUSTR_JIT_NCLS, 100>(cd, A);
+}
+#endif
+
+#if !defined(ITEM_EXPERIMENT) && !defined(CUSTR_JIT) && !defined(CUSTR_NO_ITEM_LAUNCHERS)
 template <int NS>
 static void launch_item_ns(const ChainDev& cd, const Args& a, int blocks)
 {
@@ -405,7 +463,7 @@ static void launch_item_ns(const ChainDev& cd, const Args& a, int blocks)
     else ITEM_LAUNCH((k_chain_item<NS, 8, 0>));
 #undef ITEM_LAUNCH
 }
-#else
+#elif !defined(CUSTR_JIT) && !defined(CUSTR_NO_ITEM_LAUNCHERS)
 template <int NS>
 static void launch_item_ns(const ChainDev&, const Args&, int) {}
 #endif

@@ -47,8 +47,14 @@ long long custr_launch_count(void);
 const char* custr_last_regex_tier(void);
 /* force a tier for A/B testing: 0 = auto, 1 = exact Pike VM only, 2 = bitstream generic interpreter kernel,
  * 3 = boolean results from the window-at-a-time chain kernel (k_chain64) instead of the item-buffered one,
- * 4 = chain kernels without the shape specialisations */
+ * 4 = no ahead-of-time shape specialisation (run-time compiled plan kernel when available), 5 = neither (generic kernels) */
 void custr_set_regex_tier(int tier);
+/* Run-time compiled plan kernels: the chain kernel specialised for the pattern at hand with NVRTC (about 0.6 s on first use,
+ * cached per process).  mode 0 = never, 1 = for columns of at least min_bytes chars whose plan no ahead-of-time shape covers
+ * (default, 64 MiB), 2 = always.  min_bytes <= 0 keeps the current threshold.  Without libnvrtc the ahead-of-time kernels run. */
+void custr_set_jit(int mode, long long min_bytes);
+long long custr_jit_launch_count(void);   /* launches served by run-time compiled kernels so far */
+const char* custr_jit_note(void);         /* why the last request on this thread was not served ("" if it was) */
 /* tuning / A-B switch: size of a work item of the chain and tokenize kernels in KiB of chars (default 32) */
 void custr_set_item_kib(int kib);
 /* when on, regex calls bracket their dominant kernel(s) with CUDA events on the launch stream;

@@ -195,3 +195,30 @@ def test_large_programs_beyond_1024_instructions(oracle):
         wantc, _ = ref.count_re(p)
         assert dev.count(p) == [None if r is None else int(w) for r, w in zip(rows, wantc)], p[:40]
         assert oracle.unpack(*dev.replace(p, "#").to_arrays()) == oracle.unpack(*ref.replace_re(p, "#").to_arrays())
+
+
+def test_runtime_compiled_plan_kernels(cols):
+    """regex_jit.cu: the chain kernel compiled at run time (NVRTC) with every flag / class atom of the plan as a literal must give
+    exactly what the ahead-of-time kernels and the oracle give — literals, classes with ranges and negation, assertions,
+    optional steps / early exits, anchored search (match), multi-class chains."""
+    L = lib()
+    pats = [r"\b\w{4,}\b", r"\d+", "Sun", r"[a-f]{3}\b", r"^\w{8}", r"z\w*$", r"colou?r", r"\d{1,3}", r"[^a-z ]+", r"q[aeiou]\w+", "é",
+            r"\s[A-Z]\w", r"war(n|ning)?", r"\bthe\b", r"a.c", r"x?y?z"]
+    before = L.custr_jit_launch_count()
+    served = 0
+    strs, dev, ref = cols
+    try:
+        for p in pats:
+            L.custr_set_jit(0, 0)
+            want_c, want_m = dev.contains(p), dev.match(p)
+            L.custr_set_jit(2, 0)
+            n0 = L.custr_jit_launch_count()
+            got_c, got_m = dev.contains(p), dev.match(p)
+            served += L.custr_jit_launch_count() > n0
+            assert got_c == want_c and got_m == want_m, (p, L.custr_jit_note())
+            rc, _ = ref.contains_re(p)
+            assert got_c == [None if g is None else bool(w) for g, w in zip(got_c, rc)], p
+    finally:
+        L.custr_set_jit(1, 0)
+    # (patterns that do not lower to a chain — nested alternations — never reach the chain kernels)
+    assert L.custr_jit_launch_count() > before and served >= 10, (served, L.custr_jit_note().decode())

@@ -19,6 +19,7 @@ ap.add_argument("--reps", type=int, default=30)
 ap.add_argument("--rows", type=int, default=10_000_000)
 ap.add_argument("--bytes", type=int, default=1 << 30)
 ap.add_argument("--item-kib", type=int, default=32)
+ap.add_argument("--jit", type=int, default=1, help="0 never, 1 default policy, 2 always")
 a = ap.parse_args()
 chars, offsets, validity, nulls = c2_corpus(a.rows, a.bytes)
 col = nvstrings.from_offsets(chars, offsets, a.rows, validity, nulls)
@@ -26,6 +27,7 @@ res = torch.empty(a.rows, dtype=torch.uint8, device="cuda")
 L = lib()
 L.custr_set_profiling(1)
 L.custr_set_item_kib(a.item_kib)
+L.custr_set_jit(a.jit, 0)
 tiers = [int(t) for t in a.tiers.split(",")]
 times = {t: [] for t in tiers}
 for rep in range(a.reps + 3):
@@ -37,3 +39,4 @@ for rep in range(a.reps + 3):
 L.custr_set_regex_tier(0)
 for t in tiers:
     print("tier %d: median %.4f ms  min %.4f ms  (matches %d)" % (t, float(np.median(times[t])), min(times[t]), m))
+print("jit launches", L.custr_jit_launch_count(), "| note:", L.custr_jit_note().decode())
