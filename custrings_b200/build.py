@@ -91,7 +91,30 @@ def build(verbose=False, force=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    _build_pyni()
     return LIB
+
+
+def _build_pyni():
+    """CPython extension modules pyniNVStrings / pyniNVCategory / pyniNVText (custrings_b200/pyni/): the reference's binding
+    layer for the hot path, over libcustr.so's C-ABI.  Plain g++ against this interpreter's Python.h."""
+    import sysconfig
+    inc = sysconfig.get_paths()["include"]
+    if not os.path.exists(os.path.join(inc, "Python.h")):
+        sys.stderr.write("custrings_b200.build: Python.h not found, pyni modules not built\n")
+        return
+    pdir = os.path.join(HERE, "pyni")
+    cxx = shutil.which("g++") or "g++"
+    for src, mod in (("pystrings.cpp", "pyniNVStrings"), ("pycategory.cpp", "pyniNVCategory"), ("pytext.cpp", "pyniNVText")):
+        out = os.path.join(pdir, mod + ".so")
+        deps = [os.path.join(pdir, src), os.path.join(pdir, "pyni_common.h"), os.path.join(ROOT, "include", "custr.h")]
+        if not _stale(out, deps):
+            continue
+        cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-I", inc, os.path.join(pdir, src), "-o", out, "-L", HERE, "-lcustr",
+               "-Wl,-rpath,$ORIGIN/.."]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("pyni build failed for %s:\n%s" % (src, r.stderr))
 
 
 if __name__ == "__main__":

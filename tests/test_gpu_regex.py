@@ -201,6 +201,7 @@ def test_runtime_compiled_plan_kernels(cols):
     """regex_jit.cu: the chain kernel compiled at run time (NVRTC) with every flag / class atom of the plan as a literal must give
     exactly what the ahead-of-time kernels and the oracle give — literals, classes with ranges and negation, assertions,
     optional steps / early exits, anchored search (match), multi-class chains."""
+    from custrings_b200._lib import lib
     L = lib()
     pats = [r"\b\w{4,}\b", r"\d+", "Sun", r"[a-f]{3}\b", r"^\w{8}", r"z\w*$", r"colou?r", r"\d{1,3}", r"[^a-z ]+", r"q[aeiou]\w+", "é",
             r"\s[A-Z]\w", r"war(n|ning)?", r"\bthe\b", r"a.c", r"x?y?z"]
