@@ -83,6 +83,9 @@ _SIGNATURES = {
     "custr_category_values_cptr": (vp, [vp]),
     "custr_category_remap_to_union": (vp, [vp, vp]),
     "custr_category_merge": (vp, [vp, ci, ci]),
+    "custr_category_keys_op": (vp, [vp, vp, ci]),
+    "custr_category_gather": (vp, [vp, vp, ci, ci, ci]),
+    "custr_category_gather_strings": (vp, [vp, vp, ci, ci]),
     "custr_comm_unique_id": (ci, [vp]),
     "custr_comm_create": (vp, [ci, ci, vp]),
     "custr_comm_destroy": (None, [vp]),

@@ -225,7 +225,16 @@ __global__ void k_lookup_keys(ColView local, ColView global, int32_t* __restrict
 __global__ void k_remap_values(const int32_t* __restrict__ in, const int32_t* __restrict__ map, int n, int32_t* __restrict__ out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = map[in[i]];
+    if (i < n) out[i] = in[i] < 0 ? in[i] : map[in[i]];  // -1 = "no key" (after remove_keys / set_keys) stays -1
+}
+// used[v] = 1 for every value v in [0, k); *bad counts the values outside [lo, k)
+__global__ void k_mark_used(const int32_t* __restrict__ vals, int n, int k, int lo, uint8_t* __restrict__ used, int* __restrict__ bad)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int v = vals[i];
+    if (v < lo || v >= k) atomicAdd(bad, 1);
+    else if (v >= 0 && used) used[v] = 1;
 }
 
 // byte length of every key, -1 for the null key (payload of the sharded key exchange)
@@ -552,6 +561,186 @@ custr_category* custr_category_merge(const custr_category* const* cats, int32_t 
         },
         (custr_category*)nullptr, (custr_category*)nullptr);
 }
+}  // extern "C"
+
+// ---- key-set algebra on an existing category: add_keys_and_remap NVCategory.cu:1375-1480,
+//      remove_keys_and_remap :1482-1565, remove_unused_keys_and_remap :1567-1706, set_keys_and_remap :1708-1820, gather :1142,
+//      gather_and_remap :1084, gather_strings :1011.  Key sets are dictionary-sized: their bookkeeping runs on the host, only the
+//      remap of the n values is a device pass.
+namespace {
+using CatPtr = std::unique_ptr<custr_category, void (*)(custr_category*)>;
+CatPtr own(custr_category* c) { return CatPtr(c, [](custr_category* x) { custr_category_free(x); }); }
+std::vector<int32_t> to_host32(const void* dev, size_t n)
+{
+    std::vector<int32_t> h(n);
+    if (n) {
+        CUSTR_CUDA(cudaMemcpyAsync(h.data(), dev, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, g_stream));
+        CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    }
+    return h;
+}
+// index of every row of `keys` in the sorted distinct column `sorted` (-1: absent)
+std::vector<int32_t> lookup_host(const custr_column* keys, const custr_column* sorted)
+{
+    const int32_t k = keys->n;
+    if (!k) return {};
+    Scratch<int32_t> map((size_t)k);
+    LAUNCH(k_lookup_keys, (k + 255) / 256, 256, 0, view_of(keys), view_of(sorted), map.get());
+    return to_host32(map.get(), (size_t)k);
+}
+custr_category* with_keys_and_map(const custr_category* cat, custr_column* new_keys, const std::vector<int32_t>& map)
+{
+    custr_category* out = new custr_category;
+    out->keys = new_keys;
+    out->n = cat->n;
+    out->has_null_key = new_keys && new_keys->nulls > 0;
+    out->values_buf = dev_alloc(sizeof(int32_t) * (size_t)(cat->n ? cat->n : 1));
+    if (cat->n) {
+        BufPtr d_map = upload(map.empty() ? (const void*)&cat->n : (const void*)map.data(), sizeof(int32_t) * (map.empty() ? 1 : map.size()));
+        LAUNCH(k_remap_values, (cat->n + 255) / 256, 256, 0, (const int32_t*)cat->values_buf->ptr, (const int32_t*)d_map->ptr, cat->n,
+               (int32_t*)out->values_buf->ptr);
+        CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    }
+    return out;
+}
+// keys of `cat` in sorted order minus the flagged ones -> new category (values of dropped keys become -1)
+custr_category* drop_keys(const custr_category* cat, const custr_category* sorted_self, const std::vector<uint8_t>& drop_rank)
+{
+    const int32_t k = cat->keys->n;
+    const std::vector<int32_t> rank = to_host32(sorted_self->values_buf->ptr, (size_t)k);  // old key index -> sorted rank
+    std::vector<int32_t> keep, new_of_rank(drop_rank.size(), -1);
+    for (size_t r = 0; r < drop_rank.size(); ++r)
+        if (!drop_rank[r]) { new_of_rank[r] = (int32_t)keep.size(); keep.push_back((int32_t)r); }
+    std::vector<int32_t> map((size_t)k);
+    for (int32_t i = 0; i < k; ++i) map[(size_t)i] = new_of_rank[(size_t)rank[(size_t)i]];
+    custr_column* nk = custr_gather(sorted_self->keys, keep.data(), (int32_t)keep.size(), 0);
+    if (!nk) throw ArgError{CUSTR_ERR_INVALID};
+    return with_keys_and_map(cat, nk, map);
+}
+}  // namespace
+
+extern "C" {
+// op: 0 add_keys_and_remap, 1 remove_keys_and_remap, 2 set_keys_and_remap, 3 remove_unused_keys_and_remap (strs unused)
+custr_category* custr_category_keys_op(const custr_category* cat, const custr_column* strs, int op)
+{
+    return guarded(
+        [&]() -> custr_category* {
+            if (!cat || !cat->keys || (op != 3 && !strs) || op < 0 || op > 3) throw ArgError{fail(CUSTR_ERR_ARG, "category keys op: bad argument")};
+            const custr_column* keys = cat->keys;
+            if (op == 0) {
+                const custr_column* both[2] = {keys, strs};
+                std::unique_ptr<custr_column> all(concat_columns(both, 2));
+                CatPtr uni = own(build_category(all.get()));
+                const std::vector<int32_t> map = lookup_host(keys, uni->keys);
+                custr_column* nk = uni->keys;
+                uni->keys = nullptr;
+                return with_keys_and_map(cat, nk, map);
+            }
+            if (op == 2) {
+                CatPtr uni = own(build_category(strs));
+                const std::vector<int32_t> map = lookup_host(keys, uni->keys);
+                custr_column* nk = uni->keys;
+                uni->keys = nullptr;
+                return with_keys_and_map(cat, nk, map);
+            }
+            CatPtr self = own(build_category(keys));  // sorted view of the own keys (they may be unsorted after merge_category)
+            std::vector<uint8_t> drop((size_t)self->keys->n, 0);
+            if (op == 1) {
+                CatPtr rem = own(build_category(strs));
+                const std::vector<int32_t> hit = lookup_host(self->keys, rem->keys);
+                for (size_t r = 0; r < drop.size(); ++r) drop[r] = hit[r] >= 0;
+            } else {
+                const int32_t k = keys->n;
+                Scratch<uint8_t> used((size_t)(k ? k : 1));
+                Scratch<int> bad(1);
+                CUSTR_CUDA(cudaMemsetAsync(used.get(), 0, (size_t)(k ? k : 1), g_stream));
+                CUSTR_CUDA(cudaMemsetAsync(bad.get(), 0, sizeof(int), g_stream));
+                if (cat->n) LAUNCH(k_mark_used, (cat->n + 255) / 256, 256, 0, (const int32_t*)cat->values_buf->ptr, cat->n, k, -1, used.get(), bad.get());
+                std::vector<uint8_t> h_used((size_t)k);
+                if (k) CUSTR_CUDA(cudaMemcpyAsync(h_used.data(), used.get(), (size_t)k, cudaMemcpyDeviceToHost, g_stream));
+                const std::vector<int32_t> rank = to_host32(self->values_buf->ptr, (size_t)k);
+                std::fill(drop.begin(), drop.end(), 1);
+                for (int32_t i = 0; i < k; ++i)
+                    if (h_used[(size_t)i]) drop[(size_t)rank[(size_t)i]] = 0;
+            }
+            return drop_keys(cat, self.get(), drop);
+        },
+        (custr_category*)nullptr, (custr_category*)nullptr);
+}
+
+// remap == 0: NVCategory::gather — same keys, values = pos (each in [-1, keys)); remap != 0: gather_and_remap — keys = the keys
+// that pos uses (sorted), values = pos remapped onto them (each in [0, keys)).  Out-of-range positions: CUSTR_ERR_INVALID
+// (the reference throws std::out_of_range).
+custr_category* custr_category_gather(const custr_category* cat, const int32_t* pos, int32_t count, int devmem, int remap)
+{
+    return guarded(
+        [&]() -> custr_category* {
+            if (!cat || !cat->keys || count < 0 || (count && !pos)) throw ArgError{fail(CUSTR_ERR_ARG, "category gather: bad argument")};
+            const int32_t k = cat->keys->n;
+            BufPtr vals = dev_alloc(sizeof(int32_t) * (size_t)(count ? count : 1));
+            if (count)
+                CUSTR_CUDA(cudaMemcpyAsync(vals->ptr, pos, sizeof(int32_t) * (size_t)count, devmem ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, g_stream));
+            Scratch<uint8_t> used((size_t)(k ? k : 1));
+            Scratch<int> bad(1);
+            CUSTR_CUDA(cudaMemsetAsync(used.get(), 0, (size_t)(k ? k : 1), g_stream));
+            CUSTR_CUDA(cudaMemsetAsync(bad.get(), 0, sizeof(int), g_stream));
+            // (the reference's gather documents -1 as allowed but compares against an unsigned key count, NVCategory.cu:1156-1163: -1 is
+            // rejected there too — same here)
+            if (count) LAUNCH(k_mark_used, (count + 255) / 256, 256, 0, (const int32_t*)vals->ptr, count, k, 0, used.get(), bad.get());
+            int h_bad = 0;
+            CUSTR_CUDA(cudaMemcpyAsync(&h_bad, bad.get(), sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+            std::vector<uint8_t> h_used((size_t)k);
+            if (k) CUSTR_CUDA(cudaMemcpyAsync(h_used.data(), used.get(), (size_t)k, cudaMemcpyDeviceToHost, g_stream));
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            if (h_bad) throw ArgError{fail(CUSTR_ERR_INVALID, "category gather: position out of range")};
+            custr_category tmp;  // the gathered values over the old keys
+            tmp.keys = cat->keys;
+            tmp.values_buf = vals;
+            tmp.n = count;
+            struct Unhook { custr_category& t; ~Unhook() { t.keys = nullptr; } } unhook{tmp};
+            if (!remap) {
+                custr_category* out = new custr_category;
+                out->keys = custr_slice_rows(cat->keys, 0, k);
+                out->values_buf = vals;
+                out->n = count;
+                out->has_null_key = cat->has_null_key;
+                return out;
+            }
+            CatPtr self = own(build_category(cat->keys));
+            const std::vector<int32_t> rank = to_host32(self->values_buf->ptr, (size_t)k);
+            std::vector<uint8_t> drop((size_t)self->keys->n, 1);
+            for (int32_t i = 0; i < k; ++i)
+                if (h_used[(size_t)i]) drop[(size_t)rank[(size_t)i]] = 0;
+            return drop_keys(&tmp, self.get(), drop);
+        },
+        (custr_category*)nullptr, (custr_category*)nullptr);
+}
+
+// NVCategory::gather_strings: the key strings at pos[i] (each in [0, keys))
+custr_column* custr_category_gather_strings(const custr_category* cat, const int32_t* pos, int32_t count, int devmem)
+{
+    return guarded(
+        [&]() -> custr_column* {
+            if (!cat || !cat->keys || count < 0 || (count && !pos)) throw ArgError{fail(CUSTR_ERR_ARG, "gather_strings: bad argument")};
+            BufPtr vals = dev_alloc(sizeof(int32_t) * (size_t)(count ? count : 1));
+            if (count)
+                CUSTR_CUDA(cudaMemcpyAsync(vals->ptr, pos, sizeof(int32_t) * (size_t)count, devmem ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, g_stream));
+            Scratch<int> bad(1);
+            CUSTR_CUDA(cudaMemsetAsync(bad.get(), 0, sizeof(int), g_stream));
+            if (count) LAUNCH(k_mark_used, (count + 255) / 256, 256, 0, (const int32_t*)vals->ptr, count, cat->keys->n, 0, (uint8_t*)nullptr, bad.get());
+            int h_bad = 0;
+            CUSTR_CUDA(cudaMemcpyAsync(&h_bad, bad.get(), sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            if (h_bad) throw ArgError{fail(CUSTR_ERR_INVALID, "gather_strings: position out of range")};
+            custr_column* out = custr_gather(cat->keys, (const int32_t*)vals->ptr, count, 1);
+            if (!out) throw ArgError{CUSTR_ERR_INVALID};
+            return out;
+        },
+        (custr_column*)nullptr, (custr_column*)nullptr);
+}
+}  // extern "C"
+
+extern "C" {
 
 // ---- multi-GPU: row-sharded dictionary build with the key exchange over NCCL ------------------------------
 // The only collective of the whole path.  NCCL is bound at run time (dlopen of libnccl.so.2: inside a torch process that is

@@ -349,6 +349,22 @@ NVCategory* NVCategory::merge_and_remap(NVCategory& cat)
     const custr_category* v[2] = {cat_, cat.cat_};
     return new NVCategory(checked_cat(custr_category_merge(v, 2, 1)));
 }
+NVCategory* NVCategory::add_keys_and_remap(NVStrings& strs) { return new NVCategory(checked_cat(custr_category_keys_op(cat_, strs.column(), 0))); }
+NVCategory* NVCategory::remove_keys_and_remap(NVStrings& strs) { return new NVCategory(checked_cat(custr_category_keys_op(cat_, strs.column(), 1))); }
+NVCategory* NVCategory::set_keys_and_remap(NVStrings& strs) { return new NVCategory(checked_cat(custr_category_keys_op(cat_, strs.column(), 2))); }
+NVCategory* NVCategory::remove_unused_keys_and_remap() { return new NVCategory(checked_cat(custr_category_keys_op(cat_, nullptr, 3))); }
+NVStrings* NVCategory::gather_strings(const int* pos, unsigned int elems, bool devmem)
+{
+    return new NVStrings(checked(custr_category_gather_strings(cat_, pos, (int)elems, devmem)));
+}
+NVCategory* NVCategory::gather_and_remap(const int* pos, unsigned int elems, bool devmem)
+{
+    return new NVCategory(checked_cat(custr_category_gather(cat_, pos, (int)elems, devmem, 1)));
+}
+NVCategory* NVCategory::gather(const int* pos, unsigned int elems, bool devmem)
+{
+    return new NVCategory(checked_cat(custr_category_gather(cat_, pos, (int)elems, devmem, 0)));
+}
 
 // -------------------------------------------------------------------------------------------------------------- NVText
 NVStrings* NVText::tokenize(NVStrings& strs, const char* delimiter) { return new NVStrings(checked(custr_tokenize(strs.column(), delimiter))); }

@@ -196,6 +196,51 @@ class nvcategory:
         arr = (C.c_void_p * 2)(self.m_cptr, other.m_cptr)
         return nvcategory(check_handle(lib().custr_category_merge(arr, 2, 0), "merge_category"))
 
+    def _keys_op(self, strs, op, what):
+        if strs is not None and type(strs).__name__ != "nvstrings":
+            strs = _nvs.to_device(list(strs))
+        h = lib().custr_category_keys_op(self.m_cptr, strs.m_cptr if strs is not None else None, op)
+        return nvcategory(check_handle(h, what))
+
+    def add_keys(self, strs, nulls=None):
+        """keys = sorted union with strs, values remapped.  reference nvcategory.py:720 -> NVCategory.cu:1375"""
+        return self._keys_op(strs, 0, "add_keys")
+
+    def remove_keys(self, strs, nulls=None):
+        """keys minus strs; values of removed keys become -1.  reference nvcategory.py:750 -> NVCategory.cu:1482"""
+        return self._keys_op(strs, 1, "remove_keys")
+
+    def set_keys(self, strs, nulls=None):
+        """keys = sorted distinct strs; values of keys that are gone become -1.  reference nvcategory.py:805 -> NVCategory.cu:1708"""
+        return self._keys_op(strs, 2, "set_keys")
+
+    def remove_unused_keys(self):
+        """reference nvcategory.py:780 -> NVCategory.cu:1567"""
+        return self._keys_op(None, 3, "remove_unused_keys")
+
+    def _positions(self, indexes, count):
+        if isinstance(indexes, (list, tuple)):
+            indexes = np.asarray(indexes, np.int32)
+        if isinstance(indexes, np.ndarray):
+            a = np.ascontiguousarray(indexes, np.int32)
+            return a, as_ptr(a), len(a), 0
+        return indexes, as_ptr(indexes), count, 1
+
+    def gather(self, indexes, count=0):
+        """same keys, values = indexes.  reference nvcategory.py:630 -> NVCategory.cu:1142"""
+        keep, p, n, dev = self._positions(indexes, count)
+        return nvcategory(check_handle(lib().custr_category_gather(self.m_cptr, p, n, dev, 0), "gather"))
+
+    def gather_and_remap(self, indexes, count=0):
+        """keys = the keys the indexes use, values remapped.  reference nvcategory.py:590 -> NVCategory.cu:1084"""
+        keep, p, n, dev = self._positions(indexes, count)
+        return nvcategory(check_handle(lib().custr_category_gather(self.m_cptr, p, n, dev, 1), "gather_and_remap"))
+
+    def gather_strings(self, indexes, count=0):
+        """the key strings at the given key indexes.  reference nvcategory.py:518 -> NVCategory.cu:1011"""
+        keep, p, n, dev = self._positions(indexes, count)
+        return _nvs.nvstrings(check_handle(lib().custr_category_gather_strings(self.m_cptr, p, n, dev), "gather_strings"))
+
     def __getattr__(self, name):
         if name.startswith("_") or name == "m_cptr":
             raise AttributeError(name)

@@ -33,4 +33,12 @@ public:
     static NVCategory* create_from_categories(std::vector<NVCategory*>& cats);   // :122  sorted union of keys, values remapped + appended
     NVCategory* merge_category(NVCategory& cat);                                 // :261  keys appended (not re-sorted)
     NVCategory* merge_and_remap(NVCategory& cat);                                // :270  = create_from_categories({this, cat})
+    // key-set algebra and gathers (NVCategory.cu:1011-1220,1375-1820); positions are int32 key indexes
+    NVCategory* add_keys_and_remap(NVStrings& strs);                             // :204
+    NVCategory* remove_keys_and_remap(NVStrings& strs);                          // :213
+    NVCategory* set_keys_and_remap(NVStrings& strs);                             // :234
+    NVCategory* remove_unused_keys_and_remap();                                  // :242
+    NVStrings* gather_strings(const int* pos, unsigned int elems, bool devmem = true);   // :291
+    NVCategory* gather_and_remap(const int* pos, unsigned int elems, bool devmem = true); // :312
+    NVCategory* gather(const int* pos, unsigned int elems, bool devmem = true);           // :335
 };

@@ -177,6 +177,16 @@ custr_category* custr_category_remap_to_union(const custr_category* cat, const c
  * inputs): NVCategory::merge_category :1223-1336 — keys = the first input's keys followed by the second's new keys, the first
  * values unchanged. */
 custr_category* custr_category_merge(const custr_category* const* cats, int32_t ncats, int sorted);
+/* Key-set algebra on an existing category (values keep their count, -1 = "no key"): op 0 = NVCategory::add_keys_and_remap
+ * (NVCategory.cu:1375-1480: keys = sorted union with strs), 1 = remove_keys_and_remap (:1482-1565: values of removed keys become
+ * -1), 2 = set_keys_and_remap (:1708-1820: keys = sorted distinct strs), 3 = remove_unused_keys_and_remap (:1567-1706, strs
+ * ignored). */
+custr_category* custr_category_keys_op(const custr_category* cat, const custr_column* strs, int op);
+/* NVCategory::gather (:1142, remap == 0: same keys, values = pos, each in [0, keys) — the reference rejects -1 as well) / gather_and_remap (:1084, remap != 0:
+ * keys = the keys pos uses, values remapped, each pos in [0, keys)); gather_strings (:1011): the key strings at pos[i].
+ * pos: int32[count] on the device (devmem) or host.  Out-of-range positions: CUSTR_ERR_INVALID (reference: std::out_of_range). */
+custr_category* custr_category_gather(const custr_category* cat, const int32_t* pos, int32_t count, int devmem, int remap);
+custr_column* custr_category_gather_strings(const custr_category* cat, const int32_t* pos, int32_t count, int devmem);
 
 /* ---- multi-GPU NVCategory: the one collective of the hot path.  One process per GPU; the column is sharded
  *      by contiguous row range.  custr_comm wraps an NCCL communicator (libnccl.so.2 bound at run time): rank 0 obtains a

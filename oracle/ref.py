@@ -31,7 +31,8 @@ def lib():
         L.ref_last_error.restype = cp
         for name in ("ref_create", "ref_create_from_array", "ref_replace_re", "ref_replace_re_multi", "ref_replace", "ref_replace_with_backrefs",
                      "ref_replace_multi", "ref_tokenize", "ref_tokenize_multi", "ref_cat_create", "ref_cat_create_multi",
-                     "ref_cat_keys", "ref_cat_to_strings", "ref_cat_merge", "ref_cat_from_categories"):
+                     "ref_cat_keys", "ref_cat_to_strings", "ref_cat_merge", "ref_cat_from_categories", "ref_cat_keys_op", "ref_cat_gather",
+                     "ref_cat_gather_strings"):
             getattr(L, name).restype = vp
         L.ref_create.argtypes = [vp, ci, vp, vp, ci]
         L.ref_destroy.argtypes = [vp]
@@ -71,6 +72,9 @@ def lib():
         L.ref_cat_to_strings.argtypes = [vp]
         L.ref_cat_merge.argtypes = [vp, vp, ci]
         L.ref_cat_from_categories.argtypes = [vp, ci]
+        L.ref_cat_keys_op.argtypes = [vp, vp, ci]
+        L.ref_cat_gather.argtypes = [vp, vp, C.c_uint, ci]
+        L.ref_cat_gather_strings.argtypes = [vp, vp, C.c_uint]
         _lib = L
     return _lib
 
@@ -300,6 +304,27 @@ class RefCategory:
     def to_strings(self): return RefStrings(lib().ref_cat_to_strings(self.h))
     def merge_category(self, other): return RefCategory(None, lib().ref_cat_merge(self.h, other.h, 0))
     def merge_and_remap(self, other): return RefCategory(None, lib().ref_cat_merge(self.h, other.h, 1))
+
+    def _cat(self, h):
+        if not h:
+            raise ValueError(lib().ref_last_error().decode())
+        return RefCategory(None, h)
+
+    def add_keys(self, strs): return self._cat(lib().ref_cat_keys_op(self.h, strs.h, 0))
+    def remove_keys(self, strs): return self._cat(lib().ref_cat_keys_op(self.h, strs.h, 1))
+    def set_keys(self, strs): return self._cat(lib().ref_cat_keys_op(self.h, strs.h, 2))
+    def remove_unused_keys(self): return self._cat(lib().ref_cat_keys_op(self.h, None, 3))
+
+    def gather(self, pos, remap=False):
+        a = np.ascontiguousarray(pos, np.int32)
+        return self._cat(lib().ref_cat_gather(self.h, _ptr(a), len(a), 1 if remap else 0))
+
+    def gather_strings(self, pos):
+        a = np.ascontiguousarray(pos, np.int32)
+        h = lib().ref_cat_gather_strings(self.h, _ptr(a), len(a))
+        if not h:
+            raise ValueError(lib().ref_last_error().decode())
+        return RefStrings(h)
 
     @staticmethod
     def from_categories(cats):

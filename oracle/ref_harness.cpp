@@ -219,5 +219,18 @@ void* ref_cat_from_categories(void** cs, int n)
     GUARD(return NVCategory::create_from_categories(v), nullptr);
 }
 void* ref_cat_to_strings(void* c) { GUARD(return ((NVCategory*)c)->to_strings(), nullptr); }
+// key-set algebra / gathers (NVCategory.cu:1084-1220,1375-1820): op 0 add_keys, 1 remove_keys, 2 set_keys, 3 remove_unused
+void* ref_cat_keys_op(void* c, void* strs, int op)
+{
+    NVCategory* cat = (NVCategory*)c;
+    GUARD(return op == 0 ? cat->add_keys_and_remap(*(NVStrings*)strs) : op == 1 ? cat->remove_keys_and_remap(*(NVStrings*)strs)
+                 : op == 2 ? cat->set_keys_and_remap(*(NVStrings*)strs) : cat->remove_unused_keys_and_remap(), nullptr);
+}
+void* ref_cat_gather(void* c, const int* pos, unsigned n, int remap)
+{
+    NVCategory* cat = (NVCategory*)c;
+    GUARD(return remap ? cat->gather_and_remap(pos, n, false) : cat->gather(pos, n, false), nullptr);
+}
+void* ref_cat_gather_strings(void* c, const int* pos, unsigned n) { GUARD(return ((NVCategory*)c)->gather_strings(pos, n, false), nullptr); }
 
 }  // extern "C"

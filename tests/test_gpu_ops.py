@@ -332,3 +332,43 @@ def test_create_from_index(oracle):
         assert [key(stype)(g) for g in got] == [key(stype)(w) for w in want]
         assert sorted(got, key=lambda r: (r is not None, r or "")) == sorted(rows, key=lambda r: (r is not None, r or ""))
     assert nvstrings.from_index(0, 0).size() == 0
+
+
+def test_category_key_algebra_and_gathers(oracle):
+    """add_keys / remove_keys / set_keys / remove_unused_keys / gather / gather_and_remap / gather_strings against the reference
+    (NVCategory.cu:1011-1220,1375-1820), also chained (values that already hold -1)"""
+    from custrings_b200 import nvstrings, nvcategory
+    rng = random.Random(21)
+    pool = ["eee", "aaa", "ddd", None, "é", "zz", "", "b", "日本", "a"]
+    rows = [rng.choice(pool) for _ in range(500)]
+    dev = nvcategory.from_strings(nvstrings.to_device(rows))
+    ref = oracle.RefCategory(oracle.RefStrings.from_list(rows))
+
+    def same(d, r):
+        assert d.keys().to_host() == [None if k is None else k.decode() for k in r.keys().to_list()]
+        assert d.values() == r.values().tolist()
+
+    for extra in (["ccc", "aaa", "x"], ["", None, "q"], ["eee"], []):
+        e_dev, e_ref = nvstrings.to_device(extra), oracle.RefStrings.from_list(extra)
+        same(dev.add_keys(e_dev), ref.add_keys(e_ref))
+        same(dev.remove_keys(e_dev), ref.remove_keys(e_ref))
+        if extra:
+            same(dev.set_keys(e_dev), ref.set_keys(e_ref))
+    # chained: values of removed keys are -1 and stay -1
+    gone = ["aaa", "é"]
+    d1, r1 = dev.remove_keys(nvstrings.to_device(gone)), ref.remove_keys(oracle.RefStrings.from_list(gone))
+    same(d1.add_keys(nvstrings.to_device(["k"])), r1.add_keys(oracle.RefStrings.from_list(["k"])))
+    same(d1.remove_unused_keys(), r1.remove_unused_keys())
+    same(dev.set_keys(nvstrings.to_device(["aaa", "zz"])).remove_unused_keys(), ref.set_keys(oracle.RefStrings.from_list(["aaa", "zz"])).remove_unused_keys())
+    k = dev.keys_size()
+    pos = [rng.randrange(0, k) for _ in range(300)]
+    same(dev.gather(pos), ref.gather(pos))
+    with pytest.raises(ValueError):  # documented as allowed, rejected by the reference's unsigned comparison (NVCategory.cu:1156-1163)
+        ref.gather(pos + [-1])
+    with pytest.raises(ValueError):
+        dev.gather(pos + [-1])
+    sub = [p for p in pos if p % 2 == 0] or [0]
+    same(dev.gather_and_remap(sub), ref.gather(sub, remap=True))
+    assert dev.gather_strings(pos).to_host() == [None if x is None else x.decode() for x in ref.gather_strings(pos).to_list()]
+    with pytest.raises(ValueError):
+        dev.gather([0, k])
