@@ -33,6 +33,8 @@ _SIGNATURES = {
     "custr_adopt_device": (vp, [vp, ci, vp, vp, ci]),
     "custr_create_from_array": (vp, [vp, cu]),
     "custr_create_from_index": (vp, [vp, cu, ci, ci]),
+    "custr_ipc_export": (ci, [vp, vp]),
+    "custr_ipc_import": (vp, [vp]),
     "custr_column_free": (None, [vp]),
     "custr_size": (cu, [vp]),
     "custr_chars_bytes": (cl, [vp]),
@@ -83,6 +85,10 @@ _SIGNATURES = {
     "custr_category_values_cptr": (vp, [vp]),
     "custr_category_remap_to_union": (vp, [vp, vp]),
     "custr_category_merge": (vp, [vp, ci, ci]),
+    "custr_is_class": (ci, [vp, ci, vp, ci]),
+    "custr_case": (vp, [vp, ci]),
+    "custr_strip": (vp, [vp, cp, ci]),
+    "custr_slice": (vp, [vp, ci, ci, ci]),
     "custr_category_keys_op": (vp, [vp, vp, ci]),
     "custr_category_gather": (vp, [vp, vp, ci, ci, ci]),
     "custr_category_gather_strings": (vp, [vp, vp, ci, ci]),

@@ -17,7 +17,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 # (source, extra defines, object name); regex_item.cu is built once per chain-length group so its instantiations compile in parallel
 SOURCES = [("regex_bits.cu", [], None), ("regex_item.cu", ["-DITEM_NS_GROUP=0"], "regex_item_g0"), ("regex_item.cu", ["-DITEM_NS_GROUP=1"], "regex_item_g1"),
            ("regex_item.cu", ["-DITEM_NS_GROUP=2"], "regex_item_g2"), ("regex_item.cu", ["-DITEM_NS_GROUP=3"], "regex_item_g3"),
-           ("regex.cu", [], None), ("column.cu", [], None), ("find.cu", [], None), ("split.cu", [], None), ("category.cu", [], None),
+           ("regex.cu", [], None), ("column.cu", [], None), ("attrs.cu", [], None), ("find.cu", [], None), ("split.cu", [], None), ("category.cu", [], None),
            ("regex_jit.cu", [], None), ("regex_bits_lower.cpp", [], None), ("regex_compile.cpp", [], None), ("classes.cpp", [], None)]
 # kernel headers embedded into the library for the run-time compiled plan kernels (regex_jit.cu); "cstdint" / "cuda_runtime.h"
 # are stand-ins: NVRTC has no host headers
@@ -79,6 +79,10 @@ def build(verbose=False, force=False):
     gen = os.path.join(ROOT, "tools", "gen_unicode_flags.py")
     if force or _stale(flags_inc, [gen, os.path.join(ROOT, "tools", "unicode_delta.txt")]):
         subprocess.run([sys.executable, gen], check=True, capture_output=True)
+    cases_inc = os.path.join(CSRC, "unicode_cases.inc")
+    gen2 = os.path.join(ROOT, "tools", "gen_unicode_cases.py")
+    if force or _stale(cases_inc, [gen, gen2, os.path.join(ROOT, "tools", "unicode_cases_delta.txt")]):
+        subprocess.run([sys.executable, gen2], check=True, capture_output=True)
     if force:
         shutil.rmtree(OBJ)
         os.makedirs(OBJ)

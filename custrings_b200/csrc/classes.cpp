@@ -276,6 +276,19 @@ NVStrings* NVStrings::sublist(unsigned int start, unsigned int end, int step)
     return new NVStrings(checked(custr_slice_rows(col_, (int)start, (int)end)));
 }
 
+#define CUSTR_IS(NAME, KIND) \
+    unsigned int NVStrings::NAME(bool* results, bool todevice) { return (unsigned int)checked(custr_is_class(col_, KIND, (uint8_t*)results, todevice)); }
+CUSTR_IS(isalnum, 0) CUSTR_IS(isalpha, 1) CUSTR_IS(isdigit, 2) CUSTR_IS(isspace, 3) CUSTR_IS(isdecimal, 4) CUSTR_IS(isnumeric, 5)
+CUSTR_IS(islower, 6) CUSTR_IS(isupper, 7) CUSTR_IS(is_empty, 8)
+#undef CUSTR_IS
+NVStrings* NVStrings::lower() { return new NVStrings(checked(custr_case(col_, 0))); }
+NVStrings* NVStrings::upper() { return new NVStrings(checked(custr_case(col_, 1))); }
+NVStrings* NVStrings::strip(const char* to_strip) { return new NVStrings(checked(custr_strip(col_, to_strip, 0))); }
+NVStrings* NVStrings::lstrip(const char* to_strip) { return new NVStrings(checked(custr_strip(col_, to_strip, 1))); }
+NVStrings* NVStrings::rstrip(const char* to_strip) { return new NVStrings(checked(custr_strip(col_, to_strip, 2))); }
+NVStrings* NVStrings::slice(int start, int stop, int step) { return new NVStrings(checked(custr_slice(col_, start, stop, step))); }
+NVStrings* NVStrings::get(unsigned int pos) { return slice((int)pos, (int)pos + 1, 1); }
+
 // ---------------------------------------------------------------------------------------------------------- NVCategory
 NVCategory::~NVCategory() { custr_category_free(cat_); }
 void NVCategory::destroy(NVCategory* inst) { delete inst; }

@@ -507,6 +507,59 @@ custr_column* custr_adopt_device(const char* chars, int32_t count, const int32_t
                    (custr_column*)nullptr, (custr_column*)nullptr);
 }
 
+// ---- CUDA IPC (reference cpp/include/ipc_transfer.h:31-100, NVStrings::create_ipc_transfer / create_from_ipc): hand a column
+// to another process on the same GPU without a copy through the host.  The column's three buffers are packed into ONE plain
+// cudaMalloc allocation (stream-ordered pool memory cannot be exported with cudaIpcGetMemHandle): [chars | offsets | validity]
+int custr_ipc_export(const custr_column* col, custr_ipc_handle* out)
+{
+    return guarded(
+        [&]() -> int {
+            if (!col || !out) return fail(CUSTR_ERR_ARG, "ipc_export: null argument");
+            memset(out, 0, sizeof(*out));
+            const int32_t n = col->n;
+            const size_t chars_b = ((size_t)col->nbytes + 15) & ~(size_t)15, off_b = (sizeof(int32_t) * (size_t)(n + 1) + 15) & ~(size_t)15;
+            const size_t val_b = col->validity ? (size_t)(n + 7) / 8 : 0;
+            char* base = nullptr;
+            CUSTR_CUDA(cudaMalloc(&base, chars_b + off_b + val_b + 16));
+            std::shared_ptr<void> owner(base, [](void* p) { cudaFree(p); });
+            // normalised copy: offsets rebased to 0, validity re-aligned to bit 0 (the export helper does both)
+            const int nulls = custr_create_offsets(col, base, (int32_t*)(base + chars_b), val_b ? (uint8_t*)(base + chars_b + off_b) : nullptr, 1);
+            if (nulls < 0) return nulls;
+            CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+            cudaIpcMemHandle_t h;
+            CUSTR_CUDA(cudaIpcGetMemHandle(&h, base));
+            static_assert(sizeof(h) <= sizeof(out->handle), "handle size");
+            memcpy(out->handle, &h, sizeof(h));
+            out->n = n;
+            out->nulls = nulls;
+            out->chars_bytes = col->nbytes;
+            out->offsets_at = (int64_t)chars_b;
+            out->validity_at = val_b ? (int64_t)(chars_b + off_b) : -1;
+            col->ipc_owner = owner;
+            return CUSTR_OK;
+        },
+        (int)CUSTR_ERR_ARG, (int)CUSTR_ERR_CUDA);
+}
+
+custr_column* custr_ipc_import(const custr_ipc_handle* in)
+{
+    return guarded(
+        [&]() -> custr_column* {
+            if (!in) throw ArgError{fail(CUSTR_ERR_ARG, "ipc_import: null argument")};
+            cudaIpcMemHandle_t h;
+            memcpy(&h, in->handle, sizeof(h));
+            void* base = nullptr;
+            CUSTR_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            std::shared_ptr<void> owner(base, [](void* p) { cudaIpcCloseMemHandle(p); });
+            const char* b = (const char*)base;
+            custr_column* c = create_from_offsets_impl(b, in->n, (const int32_t*)(b + in->offsets_at),
+                                                       in->validity_at >= 0 ? (const uint8_t*)(b + in->validity_at) : nullptr, in->nulls, 1, true);
+            c->ipc_owner = owner;
+            return c;
+        },
+        (custr_column*)nullptr, (custr_column*)nullptr);
+}
+
 custr_column* custr_create_from_array(const char* const* strs, uint32_t count)
 {
     return guarded(

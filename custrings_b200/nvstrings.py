@@ -72,6 +72,13 @@ def from_index(pairs, count, bdevmem=True, stype=0):
     return nvstrings(check_handle(h, "from_index"))
 
 
+def create_from_ipc(ipc_data):
+    """Column exported by another process on the same GPU (nvstrings.get_ipc_data()); zero copy.  reference nvstrings.py
+    create_from_ipc -> NVStrings::create_from_ipc (ipc_transfer.h)"""
+    buf = C.create_string_buffer(bytes(ipc_data), len(ipc_data))
+    return nvstrings(check_handle(lib().custr_ipc_import(buf), "create_from_ipc"))
+
+
 def from_strings(*args):
     """Concatenate nvstrings instances into one.  reference nvstrings.py:27"""
     cols = []
@@ -243,6 +250,13 @@ class nvstrings:
 
     sublist = gather
 
+    def get_ipc_data(self):
+        """bytes to hand to nvstrings.create_from_ipc() in another process (this column must stay alive meanwhile).
+        reference nvstrings.py get_ipc_data -> NVStrings::create_ipc_transfer"""
+        buf = C.create_string_buffer(96)
+        check_rc(lib().custr_ipc_export(self.m_cptr, buf), "get_ipc_data")
+        return buf.raw
+
     def copy(self):
         return self[0:self.size()]
 
@@ -349,6 +363,68 @@ class nvstrings:
     def startswith(self, pat, devptr=0):
         """reference nvstrings.py:2049"""
         return self._host_result(lib().custr_startswith, np.uint8, devptr, "startswith", None, True, _enc(pat))
+
+    def _is(self, kind, devptr, what):
+        return self._host_result(lib().custr_is_class, np.uint8, devptr, what, None, True, kind)
+
+    def isalnum(self, devptr=0):
+        """every character alphanumeric (at least one).  reference nvstrings.py isalnum -> attrs.cu:115"""
+        return self._is(0, devptr, "isalnum")
+
+    def isalpha(self, devptr=0):
+        return self._is(1, devptr, "isalpha")
+
+    def isdigit(self, devptr=0):
+        return self._is(2, devptr, "isdigit")
+
+    def isspace(self, devptr=0):
+        return self._is(3, devptr, "isspace")
+
+    def isdecimal(self, devptr=0):
+        return self._is(4, devptr, "isdecimal")
+
+    def isnumeric(self, devptr=0):
+        return self._is(5, devptr, "isnumeric")
+
+    def islower(self, devptr=0):
+        return self._is(6, devptr, "islower")
+
+    def isupper(self, devptr=0):
+        return self._is(7, devptr, "isupper")
+
+    def is_empty(self, devptr=0):
+        """null rows are empty too.  attrs.cu:412"""
+        if devptr:
+            check_rc(lib().custr_is_class(self.m_cptr, 8, as_ptr(devptr), 1), "is_empty")
+            return devptr
+        out = np.zeros(max(self.size(), 1), np.uint8)
+        check_rc(lib().custr_is_class(self.m_cptr, 8, as_ptr(out), 0), "is_empty")
+        return [bool(v) for v in out[: self.size()]]
+
+    def lower(self):
+        """reference nvstrings.py lower -> case.cu:30"""
+        return nvstrings(check_handle(lib().custr_case(self.m_cptr, 0), "lower"))
+
+    def upper(self):
+        return nvstrings(check_handle(lib().custr_case(self.m_cptr, 1), "upper"))
+
+    def strip(self, to_strip=None):
+        """reference nvstrings.py strip -> strip.cu:87; None strips space, newline and tab"""
+        return nvstrings(check_handle(lib().custr_strip(self.m_cptr, _enc(to_strip) if to_strip is not None else None, 0), "strip"))
+
+    def lstrip(self, to_strip=None):
+        return nvstrings(check_handle(lib().custr_strip(self.m_cptr, _enc(to_strip) if to_strip is not None else None, 1), "lstrip"))
+
+    def rstrip(self, to_strip=None):
+        return nvstrings(check_handle(lib().custr_strip(self.m_cptr, _enc(to_strip) if to_strip is not None else None, 2), "rstrip"))
+
+    def slice(self, start, stop=None, step=None):
+        """characters [start, stop) of every string, every step-th one.  reference nvstrings.py slice -> substr.cu:39"""
+        return nvstrings(check_handle(lib().custr_slice(self.m_cptr, int(start), -1 if stop is None else int(stop), 1 if step is None else int(step)), "slice"))
+
+    def get(self, i):
+        """the character at position i.  substr.cu:32"""
+        return self.slice(i, i + 1, 1)
 
     def endswith(self, pat, devptr=0):
         """reference nvstrings.py:2073"""

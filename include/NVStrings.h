@@ -87,4 +87,22 @@ private:
     int record_split_(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results, bool right);
     unsigned int column_split_(const char* delimiter, int maxsplit, std::vector<NVStrings*>& results, bool right);
     int partition_(const char* delimiter, std::vector<NVStrings*>& results, bool right);
+
+    // cheap attributes / transforms: attrs.cu:115-445, case.cu:30-190, strip.cu:30-200, substr.cu:32-83
+    unsigned int isalnum(bool* results, bool todevice = true);
+    unsigned int isalpha(bool* results, bool todevice = true);
+    unsigned int isdigit(bool* results, bool todevice = true);
+    unsigned int isspace(bool* results, bool todevice = true);
+    unsigned int isdecimal(bool* results, bool todevice = true);
+    unsigned int isnumeric(bool* results, bool todevice = true);
+    unsigned int islower(bool* results, bool todevice = true);
+    unsigned int isupper(bool* results, bool todevice = true);
+    unsigned int is_empty(bool* results, bool todevice = true);
+    NVStrings* lower();
+    NVStrings* upper();
+    NVStrings* strip(const char* to_strip = nullptr);
+    NVStrings* lstrip(const char* to_strip = nullptr);
+    NVStrings* rstrip(const char* to_strip = nullptr);
+    NVStrings* slice(int start = 0, int stop = -1, int step = 1);
+    NVStrings* get(unsigned int pos);
 };

@@ -76,6 +76,18 @@ custr_column* custr_create_from_array(const char* const* strs, uint32_t count);
  * (the layout of std::pair<const char*,size_t>), in device memory when devmem != 0 else on the host; ptr always addresses
  * DEVICE memory, ptr == NULL is a null row.  stype = NVStrings::sorttype (0 none, 1 length, 2 name, 3 both). */
 custr_column* custr_create_from_index(const void* pairs, uint32_t count, int devmem, int stype);
+/* CUDA IPC (reference cpp/include/ipc_transfer.h, NVStrings::create_ipc_transfer / create_from_ipc): export packs the column
+ * into one exportable device allocation (kept alive by `col`) and fills the handle; another process on the same GPU imports it
+ * as a zero-copy column (the mapping closes when that column is freed).  The handle is plain bytes: ship it over any channel. */
+typedef struct custr_ipc_handle {
+    unsigned char handle[64];   /* cudaIpcMemHandle_t */
+    int32_t n, nulls;
+    int64_t chars_bytes;        /* chars at offset 0 */
+    int64_t offsets_at;         /* byte offset of int32 offsets[n + 1] */
+    int64_t validity_at;        /* byte offset of the validity bits, -1 if there are no nulls */
+} custr_ipc_handle;
+int custr_ipc_export(const custr_column* col, custr_ipc_handle* out);
+custr_column* custr_ipc_import(const custr_ipc_handle* in);
 void     custr_column_free(custr_column* col);
 uint32_t custr_size(const custr_column* col);
 int64_t  custr_chars_bytes(const custr_column* col);     /* bytes in the chars buffer                      */
@@ -154,6 +166,15 @@ custr_column* custr_partition(const custr_column* col, const char* delimiter, in
 custr_column* custr_slice_rows(const custr_column* col, int32_t first, int32_t last);
 /* gather rows by index (device or host int32 indices; negative/out-of-range -> null row). */
 custr_column* custr_gather(const custr_column* col, const int32_t* indices, int32_t count, int devmem);
+
+/* ---- cheap per-character attributes and transforms: strings/attrs.cu:115-445, case.cu:30-190,
+ *      strip.cu:30-200, substr.cu:39-83 ---- */
+/* kind: 0 isalnum, 1 isalpha, 2 isdigit, 3 isspace, 4 isdecimal, 5 isnumeric, 6 islower, 7 isupper, 8 is_empty; one bool per
+ * row (null rows false; is_empty: true), returns the number of true rows */
+int custr_is_class(const custr_column* col, int kind, uint8_t* results, int devmem);
+custr_column* custr_case(const custr_column* col, int to_upper);                      /* lower() / upper()              */
+custr_column* custr_strip(const custr_column* col, const char* to_strip, int side);   /* 0 strip, 1 lstrip, 2 rstrip; NULL = " \n\t" */
+custr_column* custr_slice(const custr_column* col, int32_t start, int32_t stop, int32_t step);  /* characters [start, stop or end) */
 
 /* ---- NVText::tokenize tokens.cu:123-155 (delimiter==NULL: whitespace), token_count :337-361 ---- */
 custr_column* custr_tokenize(const custr_column* col, const char* delimiter);

@@ -32,7 +32,7 @@ def lib():
         for name in ("ref_create", "ref_create_from_array", "ref_replace_re", "ref_replace_re_multi", "ref_replace", "ref_replace_with_backrefs",
                      "ref_replace_multi", "ref_tokenize", "ref_tokenize_multi", "ref_cat_create", "ref_cat_create_multi",
                      "ref_cat_keys", "ref_cat_to_strings", "ref_cat_merge", "ref_cat_from_categories", "ref_cat_keys_op", "ref_cat_gather",
-                     "ref_cat_gather_strings"):
+                     "ref_cat_gather_strings", "ref_case", "ref_strip", "ref_slice"):
             getattr(L, name).restype = vp
         L.ref_create.argtypes = [vp, ci, vp, vp, ci]
         L.ref_destroy.argtypes = [vp]
@@ -73,6 +73,10 @@ def lib():
         L.ref_cat_merge.argtypes = [vp, vp, ci]
         L.ref_cat_from_categories.argtypes = [vp, ci]
         L.ref_cat_keys_op.argtypes = [vp, vp, ci]
+        L.ref_is_class.argtypes = [vp, ci, vp]
+        L.ref_case.argtypes = [vp, ci]
+        L.ref_strip.argtypes = [vp, cp, ci]
+        L.ref_slice.argtypes = [vp, ci, ci, ci]
         L.ref_cat_gather.argtypes = [vp, vp, C.c_uint, ci]
         L.ref_cat_gather_strings.argtypes = [vp, vp, C.c_uint]
         _lib = L
@@ -271,6 +275,11 @@ class RefStrings:
 
     def tokenize(self, delim=None):
         return RefStrings(lib().ref_tokenize(self.h, _b(delim)))
+
+    def is_class(self, kind): return self._rows(lib().ref_is_class, np.bool_, kind)
+    def case(self, upper): return RefStrings(lib().ref_case(self.h, 1 if upper else 0))
+    def strip(self, chars=None, side=0): return RefStrings(lib().ref_strip(self.h, _b(chars), side))
+    def slice(self, start, stop=-1, step=1): return RefStrings(lib().ref_slice(self.h, start, stop, step))
 
     def tokenize_multi(self, delims):
         return RefStrings(lib().ref_tokenize_multi(self.h, delims.h))

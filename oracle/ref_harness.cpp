@@ -219,6 +219,21 @@ void* ref_cat_from_categories(void** cs, int n)
     GUARD(return NVCategory::create_from_categories(v), nullptr);
 }
 void* ref_cat_to_strings(void* c) { GUARD(return ((NVCategory*)c)->to_strings(), nullptr); }
+// cheap attributes / transforms (strings/attrs.cu, case.cu, strip.cu, substr.cu)
+int ref_is_class(void* h, int kind, bool* out)
+{
+    NVStrings* s = (NVStrings*)h;
+    GUARD(return (int)(kind == 0 ? s->isalnum(out, false) : kind == 1 ? s->isalpha(out, false) : kind == 2 ? s->isdigit(out, false)
+                 : kind == 3 ? s->isspace(out, false) : kind == 4 ? s->isdecimal(out, false) : kind == 5 ? s->isnumeric(out, false)
+                 : kind == 6 ? s->islower(out, false) : kind == 7 ? s->isupper(out, false) : s->is_empty(out, false)), -100);
+}
+void* ref_case(void* h, int upper) { GUARD(return upper ? ((NVStrings*)h)->upper() : ((NVStrings*)h)->lower(), nullptr); }
+void* ref_strip(void* h, const char* chars, int side)
+{
+    NVStrings* s = (NVStrings*)h;
+    GUARD(return side == 0 ? s->strip(chars) : side == 1 ? s->lstrip(chars) : s->rstrip(chars), nullptr);
+}
+void* ref_slice(void* h, int start, int stop, int step) { GUARD(return ((NVStrings*)h)->slice(start, stop, step), nullptr); }
 // key-set algebra / gathers (NVCategory.cu:1084-1220,1375-1820): op 0 add_keys, 1 remove_keys, 2 set_keys, 3 remove_unused
 void* ref_cat_keys_op(void* c, void* strs, int op)
 {

@@ -1,7 +1,11 @@
 """Edge cases of the column layout against the bitstream kernels (windowing, row bookkeeping, views): every result
 is compared with the exact Pike-VM tier and, where cheap, with the oracle."""
+import os
+
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 PATS = [r"\b\w{4,}\b", r"\d+", r"^a", r"z$", r"é+x", r"\bq", r"[a-c]{2}\s", r"ab|cd", r"x\b", r"^$"]
@@ -90,3 +94,26 @@ def test_adopted_device_buffers():
     want = nvstrings.to_device(strs).contains(r"\b\w{4,}\b")
     assert col.contains(r"\b\w{4,}\b") == want
     assert col.to_host() == strs
+
+
+def test_ipc_export_import_between_processes(tmp_path):
+    """CUDA IPC: a column exported in this process is opened, zero copy, by a second process on the same GPU
+    (reference ipc_transfer.h / create_ipc_transfer / create_from_ipc)"""
+    import subprocess
+    import sys
+    from custrings_b200 import nvstrings
+    rows = ["héllo", None, "", "wörld 123", "x" * 300] * 50
+    col = nvstrings.to_device(rows)
+    data = col.get_ipc_data()
+    (tmp_path / "h.bin").write_bytes(data)
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from custrings_b200 import nvstrings\n"
+            "c = nvstrings.create_from_ipc(open(%r, 'rb').read())\n"
+            "import json; json.dump({'rows': c.to_host(), 'hits': c.contains('\\\\d+')}, open(%r, 'w'))\n"
+            % (ROOT, str(tmp_path / "h.bin"), str(tmp_path / "out.json")))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    out = json.load(open(tmp_path / "out.json"))
+    assert out["rows"] == rows
+    assert out["hits"] == col.contains(r"\d+")

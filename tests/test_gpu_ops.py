@@ -372,3 +372,34 @@ def test_category_key_algebra_and_gathers(oracle):
     assert dev.gather_strings(pos).to_host() == [None if x is None else x.decode() for x in ref.gather_strings(pos).to_list()]
     with pytest.raises(ValueError):
         dev.gather([0, k])
+
+
+def test_cheap_attributes_and_transforms(oracle):
+    """isalnum ... is_empty, lower / upper, strip family, slice against the reference (attrs.cu, case.cu, strip.cu, substr.cu)"""
+    from custrings_b200 import nvstrings
+    rng = random.Random(33)
+    rows = corpus.STRINGS + corpus.random_strings(rng, 300) + ["ABC", "abc1", " x\t\n", "é", "Éa", "ǄxǅǆX", "ß", "12", "٣٤", "", None, "   ", "\t", "aXbY",
+                                                                 "日本語", "xx--abc--xx", "Ⅷ", "²", "½"]
+    dev, ref = nvstrings.to_device(rows), oracle.RefStrings.from_list(rows)
+    dec = lambda r: [None if x is None else x.decode() for x in r.to_list()]  # noqa: E731
+    names = ["isalnum", "isalpha", "isdigit", "isspace", "isdecimal", "isnumeric", "islower", "isupper"]
+    for kind, name in enumerate(names):
+        want = ref.is_class(kind)[0]
+        assert getattr(dev, name)() == [None if r is None else bool(w) for r, w in zip(rows, want)], name
+    assert dev.is_empty() == [bool(w) for w in ref.is_class(8)[0]]
+    assert dev.lower().to_host() == dec(ref.case(False))
+    assert dev.upper().to_host() == dec(ref.case(True))
+    for chars in (None, " ", "x-", "é \t", "日a"):
+        assert dev.strip(chars).to_host() == dec(ref.strip(chars, 0)), chars
+        assert dev.lstrip(chars).to_host() == dec(ref.strip(chars, 1)), chars
+        assert dev.rstrip(chars).to_host() == dec(ref.strip(chars, 2)), chars
+    for start, stop in ((0, 3), (2, None), (1, 2), (5, 9), (0, 1), (40, None)):
+        assert dev.slice(start, stop).to_host() == dec(ref.slice(start, -1 if stop is None else stop)), (start, stop)
+    assert dev.get(1).to_host() == dec(ref.slice(1, 2))
+    # step > 1: defined for single-byte characters only (the reference counts the range in bytes there, custring_view.inl:831)
+    ascii_rows = [r for r in rows if r is None or r.isascii()]
+    da, ra = nvstrings.to_device(ascii_rows), oracle.RefStrings.from_list(ascii_rows)
+    for start, stop, step in ((0, None, 2), (1, 8, 3), (0, 5, 2)):
+        assert da.slice(start, stop, step).to_host() == dec(ra.slice(start, -1 if stop is None else stop, step)), (start, stop, step)
+    with pytest.raises(ValueError):
+        dev.slice(5, 2)
