@@ -523,8 +523,9 @@ int custr_ipc_export(const custr_column* col, custr_ipc_handle* out)
             CUSTR_CUDA(cudaMalloc(&base, chars_b + off_b + val_b + 16));
             std::shared_ptr<void> owner(base, [](void* p) { cudaFree(p); });
             // normalised copy: offsets rebased to 0, validity re-aligned to bit 0 (the export helper does both)
-            const int nulls = custr_create_offsets(col, base, (int32_t*)(base + chars_b), val_b ? (uint8_t*)(base + chars_b + off_b) : nullptr, 1);
-            if (nulls < 0) return nulls;
+            const int rc = custr_create_offsets(col, base, (int32_t*)(base + chars_b), val_b ? (uint8_t*)(base + chars_b + off_b) : nullptr, 1);
+            if (rc < 0) return rc;
+            const int nulls = col->nulls;
             CUSTR_CUDA(cudaStreamSynchronize(g_stream));
             cudaIpcMemHandle_t h;
             CUSTR_CUDA(cudaIpcGetMemHandle(&h, base));

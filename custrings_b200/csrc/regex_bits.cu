@@ -251,6 +251,7 @@ static const int32_t* ensure_item_bounds(const custr_column* col, const int32_t*
 #include "regex_chain64.cuh"
 
 // item-buffered chain kernel for boolean results (regex_chain_item.cuh), built in four translation units (regex_item.cu)
+int chain_item_ctas_per_sm();
 void launch_chain_item_g0(const ChainDev& cd, const Args& a, int blocks);
 void launch_chain_item_g1(const ChainDev& cd, const Args& a, int blocks);
 void launch_chain_item_g2(const ChainDev& cd, const Args& a, int blocks);
@@ -348,7 +349,7 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     if (plan.is_chain && !g_force_generic) {
         // 2048-byte windows, 64-bit streams, cp.async ring; grid = resident set (3 CTAs per SM), dynamic items
         a.item_bounds = ensure_item_bounds(col, a.offsets, a.first, a.nitems);  // once per column (it is immutable)
-        const int resident = num_sms() * 3;
+        const int resident = num_sms() * (use_item ? chain_item_ctas_per_sm() : 3);
         if (blocks > resident) blocks = resident;
         if (use_item) {
             // the plan's own run-time compiled kernel (regex_jit.cu) when no ahead-of-time shape covers the plan and the

@@ -26,7 +26,13 @@
 //     the general body.  NUL bytes are only ACCUMULATED per lane; an item that saw one re-checks its rows in phase B (rare).
 #pragma once
 
-constexpr int SEG_WINS = 18;                 // windows per segment: a 32 KiB item, its unaligned head and its last row
+#ifndef ITEM_SEG_WINS
+#define ITEM_SEG_WINS 18
+#endif
+#ifndef ITEM_MIN_CTAS
+#define ITEM_MIN_CTAS 3
+#endif
+constexpr int SEG_WINS = ITEM_SEG_WINS;                 // windows per segment: a 32 KiB item, its unaligned head and its last row
 constexpr int SEG_WORDS = SEG_WINS * 32;     // 64-bit stream words per segment
 struct __align__(128) WarpSmItem {
     char ring[RING_STAGES][WIN64];
@@ -415,7 +421,7 @@ __device__ __forceinline__ void chain_item_body(const ChainDev& cd, const Args& 
 }
 
 template <int NS, int NCLS, int SPEC = 0>
-__global__ void __launch_bounds__(THREADS, 3)
+__global__ void __launch_bounds__(THREADS, ITEM_MIN_CTAS)
 k_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant__ Args A)
 {
     chain_item_body<NS, NCLS, SPEC>(cd, A);

@@ -18,6 +18,9 @@ namespace bits {
 #include "regex_chain64.cuh"
 #include "regex_chain_item.cuh"
 
+#if ITEM_NS_GROUP == 1
+int chain_item_ctas_per_sm() { return ITEM_MIN_CTAS; }  // resident CTAs per SM the kernels are built for (grid = SMs x this)
+#endif
 #define ITEM_ENTRY_NAME2(g) launch_chain_item_g##g
 #define ITEM_ENTRY_NAME(g) ITEM_ENTRY_NAME2(g)
 void ITEM_ENTRY_NAME(ITEM_NS_GROUP)(const ChainDev& cd, const Args& a, int blocks)

@@ -136,9 +136,10 @@ inline PyObject* host_strings(const custr_column* c)
     rc = custr_create_offsets(c, chars.data(), off.data(), bits.data(), 0);
     Py_END_ALLOW_THREADS
     if (rc < 0) return fail_none();
+    const bool has_nulls = custr_null_count(c) > 0;
     PyObject* list = PyList_New(n);
     for (uint32_t i = 0; i < n; ++i) {
-        if (rc > 0 && !((bits[i >> 3] >> (i & 7)) & 1)) { Py_INCREF(Py_None); PyList_SetItem(list, i, Py_None); continue; }
+        if (has_nulls && !((bits[i >> 3] >> (i & 7)) & 1)) { Py_INCREF(Py_None); PyList_SetItem(list, i, Py_None); continue; }
         PyList_SetItem(list, i, PyUnicode_DecodeUTF8(chars.data() + off[i], off[i + 1] - off[i], "replace"));
     }
     return list;

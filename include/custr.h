@@ -96,7 +96,7 @@ const char*    custr_chars_ptr(const custr_column* col);     /* device pointers 
 const int32_t* custr_offsets_ptr(const custr_column* col);
 const uint8_t* custr_validity_ptr(const custr_column* col);  /* NULL if no nulls                            */
 /* Export to (chars, offsets[n+1], validity[(n+7)/8]); any of the three may be NULL to skip. Null rows export
- * as zero length (NVStrings.cu:427-432). Returns the null count. */
+ * as zero length (NVStrings.cu:427-432). Returns 0 like the reference (NVStrings.cu:402-482). */
 int custr_create_offsets(const custr_column* col, char* chars, int32_t* offsets, uint8_t* validity, int devmem);
 /* bitarray bit=1 valid; emptyIsNull also clears bits of empty rows. Returns the number of cleared bits. */
 int custr_set_null_bitarray(const custr_column* col, uint8_t* bitarray, int empty_is_null, int devmem);
