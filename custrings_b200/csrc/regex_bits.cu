@@ -446,5 +446,84 @@ bool tokenize_flat(const custr_column* col, const uint8_t* delims, int ndelims, 
     return true;
 }
 
+#include "split_bits.cuh"
+
+// NVStrings::split_record(delimiter) for ONE ASCII delimiter byte and no split limit through the bit-stream kernels
+// (split_bits.cuh): flat token column (chars + int32 offsets[ntok + 1]) and row_off[n + 1] (device).  False = not applicable
+// (unaligned chars base, empty column, or the column holds an empty valid row): the caller uses the per-row path.
+bool split_record_flat(const custr_column* col, uint8_t delim, BufPtr& out_chars, BufPtr& out_off, BufPtr& row_off, int64_t& ntok, int64_t& nbytes)
+{
+    if (((uintptr_t)col->chars & 15) != 0 || col->nbytes == 0 || col->n == 0 || delim >= 0x80) return false;
+    const int32_t n = col->n;
+    SplitArgs a{};
+    a.chars = col->chars;
+    a.offsets = col->offsets;
+    a.validity = col->validity;
+    a.vbit0 = col->vbit0;
+    a.n = n;
+    a.first = col->first_off;
+    a.end = col->first_off + (int32_t)col->nbytes;
+    a.nitems = (int)((col->nbytes + g_item_bytes - 1) / g_item_bytes);
+    a.delim = delim;
+    a.item_bounds = ensure_item_bounds(col, a.offsets, a.first, a.nitems);
+    const int win_base = a.first & ~(WIN64 - 1);
+    const size_t nwin = ((size_t)(a.end - win_base) + WIN64 - 1) / WIN64;
+    const size_t nslots = nwin + (size_t)a.nitems + 1;
+    Scratch<int32_t> item_w((size_t)a.nitems + 1), item_slot((size_t)a.nitems + 1);
+    CUSTR_CUDA(cudaMemsetAsync(item_w.get() + a.nitems, 0, sizeof(int32_t), g_stream));
+    LAUNCH(k_tok_item_windows, (a.nitems + 255) / 256, 256, 0, a.offsets, a.item_bounds, a.nitems, item_w.get());
+    {
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, item_w.get(), item_slot.get(), a.nitems + 1, g_stream);
+        BufPtr t = dev_alloc(tb);
+        CUSTR_CUDA(cub::DeviceScan::ExclusiveSum(t->ptr, tb, item_w.get(), item_slot.get(), a.nitems + 1, g_stream));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    a.item_slot = item_slot.get();
+    BufPtr counts = dev_alloc(sizeof(unsigned long long) * nslots), base = dev_alloc(sizeof(unsigned long long) * nslots);
+    BufPtr counter = dev_alloc(4 * sizeof(unsigned int));  // [0], [1] work-item counters of the two passes, [2] flags
+    CUSTR_CUDA(cudaMemsetAsync(counts->ptr, 0, sizeof(unsigned long long) * nslots, g_stream));
+    CUSTR_CUDA(cudaMemsetAsync(counter->ptr, 0, 4 * sizeof(unsigned int), g_stream));
+    a.slot_counts = (unsigned long long*)counts->ptr;
+    a.slot_base = (const unsigned long long*)base->ptr;
+    a.flags = (unsigned int*)counter->ptr + 2;
+    const int smem = WARPS * (int)sizeof(WarpSmSplit);
+    CUSTR_CUDA(cudaFuncSetAttribute(k_split_record64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUSTR_CUDA(cudaFuncSetAttribute(k_split_record64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int blocks = (a.nitems + WARPS - 1) / WARPS;
+    const int resident = num_sms() * 3;
+    if (blocks > resident) blocks = resident;
+    a.item_counter = (unsigned int*)counter->ptr;
+    auto kc = k_split_record64<false>;
+    LAUNCH(kc, blocks, THREADS, smem, a);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, a.slot_counts, (unsigned long long*)base->ptr, (int)nslots, g_stream);
+    BufPtr tmp = dev_alloc(tmp_bytes);
+    CUSTR_CUDA(cub::DeviceScan::ExclusiveSum(tmp->ptr, tmp_bytes, a.slot_counts, (unsigned long long*)base->ptr, (int)nslots, g_stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    unsigned long long total = 0;
+    unsigned int flags = 0;
+    CUSTR_CUDA(cudaMemcpyAsync(&total, (unsigned long long*)base->ptr + (nslots - 1), sizeof(total), cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaMemcpyAsync(&flags, a.flags, sizeof(flags), cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    if (flags & 1u) return false;  // an empty valid row: several rows' first tokens on one byte
+    ntok = (int64_t)(total >> 32);
+    nbytes = (int64_t)(total & 0xffffffffull);
+    out_chars = dev_alloc((size_t)nbytes);
+    out_off = dev_alloc(sizeof(int32_t) * (size_t)(ntok + 1));
+    row_off = dev_alloc(sizeof(int32_t) * (size_t)(n + 1));
+    const int32_t last_off = (int32_t)nbytes, last_row = (int32_t)ntok;
+    CUSTR_CUDA(cudaMemcpyAsync((int32_t*)out_off->ptr + ntok, &last_off, sizeof(int32_t), cudaMemcpyHostToDevice, g_stream));
+    CUSTR_CUDA(cudaMemcpyAsync((int32_t*)row_off->ptr + n, &last_row, sizeof(int32_t), cudaMemcpyHostToDevice, g_stream));
+    a.tok_off = (int32_t*)out_off->ptr;
+    a.row_off = (int32_t*)row_off->ptr;
+    a.out = (char*)out_chars->ptr;
+    a.item_counter = (unsigned int*)counter->ptr + 1;
+    auto kw = k_split_record64<true>;
+    LAUNCH(kw, blocks, THREADS, smem, a);
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    return true;
+}
+
 }  // namespace bits
 }  // namespace custr

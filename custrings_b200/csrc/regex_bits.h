@@ -43,6 +43,9 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
 // delimiter bytes.  Produces the flat token column (chars + int32 offsets[ntok + 1]).  False = not applicable.
 bool tokenize_flat(const custr_column* col, const uint8_t* delims, int ndelims, BufPtr& out_chars, BufPtr& out_off, int64_t& ntok,
                    int64_t& nbytes);
+// NVStrings::split_record with one ASCII delimiter byte and no split limit as a bit-stream compaction (split_bits.cuh): flat
+// token column + row_off[n + 1] on the device.  False = not applicable (e.g. the column holds an empty valid row).
+bool split_record_flat(const custr_column* col, uint8_t delim, BufPtr& out_chars, BufPtr& out_off, BufPtr& row_off, int64_t& ntok, int64_t& nbytes);
 extern thread_local bool g_force_generic;
 extern thread_local bool g_no_spec;
 extern thread_local bool g_chain_win;

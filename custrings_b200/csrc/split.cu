@@ -355,6 +355,20 @@ int custr_split_record(const custr_column* col, const char* delimiter, int32_t m
     return guarded(
         [&]() -> int {
             if (!col || !tokens) return fail(CUSTR_ERR_ARG, "split_record: null argument");
+            // one ASCII delimiter byte, no split limit: bit-stream compaction (split_bits.cuh), no per-row walk
+            if (delimiter && delimiter[0] && !delimiter[1] && (unsigned char)delimiter[0] < 0x80 && maxsplit < 0 && !bits::g_force_generic) {
+                BufPtr chars, off, row_off;
+                int64_t ntok = 0, nbytes = 0;
+                if (bits::split_record_flat(col, (uint8_t)delimiter[0], chars, off, row_off, ntok, nbytes)) {
+                    if (row_offsets) {
+                        CUSTR_CUDA(cudaMemcpyAsync(row_offsets, row_off->ptr, sizeof(int32_t) * (size_t)(col->n + 1),
+                                                   devmem ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, g_stream));
+                        CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+                    }
+                    *tokens = make_column(chars, off, nullptr, (int32_t)ntok, 0, nbytes);
+                    return (int)ntok;
+                }
+            }
             ParamHolder h;
             make_split_params(h, delimiter, maxsplit, true);
             int total = 0;

@@ -1,0 +1,241 @@
+// NVStrings::split_record (strings/split.cu:125-223) with a single ASCII delimiter byte and no split limit, as a bit-stream
+// compaction — included by regex_bits.cu inside custr::bits, after tokenize_bits.cuh whose window machinery it shares.
+//
+// Per-row semantics (custring_view.inl:1169-1279): a valid row yields 1 + (number of delimiter bytes) tokens, empty ones
+// included ("a,,b" -> "a", "", "b"; "" -> ""), a null row yields none.  In stream terms, with D = delimiter bytes and
+// RSV = first byte of every valid row:
+//     output chars   = the non-delimiter bytes T = ~D in order (stream compaction, exactly tokenize's)
+//     token offsets  = one entry per EVENT in position order — a RSV bit (the row's first token) or a D bit (the token behind
+//                      it) — whose value is the number of T bytes before that position; a row that starts with the delimiter
+//                      has both events on one byte, the row start first (same value: its first token is empty)
+//     row_offsets[r] = number of events before the start of row r
+// The one thing bits cannot express is several VALID rows starting on the same byte, i.e. an empty valid row: the count pass
+// flags it and the caller takes the per-row path for that column.
+// Two passes like tokenize: count (events, T bytes) per (item, window) slot -> exclusive scan -> write.
+#pragma once
+
+struct SplitArgs {
+    const char* chars;
+    const int32_t* offsets;
+    const uint8_t* validity;  // null: every row valid
+    int32_t vbit0;
+    int32_t n, first, end, nitems;
+    unsigned int* item_counter;
+    const int32_t* item_bounds;
+    uint32_t delim;
+    const int32_t* item_slot;
+    unsigned long long* slot_counts;      // count pass: (events << 32 | bytes) per slot
+    const unsigned long long* slot_base;  // write pass: exclusive scan of slot_counts
+    unsigned int* flags;                  // count pass: bit 0 = an empty valid row exists (not expressible: caller falls back)
+    int32_t* tok_off;                     // write pass outputs
+    int32_t* row_off;
+    char* out;
+};
+
+struct __align__(64) WarpSmSplit {
+    char ring[RING_STAGES][WIN64];
+    uint32_t rs[64];    // ROWSTART of valid rows (RSV), one bit per byte of the window
+    uint32_t dd[64];    // D & own: the delimiter bytes this item owns
+    uint32_t pre[32];   // exclusive prefix over the lanes of (events << 16 | T bytes)
+    char tile[WIN64 + 32];
+};
+
+__device__ __forceinline__ bool split_row_valid(const SplitArgs& A, int row)
+{
+    if (!A.validity) return true;
+    const int b = A.vbit0 + row;
+    return (A.validity[b >> 3] >> (b & 7)) & 1;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(THREADS, 3)
+k_split_record64(const __grid_constant__ SplitArgs A)
+{
+    extern __shared__ __align__(64) unsigned char split_dsm[];
+    WarpSmSplit* sm = (WarpSmSplit*)split_dsm;
+    LaneCtx L;
+    L.lane = lane_id();
+    asm volatile("" : "+r"(L.lane));
+    L.src = (L.lane + 31) & 31;
+    L.is31 = L.lane == 31;
+    L.m31 = L.lane == 31 ? 1u : 0u;
+    const uint32_t lane = L.lane;
+    WarpSmSplit& W = sm[threadIdx.x >> 5];
+    uint32_t wb = (uint32_t)__cvta_generic_to_shared(&W);
+    uint32_t my0 = wb + ring_lane_offset(lane);
+    const uint32_t rs_base = wb + (uint32_t)offsetof(WarpSmSplit, rs);
+    const uint32_t dd_base = wb + (uint32_t)offsetof(WarpSmSplit, dd);
+    const uint32_t pre_base = wb + (uint32_t)offsetof(WarpSmSplit, pre);
+    const char* gsrc = A.chars + 64 * (int)lane;
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(A.item_counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= A.nitems) break;
+        const int ra = __ldg(A.item_bounds + item), rb = __ldg(A.item_bounds + item + 1);
+        const int slot0 = __ldg(A.item_slot + item);
+        int byte_a = 0, byte_b = 0;
+        if (ra < rb) {
+            byte_a = __ldg(A.offsets + ra);
+            byte_b = __ldg(A.offsets + rb);
+        }
+        if (ra >= rb || byte_a >= byte_b) {
+            // rows without a byte: valid ones are empty rows (flagged: the caller falls back), null ones have no token and
+            // start where the next slot starts
+            if (ra < rb) {
+                for (int j0 = ra; j0 < rb; j0 += 32) {
+                    const int j = j0 + (int)lane;
+                    if (j < rb) {
+                        if (!WRITE) { if (split_row_valid(A, j)) atomicOr(A.flags, 1u); }
+                        else A.row_off[j] = (int)(__ldg(A.slot_base + slot0) >> 32);
+                    }
+                }
+            }
+            continue;
+        }
+        int ws = byte_a & ~(WIN64 - 1);
+        const int ws0 = ws;
+        int kcur = ra;  // next row whose start has not been placed (rows ra .. rb-1 start in [byte_a, byte_b])
+        int stage = 0;
+        __syncwarp();
+        ring_issue(my0, gsrc, A.chars, ws, A.end, lane);
+
+        for (; ws < byte_b; ws += WIN64, stage ^= 1) {
+            const int we = ws + WIN64;
+            const bool more = we < byte_b;
+            const bool last = !more;
+            const uint32_t cur0 = my0 + (uint32_t)stage * WIN64;
+            if (more) ring_issue(my0 + (uint32_t)(stage ^ 1) * WIN64, gsrc, A.chars, we, A.end, lane);
+
+            // ---- RSV bits: rows of this item that start inside [ws, we) (the last window also takes the rows that start at
+            //      its very end: trailing rows without bytes); kfirst = first such row
+            asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(rs_base + 8u * lane), "r"(0u) : "memory");
+            __syncwarp();
+            const int kfirst = kcur;
+            for (;;) {
+                const int j = kcur + (int)lane;
+                const int o = j < rb ? __ldg(A.offsets + j) : 0x7fffffff;
+                const bool inw = j < rb && (o < we || (last && o <= we));
+                if (inw) {
+                    const bool valid = split_row_valid(A, j);
+                    if (valid && o < we) reds_or(rs_base + 4u * (uint32_t)((o - ws) >> 5), 1u << ((o - ws) & 31));
+                    if (!WRITE && valid && __ldg(A.offsets + j + 1) == o) atomicOr(A.flags, 1u);  // empty valid row
+                }
+                const unsigned m_in = __ballot_sync(FULL, inw);
+                kcur += __popc(m_in);
+                if (m_in != FULL) break;
+            }
+            __syncwarp();
+            const u64 rsv = lds64(rs_base + 8u * lane);
+
+            // ---- bytes -> bit planes -> delimiter stream
+            if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            u64 p[8];
+            const uint4 v0 = lds128(cur0), v1 = lds128(cur0 ^ 16u), v2 = lds128(cur0 ^ 32u), v3 = lds128(cur0 ^ 48u);
+            {
+                uint32_t pl[8], ph[8];
+                transpose_planes(v0, v1, pl);
+                transpose_planes(v2, v3, ph);
+#pragma unroll
+                for (int b = 0; b < 8; ++b) p[b] = mk64(pl[b], ph[b]);
+            }
+            const int wp = ws + 64 * (int)lane;
+            u64 own = 0;  // this work item owns the bytes of [byte_a, byte_b)
+            if (wp + 64 > byte_a && wp < byte_b) {
+                own = ~0ull;
+                if (wp < byte_a) own &= ~0ull << (byte_a - wp);
+                if (wp + 64 > byte_b) own &= ~0ull >> (wp + 64 - byte_b);
+            }
+            const u64 D = cls_eq(p, A.delim) & ~p[7] & own;
+            const u64 T = ~D & own;
+            const uint32_t cnt = ((uint32_t)(__popcll(D) + __popcll(rsv)) << 16) | (uint32_t)__popcll(T);  // events <= 128, bytes <= 64
+            const size_t slot = (size_t)slot0 + (size_t)((ws - ws0) / WIN64);
+            if (!WRITE) {
+                const uint32_t tot = __reduce_add_sync(FULL, cnt);
+                if (lane == 0 && tot) atomicAdd(A.slot_counts + slot, ((unsigned long long)(tot >> 16) << 32) | (tot & 0xffffu));
+                continue;
+            }
+            // ---- write pass: exclusive prefix of (events, bytes) over the lanes
+            uint32_t pre = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, pre, d);
+                if ((int)lane >= d) pre += v;
+            }
+            const uint32_t total = __shfl_sync(FULL, pre, 31);
+            pre -= cnt;
+            const unsigned long long base = __ldg(A.slot_base + slot);
+            const long long out_a = (long long)(base & 0xffffffffull);
+            const int tok_a = (int)(base >> 32);
+            const int nbytes = (int)(total & 0xffffu);
+            const uint32_t phase = (uint32_t)(out_a & 15);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dd_base + 8u * lane), "r"(lo32(D)), "r"(hi32(D)) : "memory");
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(pre_base + 4u * lane), "r"(pre) : "memory");
+            // events of my word, in position order; a byte that is both a row start and a delimiter gives two entries
+            {
+                int t = tok_a + (int)(pre >> 16);
+                int32_t off0 = (int32_t)(out_a + (pre & 0xffffu));
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t d32 = h ? hi32(D) : lo32(D), r32 = h ? hi32(rsv) : lo32(rsv), t32 = h ? hi32(T) : lo32(T);
+                    uint32_t e32 = d32 | r32;
+                    while (e32) {
+                        const int b = __ffs((int)e32) - 1;
+                        e32 &= e32 - 1;
+                        const int32_t off = off0 + __popc(t32 & ((1u << b) - 1u));
+                        if ((r32 >> b) & 1u) A.tok_off[t++] = off;
+                        if ((d32 >> b) & 1u) A.tok_off[t++] = off;
+                    }
+                    off0 += __popc(t32);
+                }
+            }
+            // bytes of my word -> tile (as in tokenize)
+            {
+                uint32_t o = wb + (uint32_t)offsetof(WarpSmSplit, tile) + phase + (pre & 0xffffu);
+                const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t m = (uint32_t)(T >> (4 * i)) & 15u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (m & (1u << k)) {
+                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(o), "r"(w[i] >> (8 * k)) : "memory");
+                            ++o;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- row_offsets of the rows that start in this window: events before the row's first byte
+            for (int k0 = kfirst; k0 < kcur; k0 += 32) {
+                const int j = k0 + (int)lane;
+                if (j < kcur) {
+                    const int x = __ldg(A.offsets + j) - ws;  // 0 .. 2048
+                    int before;
+                    if (x >= WIN64) before = (int)(total >> 16);
+                    else {
+                        const uint32_t l = (uint32_t)x >> 6, bit = (uint32_t)x & 63u;
+                        const u64 below = (1ull << bit) - 1ull;
+                        before = (int)(lds32(pre_base + 4u * l) >> 16) + __popcll(lds64(dd_base + 8u * l) & below) + __popcll(lds64(rs_base + 8u * l) & below);
+                    }
+                    A.row_off[j] = tok_a + before;
+                }
+            }
+            // tile -> output, 16-byte stores on the aligned interior
+            {
+                const long long a0 = out_a & ~15ll, oe = out_a + nbytes;
+                for (long long q = a0 + 16 * (int)lane; q < oe; q += 16 * 32) {
+                    const char* src = W.tile + (q - a0);
+                    if (q >= out_a && q + 16 <= oe) *(uint4*)(A.out + q) = *(const uint4*)src;
+                    else {
+                        const long long lo = q < out_a ? out_a : q, hi = q + 16 < oe ? q + 16 : oe;
+                        for (long long r = lo; r < hi; ++r) A.out[r] = W.tile[r - a0];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}

@@ -143,3 +143,33 @@ def test_c1_split_csv_shape(oracle):
     assert len(cols) == len(want) == 12
     for a, b in zip(cols, want):
         assert oracle.unpack(*a.to_arrays()) == b.to_list()
+
+
+def test_split_record_bitstream_equals_per_row_path(c2, oracle):
+    """split_record with one delimiter byte through the bit-stream compaction (split_bits.cuh) against this repo's per-row path
+    on 2 M rows of C2 (many work items, rows straddling windows, null rows) and against the oracle on a prefix; a column
+    with empty valid rows must fall back and still be right."""
+    from custrings_b200 import nvstrings
+    from custrings_b200._lib import lib
+    from custrings_b200.workloads import slice_rows
+    n, chars, offsets, validity, nulls, col = c2
+    sub = col[0:2_000_000]
+    for delim in (" ", "e"):
+        tok_b, ro_b = sub.split_record_flat(delim)
+        lib().custr_set_regex_tier(2)  # bit-stream paths off: per-row kernels
+        try:
+            tok_r, ro_r = sub.split_record_flat(delim)
+        finally:
+            lib().custr_set_regex_tier(0)
+        assert np.array_equal(ro_b, ro_r), delim
+        for a, b in zip(tok_b.to_arrays(), tok_r.to_arrays()):
+            assert np.array_equal(a, b), delim
+    m = 50_000
+    c, o, v, nn = slice_rows(chars, offsets, validity, 0, m)
+    want, total = oracle.RefStrings.from_arrays(c, o, v, nn).split_record(" ")
+    got = nvstrings.from_offsets(c, o, m, v, nn).split_record(" ")
+    assert [None if g is None else g.to_host() for g in got] == [None if w is None else [x.decode() for x in w.to_list()] for w in want]
+    rows = ["a b", "", None, " x ", "", "tail"] * 4000  # empty VALID rows: not expressible as bits, must take the per-row path
+    got = nvstrings.to_device(rows).split_record(" ")
+    want = oracle.RefStrings.from_list(rows).split_record(" ")[0]
+    assert [None if g is None else g.to_host() for g in got] == [None if w is None else [x.decode() for x in w.to_list()] for w in want]

@@ -86,10 +86,10 @@ def test_pyni_entry_points_against_oracle(oracle):
         assert [host(c) for c in ps.n_split(h, " ", -1)] == [dec(c) for c in ref.split(" ")]
         assert [host(c) for c in ps.n_rsplit(h, None, 2)] == [dec(c) for c in ref.split(None, 2, right=True)]
         rec = ps.n_split_record(h, ",", -1)
-        want = ref.split_record(",")
+        want = ref.split_record(",")[0]
         assert [None if c == 0 else host(c) for c in rec] == [None if w is None else dec(w) for w in want]
         part = ps.n_partition(h, " ")
-        wantp = ref.partition(" ")
+        wantp = ref.partition(" ")[0]
         assert [None if c == 0 else host(c) for c in part] == [None if w is None else dec(w) for w in wantp]
         assert [host(c) for c in ps.n_findall(h, r"\d+")] == [dec(c) for c in ref.findall(r"\d+")]
         assert [host(c) for c in ps.n_extract(h, r"(\w)(\d)")] == [dec(c) for c in ref.extract(r"(\w)(\d)")]
