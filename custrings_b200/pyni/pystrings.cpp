@@ -401,7 +401,7 @@ static PyObject* n_extract_record(PyObject*, PyObject* args)
     for (int g = 0; g < k && g < 64; ++g) custr_column_free(cols[g]);
     return handle_list(rows);
 }
-// n_partition / n_rpartition (cptr, delimiter) -> one 3-row handle per row (0 for null rows)
+// n_partition / n_rpartition (cptr, delimiter) -> one 3-row handle per row (three nulls for a null row, like the reference)
 static PyObject* partition_like(PyObject* args, int right)
 {
     const custr_column* c = col_arg(args, 0);
@@ -410,10 +410,8 @@ static PyObject* partition_like(PyObject* args, int right)
     GIL_FREE(flat = custr_partition(c, d, right));
     if (!flat) return fail_none();
     const uint32_t n = custr_size(c);
-    const std::vector<uint8_t> valid = valid_rows(c);
     std::vector<custr_column*> rows(n, nullptr);
-    for (uint32_t i = 0; i < n; ++i)
-        if (valid[i]) rows[i] = custr_slice_rows(flat, (int32_t)(3 * i), (int32_t)(3 * i + 3));
+    for (uint32_t i = 0; i < n; ++i) rows[i] = custr_slice_rows(flat, (int32_t)(3 * i), (int32_t)(3 * i + 3));
     custr_column_free(flat);
     return handle_list(rows);
 }

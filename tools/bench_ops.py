@@ -57,7 +57,25 @@ def main():
     report("contains literal", timed(lambda: L.custr_contains(col.m_cptr, b"abcd", res8.data_ptr(), 1)), n, nbytes)
     report("find literal", timed(lambda: L.custr_find(col.m_cptr, b"abcd", 0, -1, res32.data_ptr(), 1)), n, nbytes)
     report("tokenize whitespace", timed(lambda: nvtext.tokenize(col), 3), n, nbytes)
-    report("split_record ' ' (flat)", timed(lambda: col.split_record_flat(" "), 3), n, nbytes)
+    report("split_record ' ' (flat, row offsets copied to the host)", timed(lambda: col.split_record_flat(" "), 3), n, nbytes)
+    import ctypes as C
+    row_off_dev = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+
+    def split_dev(delim=b" "):
+        tok = C.c_void_p()
+        k = L.custr_split_record(col.m_cptr, delim, -1, C.byref(tok), row_off_dev.data_ptr(), 1)
+        assert k >= 0, L.custr_last_error()
+        L.custr_column_free(tok)
+        return k
+    l0 = L.custr_launch_count()
+    ntok = split_dev()
+    report("split_record ' ' (flat, device resident; bit streams)", timed(split_dev, 5), n, nbytes,
+           {"tokens": int(ntok), "launches_per_call": int(L.custr_launch_count() - l0)})
+    L.custr_set_regex_tier(2)
+    try:
+        report("split_record ' ' (flat, device resident; per-row walk)", timed(split_dev, 3), n, nbytes)
+    finally:
+        L.custr_set_regex_tier(0)
     sub = col[0:1_000_000]
     report("split(' ', n=7) 8 columns, 1M rows", timed(lambda: sub.split(" ", 7), 3), 1_000_000, int(sub.byte_count()))
     report("hash", timed(lambda: L.custr_hash(col.m_cptr, res32.data_ptr(), 1)), n, nbytes)
