@@ -5,6 +5,7 @@
 // needle staged in shared memory.
 #include "common.cuh"
 #include "rowops.cuh"
+#include "regex_bits.h"
 
 namespace custr {
 
@@ -341,6 +342,12 @@ custr_column* custr_replace(const custr_column* col, const char* str, const char
             int32_t n = col->n;
             if (n == 0) return custr_create_from_offsets(nullptr, 0, nullptr, nullptr, 0, 0);
             int m = (int)strlen(str), rl = (int)strlen(repl);
+            if (maxrepl < 0 && !bits::g_force_generic) {  // every occurrence: bit-stream splice (replace_bits.cuh), no per-row walk
+                BufPtr chars, off;
+                int64_t total = 0;
+                if (bits::replace_literal_flat(col, str, m, repl, rl, chars, off, total))
+                    return make_column(chars, off, validity_copy(col), n, col->nulls, total);
+            }
             BufPtr d_t = upload(str, m + 1), d_r = upload(repl, rl + 1);
             Scratch<int32_t> lens((size_t)n + 1);
             CUSTR_CUDA(cudaMemsetAsync(lens.get() + n, 0, sizeof(int32_t), g_stream));

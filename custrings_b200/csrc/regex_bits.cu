@@ -447,6 +447,7 @@ bool tokenize_flat(const custr_column* col, const uint8_t* delims, int ndelims, 
 }
 
 #include "split_bits.cuh"
+#include "replace_bits.cuh"
 
 // NVStrings::split_record(delimiter) for ONE ASCII delimiter byte and no split limit through the bit-stream kernels
 // (split_bits.cuh): flat token column (chars + int32 offsets[ntok + 1]) and row_off[n + 1] (device).  False = not applicable
@@ -520,6 +521,79 @@ bool split_record_flat(const custr_column* col, uint8_t delim, BufPtr& out_chars
     a.out = (char*)out_chars->ptr;
     a.item_counter = (unsigned int*)counter->ptr + 1;
     auto kw = k_split_record64<true>;
+    LAUNCH(kw, blocks, THREADS, smem, a);
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    return true;
+}
+
+// NVStrings::replace, literal target, every occurrence (replace_bits.cuh).  false = not expressible there (bordered or long
+// target, replacement that could overflow the staging tile, unaligned view): the caller takes the per-row path.
+bool replace_literal_flat(const custr_column* col, const char* pat, int m, const char* repl, int rlen, BufPtr& out_chars, BufPtr& out_off,
+                          int64_t& nbytes)
+{
+    if (((uintptr_t)col->chars & 15) != 0 || col->nbytes == 0 || col->n == 0) return false;
+    if (m < 1 || m > REPL_PAT_MAX || rlen > REPL_REPL_MAX) return false;
+    for (int b = 1; b < m; ++b)  // a border: occurrences could overlap and the leftmost scan would skip some
+        if (memcmp(pat, pat + (m - b), (size_t)b) == 0) return false;
+    if (rlen > m && REPL_STRIDE + ((REPL_STRIDE + m - 1) / m) * (rlen - m) + m > REPL_TILE) return false;
+    const int32_t n = col->n;
+    ReplArgs a{};
+    a.chars = col->chars;
+    a.offsets = col->offsets;
+    a.n = n;
+    a.first = col->first_off;
+    a.end = col->first_off + (int32_t)col->nbytes;
+    a.nitems = (int)((col->nbytes + g_item_bytes - 1) / g_item_bytes);
+    a.m = m;
+    a.rlen = rlen;
+    memcpy(a.pat, pat, (size_t)m);
+    memcpy(a.repl, repl, (size_t)rlen);
+    a.item_bounds = ensure_item_bounds(col, a.offsets, a.first, a.nitems);
+    const size_t nslots = (size_t)col->nbytes / REPL_STRIDE + 2 * (size_t)a.nitems + 2;
+    Scratch<int32_t> item_w((size_t)a.nitems + 1), item_slot((size_t)a.nitems + 1);
+    CUSTR_CUDA(cudaMemsetAsync(item_w.get() + a.nitems, 0, sizeof(int32_t), g_stream));
+    LAUNCH(k_repl_item_windows, (a.nitems + 255) / 256, 256, 0, a.offsets, a.item_bounds, a.nitems, item_w.get());
+    {
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, item_w.get(), item_slot.get(), a.nitems + 1, g_stream);
+        BufPtr t = dev_alloc(tb);
+        CUSTR_CUDA(cub::DeviceScan::ExclusiveSum(t->ptr, tb, item_w.get(), item_slot.get(), a.nitems + 1, g_stream));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    a.item_slot = item_slot.get();
+    BufPtr counts = dev_alloc(sizeof(unsigned long long) * nslots), base = dev_alloc(sizeof(unsigned long long) * nslots);
+    BufPtr counter = dev_alloc(2 * sizeof(unsigned int));  // work-item counters of the two passes
+    CUSTR_CUDA(cudaMemsetAsync(counts->ptr, 0, sizeof(unsigned long long) * nslots, g_stream));
+    CUSTR_CUDA(cudaMemsetAsync(counter->ptr, 0, 2 * sizeof(unsigned int), g_stream));
+    a.slot_counts = (unsigned long long*)counts->ptr;
+    a.slot_base = (const unsigned long long*)base->ptr;
+    const int smem = WARPS * (int)sizeof(WarpSmRepl);
+    CUSTR_CUDA(cudaFuncSetAttribute(k_replace_lit64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUSTR_CUDA(cudaFuncSetAttribute(k_replace_lit64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int blocks = (a.nitems + WARPS - 1) / WARPS;
+    const int resident = num_sms() * 3;
+    if (blocks > resident) blocks = resident;
+    a.item_counter = (unsigned int*)counter->ptr;
+    auto kc = k_replace_lit64<false>;
+    LAUNCH(kc, blocks, THREADS, smem, a);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, a.slot_counts, (unsigned long long*)base->ptr, (int)nslots, g_stream);
+    BufPtr tmp = dev_alloc(tmp_bytes);
+    CUSTR_CUDA(cub::DeviceScan::ExclusiveSum(tmp->ptr, tmp_bytes, a.slot_counts, (unsigned long long*)base->ptr, (int)nslots, g_stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    unsigned long long total = 0;
+    CUSTR_CUDA(cudaMemcpyAsync(&total, (unsigned long long*)base->ptr + (nslots - 1), sizeof(total), cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    if (total > 0x7fffffffull) throw ArgError{fail(CUSTR_ERR_INVALID, "replace: result exceeds 2 GiB of chars")};
+    nbytes = (int64_t)total;
+    out_chars = dev_alloc((size_t)nbytes);
+    out_off = dev_alloc(sizeof(int32_t) * (size_t)(n + 1));
+    const int32_t last_off = (int32_t)nbytes;
+    CUSTR_CUDA(cudaMemcpyAsync((int32_t*)out_off->ptr + n, &last_off, sizeof(int32_t), cudaMemcpyHostToDevice, g_stream));
+    a.new_off = (int32_t*)out_off->ptr;
+    a.out = (char*)out_chars->ptr;
+    a.item_counter = (unsigned int*)counter->ptr + 1;
+    auto kw = k_replace_lit64<true>;
     LAUNCH(kw, blocks, THREADS, smem, a);
     CUSTR_CUDA(cudaStreamSynchronize(g_stream));
     return true;

@@ -46,6 +46,9 @@ bool tokenize_flat(const custr_column* col, const uint8_t* delims, int ndelims, 
 // NVStrings::split_record with one ASCII delimiter byte and no split limit as a bit-stream compaction (split_bits.cuh): flat
 // token column + row_off[n + 1] on the device.  False = not applicable (e.g. the column holds an empty valid row).
 bool split_record_flat(const custr_column* col, uint8_t delim, BufPtr& out_chars, BufPtr& out_off, BufPtr& row_off, int64_t& ntok, int64_t& nbytes);
+// replace with a literal target, every occurrence (replace_bits.cuh); false = not expressible, take the per-row path
+bool replace_literal_flat(const custr_column* col, const char* pat, int m, const char* repl, int rlen, BufPtr& out_chars, BufPtr& out_off,
+                          int64_t& nbytes);
 extern thread_local bool g_force_generic;
 extern thread_local bool g_no_spec;
 extern thread_local bool g_chain_win;

@@ -173,22 +173,40 @@ k_split_record64(const __grid_constant__ SplitArgs A)
             const uint32_t phase = (uint32_t)(out_a & 15);
             asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dd_base + 8u * lane), "r"(lo32(D)), "r"(hi32(D)) : "memory");
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(pre_base + 4u * lane), "r"(pre) : "memory");
-            // events of my word, in position order; a byte that is both a row start and a delimiter gives two entries
+            // events of my word, in position order; a byte that is both a row start and a delimiter gives two entries, the row
+            // start first.  Values are staged as 16-bit distances from out_a in the ring stage this window came from (its bytes
+            // now live in registers) and written back coalesced; a window with more events than the stage holds stores directly.
+            __syncwarp();  // every lane has read its chunk of this ring stage
+            const int nev = (int)(total >> 16);
+            const bool staged = nev <= WIN64 / 2 - 4;
+            const uint32_t evbuf = wb + (uint32_t)stage * WIN64 + 2u * ((uint32_t)tok_a & 3u);  // entry 0 = token tok_a
             {
-                int t = tok_a + (int)(pre >> 16);
-                int32_t off0 = (int32_t)(out_a + (pre & 0xffffu));
+                int rank0 = (int)(pre >> 16);
+                int val0 = (int)(pre & 0xffffu);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const uint32_t d32 = h ? hi32(D) : lo32(D), r32 = h ? hi32(rsv) : lo32(rsv), t32 = h ? hi32(T) : lo32(T);
-                    uint32_t e32 = d32 | r32;
-                    while (e32) {
-                        const int b = __ffs((int)e32) - 1;
-                        e32 &= e32 - 1;
-                        const int32_t off = off0 + __popc(t32 & ((1u << b) - 1u));
-                        if ((r32 >> b) & 1u) A.tok_off[t++] = off;
-                        if ((d32 >> b) & 1u) A.tok_off[t++] = off;
+                    const uint32_t d32 = h ? hi32(D) : lo32(D), r32 = h ? hi32(rsv) : lo32(rsv), o32 = h ? hi32(own) : lo32(own);
+                    // T bytes below bit b of this half = (b - first owned bit) - delimiters below b: own is one run of bits
+                    const int c0 = val0 - (o32 ? __ffs((int)o32) - 1 : 0);
+                    int nd = 0;
+                    for (uint32_t e = d32; e; e &= e - 1, ++nd) {  // the token behind each delimiter
+                        const int b = __ffs((int)e) - 1;
+                        const int rank = rank0 + nd + __popc(r32 & ((2u << b) - 1u));
+                        const int val = c0 + b - nd;
+                        if (staged) asm volatile("st.shared.u16 [%0], %1;" ::"r"(evbuf + 2u * (uint32_t)rank), "h"((unsigned short)val) : "memory");
+                        else A.tok_off[tok_a + rank] = (int32_t)out_a + val;
                     }
-                    off0 += __popc(t32);
+                    int nr = 0;
+                    for (uint32_t e = r32; e; e &= e - 1, ++nr) {  // the first token of each row (few)
+                        const int b = __ffs((int)e) - 1;
+                        const int ndb = __popc(d32 & ((1u << b) - 1u));
+                        const int rank = rank0 + nr + ndb;
+                        const int val = c0 + b - ndb;
+                        if (staged) asm volatile("st.shared.u16 [%0], %1;" ::"r"(evbuf + 2u * (uint32_t)rank), "h"((unsigned short)val) : "memory");
+                        else A.tok_off[tok_a + rank] = (int32_t)out_a + val;
+                    }
+                    rank0 += nd + nr;
+                    val0 += __popc(o32) - nd;
                 }
             }
             // bytes of my word -> tile (as in tokenize)
@@ -223,18 +241,23 @@ k_split_record64(const __grid_constant__ SplitArgs A)
                     A.row_off[j] = tok_a + before;
                 }
             }
-            // tile -> output, 16-byte stores on the aligned interior
-            {
-                const long long a0 = out_a & ~15ll, oe = out_a + nbytes;
-                for (long long q = a0 + 16 * (int)lane; q < oe; q += 16 * 32) {
-                    const char* src = W.tile + (q - a0);
-                    if (q >= out_a && q + 16 <= oe) *(uint4*)(A.out + q) = *(const uint4*)src;
+            if (staged) {  // staged events -> token offsets, 16-byte stores on the aligned interior
+                const int a0 = tok_a & ~3, te = tok_a + nev;
+                const uint32_t buf0 = wb + (uint32_t)stage * WIN64;
+                const int32_t add = (int32_t)out_a;
+                for (int q = a0 + 4 * (int)lane; q < te; q += 128) {
+                    const u64 v = lds64(buf0 + 2u * (uint32_t)(q - a0));
+                    const int4 o = make_int4(add + (int)(lo32(v) & 0xffffu), add + (int)(lo32(v) >> 16), add + (int)(hi32(v) & 0xffffu), add + (int)(hi32(v) >> 16));
+                    if (q >= tok_a && q + 4 <= te) *(int4*)(A.tok_off + q) = o;
                     else {
-                        const long long lo = q < out_a ? out_a : q, hi = q + 16 < oe ? q + 16 : oe;
-                        for (long long r = lo; r < hi; ++r) A.out[r] = W.tile[r - a0];
+                        if (q >= tok_a && q < te) A.tok_off[q] = o.x;
+                        if (q + 1 >= tok_a && q + 1 < te) A.tok_off[q + 1] = o.y;
+                        if (q + 2 >= tok_a && q + 2 < te) A.tok_off[q + 2] = o.z;
+                        if (q + 3 >= tok_a && q + 3 < te) A.tok_off[q + 3] = o.w;
                     }
                 }
             }
+            flush_tile(W.tile, A.out, out_a, nbytes, lane);
             __syncwarp();
         }
     }

@@ -64,6 +64,24 @@ __global__ void k_tok_item_windows(const int32_t* __restrict__ offsets, const in
     out[item] = w;
 }
 
+// tile (its byte 0 = output byte out_a & ~15) -> out[out_a, out_a + nbytes): 16-byte stores on the aligned interior; the partial
+// chunk at either end goes out byte-wise, one byte per lane (lanes 0-15 the head, 16-31 the tail)
+__device__ __forceinline__ void flush_tile(const char* tile, char* __restrict__ out, long long out_a, int nbytes, uint32_t lane)
+{
+    const long long a0 = out_a & ~15ll, oe = out_a + nbytes;
+    for (long long q = a0 + 16 * (int)lane; q + 16 <= oe; q += 16 * 32)
+        if (q >= out_a) *(uint4*)(out + q) = *(const uint4*)(tile + (q - a0));
+    const long long qt = oe & ~15ll;
+    const int i = (int)lane & 15;
+    if (lane < 16) {
+        const long long r = a0 + i;
+        if (a0 < out_a && r >= out_a && r < oe) out[r] = tile[r - a0];
+    } else {
+        const long long r = qt + i;
+        if ((qt > a0 || a0 == out_a) && r < oe) out[r] = tile[r - a0];
+    }
+}
+
 template <bool WRITE>
 __global__ void __launch_bounds__(THREADS, 3)
 k_tokenize64(const __grid_constant__ TokArgs A)
@@ -222,18 +240,7 @@ k_tokenize64(const __grid_constant__ TokArgs A)
             __syncwarp();
             if (stage_toks)
                 for (int i = (int)lane; i < ntoks; i += 32) A.tok_off[tok_a + i] = (int32_t)lds32(tokbuf + 4u * (uint32_t)i);
-            // tile -> output, 16-byte stores on the aligned interior
-            {
-                const long long a0 = out_a & ~15ll, oe = out_a + nbytes;
-                for (long long q = a0 + 16 * (int)lane; q < oe; q += 16 * 32) {
-                    const char* src = W.tile + (q - a0);
-                    if (q >= out_a && q + 16 <= oe) *(uint4*)(A.out + q) = *(const uint4*)src;
-                    else {
-                        const long long lo = q < out_a ? out_a : q, hi = q + 16 < oe ? q + 16 : oe;
-                        for (long long r = lo; r < hi; ++r) A.out[r] = W.tile[r - a0];
-                    }
-                }
-            }
+            flush_tile(W.tile, A.out, out_a, nbytes, lane);
             __syncwarp();
         }
     }

@@ -173,3 +173,51 @@ def test_split_record_bitstream_equals_per_row_path(c2, oracle):
     got = nvstrings.to_device(rows).split_record(" ")
     want = oracle.RefStrings.from_list(rows).split_record(" ")[0]
     assert [None if g is None else g.to_host() for g in got] == [None if w is None else [x.decode() for x in w.to_list()] for w in want]
+
+
+def test_literal_replace_bitstream_equals_per_row_path(c2, oracle):
+    """replace with a literal, border-free target through the bit-stream splice (replace_bits.cuh) against this repo's per-row
+    path on 2 M rows of C2 and against the oracle on a prefix; then targeted layouts: occurrences straddling lane / window /
+    row boundaries, rows longer than many windows, empty and null rows, multi-byte targets, growing and shrinking replacements,
+    and a bordered target ("aa"), which must take the per-row path and still be right."""
+    from custrings_b200 import nvstrings
+    from custrings_b200._lib import lib
+    from custrings_b200.workloads import slice_rows
+    n, chars, offsets, validity, nulls, col = c2
+
+    def both(column, tgt, repl):
+        got = column.replace(tgt, repl, regex=False)
+        lib().custr_set_regex_tier(2)  # bit-stream paths off: per-row kernel
+        try:
+            ref = column.replace(tgt, repl, regex=False)
+        finally:
+            lib().custr_set_regex_tier(0)
+        for a, b in zip(got.to_arrays(), ref.to_arrays()):
+            assert np.array_equal(a, b), (tgt, repl)
+        return got
+
+    sub = col[0:2_000_000]
+    for tgt, repl in ((" ", "_"), ("e", ""), ("th", "THE"), ("ing ", "#"), ("a", "xyz")):
+        both(sub, tgt, repl)
+    m = 50_000
+    c, o, v, nn = slice_rows(chars, offsets, validity, 0, m)
+    want = oracle.RefStrings.from_arrays(c, o, v, nn).replace("he", "<HE>")
+    got = nvstrings.from_offsets(c, o, m, v, nn).replace("he", "<HE>", regex=False)
+    assert got.to_host() == [None if x is None else x.decode() for x in want.to_list()]
+
+    rng = np.random.default_rng(11)
+    rows = []
+    for k in range(3000):
+        ln = int(rng.choice([0, 1, 2, 3, 30, 63, 64, 65, 127, 1983, 1984, 1985, 2047, 2048, 2049, 5000]))
+        rows.append(None if k % 97 == 5 else "".join(rng.choice(list("abcé ,"), ln).tolist()))
+    rows.append("ab" * 40_000)                      # one row over many windows, every byte replaced
+    rows.append("x" * 100_000 + "abc")
+    rows += ["abc", "", "bc", "ab", "cab", None, "abcabc"] * 50
+    dev = nvstrings.to_device(rows)
+    ref = oracle.RefStrings.from_list(rows)
+    for tgt, repl in (("ab", "X"), ("abc", ""), ("c", "cc"), ("é", "e"), ("b,", "béb"), (", ", ""), ("ca", "123456"), ("é ", "")):
+        got = both(dev, tgt, repl)
+        assert got.to_host() == [None if x is None else x.decode() for x in ref.replace(tgt, repl).to_list()], (tgt, repl)
+    for tgt, repl in (("aa", "b"), ("abab", "-")):  # bordered targets: per-row path
+        got = dev.replace(tgt, repl, regex=False)
+        assert got.to_host() == [None if x is None else x.decode() for x in ref.replace(tgt, repl).to_list()], (tgt, repl)

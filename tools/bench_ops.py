@@ -53,7 +53,13 @@ def main():
     L.custr_set_regex_tier(0)
     report("count_re (bit streams + word scans, last-loop chains)", timed(lambda: L.custr_count_re(col.m_cptr, pat, res32.data_ptr(), 1), 3), n, nbytes)
     report("replace_re \\b\\w{4,}\\b -> # (bit streams + word scans, 2 passes)", timed(lambda: col.replace(r"\b\w{4,}\b", "#"), 3), n, nbytes)
-    report("replace_re literal 'ab' -> X (literal kernel)", timed(lambda: col.replace("ab", "X"), 3), n, nbytes)
+    report("replace literal 'ab' -> X (bit-stream splice)", timed(lambda: col.replace("ab", "X"), 3), n, nbytes)
+    report("replace literal ' ' -> '_' (bit-stream splice)", timed(lambda: col.replace(" ", "_", regex=False), 3), n, nbytes)
+    L.custr_set_regex_tier(2)
+    try:
+        report("replace literal 'ab' -> X (per-row walk)", timed(lambda: col.replace("ab", "X"), 3), n, nbytes)
+    finally:
+        L.custr_set_regex_tier(0)
     report("contains literal", timed(lambda: L.custr_contains(col.m_cptr, b"abcd", res8.data_ptr(), 1)), n, nbytes)
     report("find literal", timed(lambda: L.custr_find(col.m_cptr, b"abcd", 0, -1, res32.data_ptr(), 1)), n, nbytes)
     report("tokenize whitespace", timed(lambda: nvtext.tokenize(col), 3), n, nbytes)
@@ -69,8 +75,8 @@ def main():
         return k
     l0 = L.custr_launch_count()
     ntok = split_dev()
-    report("split_record ' ' (flat, device resident; bit streams)", timed(split_dev, 5), n, nbytes,
-           {"tokens": int(ntok), "launches_per_call": int(L.custr_launch_count() - l0)})
+    per_call = int(L.custr_launch_count() - l0)
+    report("split_record ' ' (flat, device resident; bit streams)", timed(split_dev, 5), n, nbytes, {"tokens": int(ntok), "launches_per_call": per_call})
     L.custr_set_regex_tier(2)
     try:
         report("split_record ' ' (flat, device resident; per-row walk)", timed(split_dev, 3), n, nbytes)

@@ -4,7 +4,8 @@ per source line of the kernel body (inlined helpers are charged to the line that
 histogram weighted by execution count.  The SASS <-> source-line map comes from nvdisasm's line info of the object that was
 profiled (built with -lineinfo).
 
-    python tools/ncu_by_line.py REPORT.ncu-rep OBJECT.o KERNEL_SUBSTRING [--windows N] > profiles/...txt"""
+    python tools/ncu_by_line.py REPORT.ncu-rep OBJECT.o KERNEL_SUBSTRING [--windows N] [--launch I] > profiles/...txt
+(--launch I: the I-th launch of a report that holds several)"""
 import collections
 import csv
 import io
@@ -20,9 +21,13 @@ ALU = {"LOP3", "SHF", "PRMT", "ISETP", "SEL", "IADD3", "VIADD", "LEA", "PLOP3", 
 
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr, data = rows[1], rows[2:]
+heads = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]  # one section per captured launch
+which = int(sys.argv[sys.argv.index("--launch") + 1]) if "--launch" in sys.argv else 0
+h0 = heads[which]
+h1 = heads[which + 1] if which + 1 < len(heads) else len(rows)
+hdr, data = rows[h0 + 1], rows[h0 + 2:h1]
 iS, iE = hdr.index("Source"), hdr.index("Instructions Executed")
-execs = [(r[iS].strip(), int(r[iE] or 0)) for r in data]
+execs = [(r[iS].strip(), int(r[iE] or 0)) for r in data if len(r) > max(iS, iE)]
 
 with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=td, capture_output=True)
