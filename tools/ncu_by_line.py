@@ -4,7 +4,7 @@ per source line of the kernel body (inlined helpers are charged to the line that
 histogram weighted by execution count.  The SASS <-> source-line map comes from nvdisasm's line info of the object that was
 profiled (built with -lineinfo).
 
-    python tools/ncu_by_line.py REPORT.ncu-rep OBJECT.o KERNEL_SUBSTRING [--windows N] [--launch I] > profiles/...txt
+    python tools/ncu_by_line.py REPORT.ncu-rep OBJECT.o KERNEL_SUBSTRING [--windows N] [--launch I] [--depth D] > profiles/...txt
 (--launch I: the I-th launch of a report that holds several)"""
 import collections
 import csv
@@ -17,6 +17,7 @@ import tempfile
 
 rep, obj, key = sys.argv[1:4]
 nwin = float(sys.argv[sys.argv.index("--windows") + 1]) if "--windows" in sys.argv else 524288.0
+depth = int(sys.argv[sys.argv.index("--depth") + 1]) if "--depth" in sys.argv else 0  # 1: the kernel body is itself an inlined function
 ALU = {"LOP3", "SHF", "PRMT", "ISETP", "SEL", "IADD3", "VIADD", "LEA", "PLOP3", "POPC", "FLO", "BREV", "VIMNMX", "SGXT", "BMSK", "MOV", "IADD", "VOTE"}
 
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
@@ -44,7 +45,7 @@ for l in dis[start:end]:
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
         if pend:
-            cur, pend = pend[-1], []
+            cur, pend = pend[max(0, len(pend) - 1 - depth)], []
         ins.append((m.group(2).strip(), cur))
 if len(ins) != len(execs):
     sys.exit("instruction count mismatch: report %d vs object %d (not the profiled binary?)" % (len(execs), len(ins)))
