@@ -452,9 +452,14 @@ bool tokenize_flat(const custr_column* col, const uint8_t* delims, int ndelims, 
 // NVStrings::split_record(delimiter) for ONE ASCII delimiter byte and no split limit through the bit-stream kernels
 // (split_bits.cuh): flat token column (chars + int32 offsets[ntok + 1]) and row_off[n + 1] (device).  False = not applicable
 // (unaligned chars base, empty column, or the column holds an empty valid row): the caller uses the per-row path.
+// The splice kernels pay per byte AND per row start (ROWSTART scatter, one output offset per row); the per-row kernels pay per
+// row.  Below ~16 bytes per row (the README's day-of-week column: 3.3) the per-row walk wins — C3 chain 1.9 ms vs 5.7 ms.
+constexpr int64_t STREAM_MIN_ROW_BYTES = 16;
+
 bool split_record_flat(const custr_column* col, uint8_t delim, BufPtr& out_chars, BufPtr& out_off, BufPtr& row_off, int64_t& ntok, int64_t& nbytes)
 {
     if (((uintptr_t)col->chars & 15) != 0 || col->nbytes == 0 || col->n == 0 || delim >= 0x80) return false;
+    if (col->nbytes < STREAM_MIN_ROW_BYTES * (int64_t)col->n) return false;
     const int32_t n = col->n;
     SplitArgs a{};
     a.chars = col->chars;
@@ -533,6 +538,7 @@ bool replace_literal_flat(const custr_column* col, const char* pat, int m, const
 {
     if (((uintptr_t)col->chars & 15) != 0 || col->nbytes == 0 || col->n == 0) return false;
     if (m < 1 || m > REPL_PAT_MAX || rlen > REPL_REPL_MAX) return false;
+    if (col->nbytes < STREAM_MIN_ROW_BYTES * (int64_t)col->n) return false;
     for (int b = 1; b < m; ++b)  // a border: occurrences could overlap and the leftmost scan would skip some
         if (memcmp(pat, pat + (m - b), (size_t)b) == 0) return false;
     if (rlen > m && REPL_STRIDE + ((REPL_STRIDE + m - 1) / m) * (rlen - m) + m > REPL_TILE) return false;

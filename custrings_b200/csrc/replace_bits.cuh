@@ -42,7 +42,7 @@ struct __align__(64) WarpSmRepl {
     uint32_t kk[64];    // kept bytes this window owns
     uint32_t mm[64];    // occurrence starts this window owns
     uint32_t pre[32];   // exclusive prefix over the lanes of the output bytes
-    char tile[REPL_TILE + 32];
+    char tile[tile_padded_bytes(REPL_TILE + 32)];
 };
 
 // number of windows every work item touches (0 for an item without bytes)
@@ -203,7 +203,8 @@ k_replace_lit64(const __grid_constant__ ReplArgs A)
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(pre_base + 4u * lane), "r"(pre) : "memory");
             // my kept bytes and replacements -> tile, in position order
             {
-                uint32_t o = wb + (uint32_t)offsetof(WarpSmRepl, tile) + phase + pre;
+                const uint32_t tile = wb + (uint32_t)offsetof(WarpSmRepl, tile);
+                uint32_t o = phase + pre;
                 const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -211,11 +212,11 @@ k_replace_lit64(const __grid_constant__ ReplArgs A)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (mm4 & (1u << k)) {
-                            for (int q = 0; q < rlen; ++q) asm volatile("st.shared.u8 [%0], %1;" ::"r"(o + (uint32_t)q), "r"(lds8(repl_base + (uint32_t)q)) : "memory");
+                            for (int q = 0; q < rlen; ++q) asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile + tile_pad(o + (uint32_t)q)), "r"(lds8(repl_base + (uint32_t)q)) : "memory");
                             o += (uint32_t)rlen;
                         }
                         if (km & (1u << k)) {
-                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(o), "r"(w[i] >> (8 * k)) : "memory");
+                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile + tile_pad(o)), "r"(w[i] >> (8 * k)) : "memory");
                             ++o;
                         }
                     }
@@ -238,7 +239,7 @@ k_replace_lit64(const __grid_constant__ ReplArgs A)
                     A.new_off[j] = (int32_t)(out_a + before);
                 }
             }
-            flush_tile(W.tile, A.out, out_a, (int)total, lane);
+            flush_tile(wb + (uint32_t)offsetof(WarpSmRepl, tile), A.out, out_a, (int)total, lane);
             __syncwarp();
         }
     }

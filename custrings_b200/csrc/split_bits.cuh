@@ -37,7 +37,7 @@ struct __align__(64) WarpSmSplit {
     uint32_t rs[64];    // ROWSTART of valid rows (RSV), one bit per byte of the window
     uint32_t dd[64];    // D & own: the delimiter bytes this item owns
     uint32_t pre[32];   // exclusive prefix over the lanes of (events << 16 | T bytes)
-    char tile[WIN64 + 32];
+    char tile[tile_padded_bytes(WIN64 + 32)];
 };
 
 __device__ __forceinline__ bool split_row_valid(const SplitArgs& A, int row)
@@ -211,7 +211,8 @@ k_split_record64(const __grid_constant__ SplitArgs A)
             }
             // bytes of my word -> tile (as in tokenize)
             {
-                uint32_t o = wb + (uint32_t)offsetof(WarpSmSplit, tile) + phase + (pre & 0xffffu);
+                const uint32_t tile = wb + (uint32_t)offsetof(WarpSmSplit, tile);
+                uint32_t o = phase + (pre & 0xffffu);
                 const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -219,7 +220,7 @@ k_split_record64(const __grid_constant__ SplitArgs A)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (m & (1u << k)) {
-                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(o), "r"(w[i] >> (8 * k)) : "memory");
+                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile + tile_pad(o)), "r"(w[i] >> (8 * k)) : "memory");
                             ++o;
                         }
                     }
@@ -257,7 +258,7 @@ k_split_record64(const __grid_constant__ SplitArgs A)
                     }
                 }
             }
-            flush_tile(W.tile, A.out, out_a, nbytes, lane);
+            flush_tile(wb + (uint32_t)offsetof(WarpSmSplit, tile), A.out, out_a, nbytes, lane);
             __syncwarp();
         }
     }

@@ -33,10 +33,17 @@ struct TokArgs {
 
 constexpr int TOK_DELIMS_MAX = 8;
 
+// The staging tile is padded by one word per 64 bytes: lanes that each write ~64 output bytes start 17 words apart instead of
+// 16, so their byte stores fall into different banks (unpadded, a window that drops nothing is a 16-way conflict per store:
+// profiles/r2_ncu_splice.txt).  tile_pad maps a logical tile offset to its padded one; 16-byte aligned logical chunks stay
+// contiguous (they never straddle a 64-byte block) but are only word aligned.
+__device__ __forceinline__ uint32_t tile_pad(uint32_t o) { return o + ((o >> 6) << 2); }
+constexpr int tile_padded_bytes(int logical) { return logical + (logical / 64 + 1) * 4; }
+
 struct __align__(64) WarpSmTok {
     char ring[RING_STAGES][WIN64];
     uint32_t rs[64];
-    char tile[WIN64 + 32];  // compacted bytes of the window, mirrored to the 16-byte phase of the output
+    char tile[tile_padded_bytes(WIN64 + 32)];  // compacted bytes of the window, mirrored to the 16-byte phase of the output
 };
 
 __device__ __forceinline__ u64 delim_stream(const TokArgs& A, const u64 (&p)[8])
@@ -64,21 +71,24 @@ __global__ void k_tok_item_windows(const int32_t* __restrict__ offsets, const in
     out[item] = w;
 }
 
-// tile (its byte 0 = output byte out_a & ~15) -> out[out_a, out_a + nbytes): 16-byte stores on the aligned interior; the partial
-// chunk at either end goes out byte-wise, one byte per lane (lanes 0-15 the head, 16-31 the tail)
-__device__ __forceinline__ void flush_tile(const char* tile, char* __restrict__ out, long long out_a, int nbytes, uint32_t lane)
+// tile (shared address; its logical byte 0 = output byte out_a & ~15) -> out[out_a, out_a + nbytes): 16-byte stores on the
+// aligned interior; the partial chunk at either end goes out byte-wise, one byte per lane (lanes 0-15 the head, 16-31 the tail)
+__device__ __forceinline__ void flush_tile(uint32_t tile, char* __restrict__ out, long long out_a, int nbytes, uint32_t lane)
 {
     const long long a0 = out_a & ~15ll, oe = out_a + nbytes;
     for (long long q = a0 + 16 * (int)lane; q + 16 <= oe; q += 16 * 32)
-        if (q >= out_a) *(uint4*)(out + q) = *(const uint4*)(tile + (q - a0));
+        if (q >= out_a) {
+            const uint32_t a = tile + tile_pad((uint32_t)(q - a0));
+            *(uint4*)(out + q) = make_uint4(lds32(a), lds32(a + 4u), lds32(a + 8u), lds32(a + 12u));
+        }
     const long long qt = oe & ~15ll;
     const int i = (int)lane & 15;
     if (lane < 16) {
         const long long r = a0 + i;
-        if (a0 < out_a && r >= out_a && r < oe) out[r] = tile[r - a0];
+        if (a0 < out_a && r >= out_a && r < oe) out[r] = (char)lds8(tile + tile_pad((uint32_t)(r - a0)));
     } else {
         const long long r = qt + i;
-        if ((qt > a0 || a0 == out_a) && r < oe) out[r] = tile[r - a0];
+        if ((qt > a0 || a0 == out_a) && r < oe) out[r] = (char)lds8(tile + tile_pad((uint32_t)(r - a0)));
     }
 }
 
@@ -223,7 +233,8 @@ k_tokenize64(const __grid_constant__ TokArgs A)
             // bytes of my word -> tile: straight-line, one predicated byte store per input byte (the words are still in
             // registers; delimiters are sparse, so nearly every store is taken)
             {
-                uint32_t o = wb + (uint32_t)offsetof(WarpSmTok, tile) + phase + (pre & 0xffffu);
+                const uint32_t tile = wb + (uint32_t)offsetof(WarpSmTok, tile);
+                uint32_t o = phase + (pre & 0xffffu);
                 const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -231,7 +242,7 @@ k_tokenize64(const __grid_constant__ TokArgs A)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (m & (1u << k)) {
-                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(o), "r"(w[i] >> (8 * k)) : "memory");
+                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile + tile_pad(o)), "r"(w[i] >> (8 * k)) : "memory");
                             ++o;
                         }
                     }
@@ -240,7 +251,7 @@ k_tokenize64(const __grid_constant__ TokArgs A)
             __syncwarp();
             if (stage_toks)
                 for (int i = (int)lane; i < ntoks; i += 32) A.tok_off[tok_a + i] = (int32_t)lds32(tokbuf + 4u * (uint32_t)i);
-            flush_tile(W.tile, A.out, out_a, nbytes, lane);
+            flush_tile(wb + (uint32_t)offsetof(WarpSmTok, tile), A.out, out_a, nbytes, lane);
             __syncwarp();
         }
     }
