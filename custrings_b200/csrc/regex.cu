@@ -1267,6 +1267,15 @@ custr_column* custr_replace_re(const custr_column* col, const char* pattern, con
                 SpanRun sr;
                 if (run_span_streams(*c, col, sr)) {
                     const int k_chars = (int)cd->nsteps - 1;
+                    if (maxrepl < 0 && !bits::g_chain_win && bits::replace_spans_ok(*cd) && read_dirty(sr) == 0) {
+                        // single-class chain, every match: streaming splice over the span streams, no per-row walk
+                        BufPtr chars2, off2;
+                        int64_t total2 = 0;
+                        if (bits::replace_spans_flat(col, *cd, sr.ss, repl, repl_len, chars2, off2, total2)) {
+                            g_last_tier = "bitsplice";
+                            return make_column(chars2, off2, copy_validity(col), n, col->nulls, total2);
+                        }
+                    }
                     LAUNCH(k_span_replace, vm_grid(n) * 2, 256, 0, view_of(col), sr.view(), (const uint8_t*)sr.hits->ptr, k_chars, repl_len, maxrepl,
                            lens.get());
                     if (read_dirty(sr) == 0) {

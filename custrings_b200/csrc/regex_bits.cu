@@ -342,6 +342,7 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
         spans->k = a.span_k;
         spans->a = a.span_a;
         spans->base = a.span_base;
+        spans->words = (long long)words;
     }
     int blocks = (a.nitems + WARPS - 1) / WARPS;
     int cap = num_sms() * 8;
@@ -531,34 +532,21 @@ bool split_record_flat(const custr_column* col, uint8_t delim, BufPtr& out_chars
     return true;
 }
 
-// NVStrings::replace, literal target, every occurrence (replace_bits.cuh).  false = not expressible there (bordered or long
-// target, replacement that could overflow the staging tile, unaligned view): the caller takes the per-row path.
-bool replace_literal_flat(const custr_column* col, const char* pat, int m, const char* repl, int rlen, BufPtr& out_chars, BufPtr& out_off,
-                          int64_t& nbytes)
+// Both splice modes of replace_bits.cuh: count pass -> scan -> write pass.  `a` holds the mode's matcher arguments.
+static bool splice_run(const custr_column* col, ReplArgs& a, int mode, BufPtr& out_chars, BufPtr& out_off, int64_t& nbytes)
 {
-    if (((uintptr_t)col->chars & 15) != 0 || col->nbytes == 0 || col->n == 0) return false;
-    if (m < 1 || m > REPL_PAT_MAX || rlen > REPL_REPL_MAX) return false;
-    if (col->nbytes < STREAM_MIN_ROW_BYTES * (int64_t)col->n) return false;
-    for (int b = 1; b < m; ++b)  // a border: occurrences could overlap and the leftmost scan would skip some
-        if (memcmp(pat, pat + (m - b), (size_t)b) == 0) return false;
-    if (rlen > m && REPL_STRIDE + ((REPL_STRIDE + m - 1) / m) * (rlen - m) + m > REPL_TILE) return false;
     const int32_t n = col->n;
-    ReplArgs a{};
     a.chars = col->chars;
     a.offsets = col->offsets;
     a.n = n;
     a.first = col->first_off;
     a.end = col->first_off + (int32_t)col->nbytes;
     a.nitems = (int)((col->nbytes + g_item_bytes - 1) / g_item_bytes);
-    a.m = m;
-    a.rlen = rlen;
-    memcpy(a.pat, pat, (size_t)m);
-    memcpy(a.repl, repl, (size_t)rlen);
     a.item_bounds = ensure_item_bounds(col, a.offsets, a.first, a.nitems);
     const size_t nslots = (size_t)col->nbytes / REPL_STRIDE + 2 * (size_t)a.nitems + 2;
     Scratch<int32_t> item_w((size_t)a.nitems + 1), item_slot((size_t)a.nitems + 1);
     CUSTR_CUDA(cudaMemsetAsync(item_w.get() + a.nitems, 0, sizeof(int32_t), g_stream));
-    LAUNCH(k_repl_item_windows, (a.nitems + 255) / 256, 256, 0, a.offsets, a.item_bounds, a.nitems, item_w.get());
+    LAUNCH(k_repl_item_windows, (a.nitems + 255) / 256, 256, 0, a.offsets, a.item_bounds, a.nitems, mode == 1 ? ~63 : ~15, item_w.get());
     {
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, item_w.get(), item_slot.get(), a.nitems + 1, g_stream);
@@ -568,19 +556,21 @@ bool replace_literal_flat(const custr_column* col, const char* pat, int m, const
     }
     a.item_slot = item_slot.get();
     BufPtr counts = dev_alloc(sizeof(unsigned long long) * nslots), base = dev_alloc(sizeof(unsigned long long) * nslots);
-    BufPtr counter = dev_alloc(2 * sizeof(unsigned int));  // work-item counters of the two passes
+    BufPtr counter = dev_alloc(4 * sizeof(unsigned int));  // [0], [1] work-item counters of the two passes, [2] flags
     CUSTR_CUDA(cudaMemsetAsync(counts->ptr, 0, sizeof(unsigned long long) * nslots, g_stream));
-    CUSTR_CUDA(cudaMemsetAsync(counter->ptr, 0, 2 * sizeof(unsigned int), g_stream));
+    CUSTR_CUDA(cudaMemsetAsync(counter->ptr, 0, 4 * sizeof(unsigned int), g_stream));
     a.slot_counts = (unsigned long long*)counts->ptr;
     a.slot_base = (const unsigned long long*)base->ptr;
+    a.flags = (unsigned int*)counter->ptr + 2;
     const int smem = WARPS * (int)sizeof(WarpSmRepl);
-    CUSTR_CUDA(cudaFuncSetAttribute(k_replace_lit64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUSTR_CUDA(cudaFuncSetAttribute(k_replace_lit64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    auto kc = mode == 1 ? k_replace_splice64<1, false> : k_replace_splice64<0, false>;
+    auto kw = mode == 1 ? k_replace_splice64<1, true> : k_replace_splice64<0, true>;
+    CUSTR_CUDA(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUSTR_CUDA(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int blocks = (a.nitems + WARPS - 1) / WARPS;
     const int resident = num_sms() * 3;
     if (blocks > resident) blocks = resident;
     a.item_counter = (unsigned int*)counter->ptr;
-    auto kc = k_replace_lit64<false>;
     LAUNCH(kc, blocks, THREADS, smem, a);
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, a.slot_counts, (unsigned long long*)base->ptr, (int)nslots, g_stream);
@@ -588,8 +578,11 @@ bool replace_literal_flat(const custr_column* col, const char* pat, int m, const
     CUSTR_CUDA(cub::DeviceScan::ExclusiveSum(tmp->ptr, tmp_bytes, a.slot_counts, (unsigned long long*)base->ptr, (int)nslots, g_stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     unsigned long long total = 0;
+    unsigned int flags = 0;
     CUSTR_CUDA(cudaMemcpyAsync(&total, (unsigned long long*)base->ptr + (nslots - 1), sizeof(total), cudaMemcpyDeviceToHost, g_stream));
+    CUSTR_CUDA(cudaMemcpyAsync(&flags, a.flags, sizeof(flags), cudaMemcpyDeviceToHost, g_stream));
     CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    if (flags & 1u) return false;
     if (total > 0x7fffffffull) throw ArgError{fail(CUSTR_ERR_INVALID, "replace: result exceeds 2 GiB of chars")};
     nbytes = (int64_t)total;
     out_chars = dev_alloc((size_t)nbytes);
@@ -599,10 +592,65 @@ bool replace_literal_flat(const custr_column* col, const char* pat, int m, const
     a.new_off = (int32_t*)out_off->ptr;
     a.out = (char*)out_chars->ptr;
     a.item_counter = (unsigned int*)counter->ptr + 1;
-    auto kw = k_replace_lit64<true>;
     LAUNCH(kw, blocks, THREADS, smem, a);
     CUSTR_CUDA(cudaStreamSynchronize(g_stream));
     return true;
+}
+// every occurrence adds rlen bytes and removes at least `shortest`: the most a 1984-byte window can emit must fit the tile
+static bool splice_fits_tile(int shortest, int rlen)
+{
+    return rlen <= shortest || REPL_STRIDE + ((REPL_STRIDE + shortest - 1) / shortest) * (rlen - shortest) + shortest <= REPL_TILE;
+}
+
+// NVStrings::replace, literal target, every occurrence (replace_bits.cuh MODE 0).  false = not expressible there (bordered or
+// long target, replacement that could overflow the staging tile, unaligned view, very short rows): the caller takes the per-row path.
+bool replace_literal_flat(const custr_column* col, const char* pat, int m, const char* repl, int rlen, BufPtr& out_chars, BufPtr& out_off,
+                          int64_t& nbytes)
+{
+    if (((uintptr_t)col->chars & 15) != 0 || col->nbytes == 0 || col->n == 0) return false;
+    if (m < 1 || m > REPL_PAT_MAX || rlen > REPL_REPL_MAX) return false;
+    if (col->nbytes < STREAM_MIN_ROW_BYTES * (int64_t)col->n) return false;
+    for (int b = 1; b < m; ++b)  // a border: occurrences could overlap and the leftmost scan would skip some
+        if (memcmp(pat, pat + (m - b), (size_t)b) == 0) return false;
+    if (!splice_fits_tile(m, rlen)) return false;
+    ReplArgs a{};
+    a.m = m;
+    a.rlen = rlen;
+    memcpy(a.pat, pat, (size_t)m);
+    memcpy(a.repl, repl, (size_t)rlen);
+    return splice_run(col, a, 0, out_chars, out_off, nbytes);
+}
+
+// replace_re, every match, for single-class chains (replace_bits.cuh MODE 1) from the span streams a run() over the same column
+// left in `ss`.  false = not this family / not expressible: the caller walks the streams per row (span_walk.cuh).
+bool replace_spans_ok(const ChainDev& cd)
+{
+    if (cd.nsteps < 1 || cd.nsteps > CHAIN_MAX_STEPS) return false;
+    for (uint32_t s = 0; s < cd.nsteps; ++s) {
+        const ChainStepD& st = cd.steps[s];
+        if (st.cls != cd.steps[cd.nsteps - 1].cls || st.opt || (s > 0 && st.before)) return false;
+        if ((st.loop != 0) != (s + 1 == cd.nsteps) || (st.exit != 0) != (s + 1 == cd.nsteps)) return false;
+    }
+    return true;
+}
+bool replace_spans_flat(const custr_column* col, const ChainDev& cd, const SpanStreams& ss, const char* repl, int rlen, BufPtr& out_chars,
+                        BufPtr& out_off, int64_t& nbytes)
+{
+    if (!replace_spans_ok(cd) || !ss.m || ss.words <= 0) return false;
+    if (((uintptr_t)col->chars & 15) != 0 || col->nbytes == 0 || col->n == 0 || rlen > REPL_REPL_MAX) return false;
+    if (col->nbytes < STREAM_MIN_ROW_BYTES * (int64_t)col->n) return false;
+    if (!splice_fits_tile((int)cd.nsteps, rlen)) return false;
+    ReplArgs a{};
+    a.m = (int)cd.nsteps;
+    a.rlen = rlen;
+    memcpy(a.repl, repl, (size_t)rlen);
+    a.span_m = ss.m;
+    a.span_k = ss.k;
+    a.span_a = ss.a;
+    a.span_words = ss.words;
+    a.span_base = ss.base;
+    a.k_chars = (int)cd.nsteps - 1;
+    return splice_run(col, a, 1, out_chars, out_off, nbytes);
 }
 
 }  // namespace bits

@@ -29,6 +29,7 @@ struct SpanStreams {
     const unsigned long long* k = nullptr;
     const unsigned long long* a = nullptr;
     int32_t base = 0;   // byte offset (into chars) of bit 0
+    long long words = 0;  // 64-bit words per stream
     BufPtr keep;
     // count mode: when set (and count_in_kernel_ok(plan)) the kernel writes the number of matches of every row here and
     // leaves no streams; `out` of run() is then unused
@@ -49,6 +50,11 @@ bool split_record_flat(const custr_column* col, uint8_t delim, BufPtr& out_chars
 // replace with a literal target, every occurrence (replace_bits.cuh); false = not expressible, take the per-row path
 bool replace_literal_flat(const custr_column* col, const char* pat, int m, const char* repl, int rlen, BufPtr& out_chars, BufPtr& out_off,
                           int64_t& nbytes);
+struct ChainDev;
+// replace_re, every match, for single-class chains (x{n,} / x+ with assertions) from the span streams (replace_bits.cuh MODE 1)
+bool replace_spans_ok(const ChainDev& cd);
+bool replace_spans_flat(const custr_column* col, const ChainDev& cd, const SpanStreams& ss, const char* repl, int rlen, BufPtr& out_chars,
+                        BufPtr& out_off, int64_t& nbytes);
 extern thread_local bool g_force_generic;
 extern thread_local bool g_no_spec;
 extern thread_local bool g_chain_win;

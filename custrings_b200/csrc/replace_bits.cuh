@@ -14,6 +14,18 @@
 // occurrence that starts in an owned byte always has its m <= 32 bytes (and the row starts among them) inside the window.
 // What flows forward between windows is the number of leading bytes still covered by the last occurrence of the previous one.
 // Two passes like split: output bytes per (item, window) slot -> exclusive scan -> write.
+//
+// MODE 1 — replace_re for single-class chains (x{n,} / x+ with any leading and trailing assertions, e.g. \b\w{4,}\b, \d+, \s+):
+// the same splice fed by the chain kernel's span streams (regex_bits.h SpanStreams: M = a match can begin its LAST step here,
+// K = the match may continue into this byte, A = a match may end behind this byte) instead of a literal compare.  Every step has
+// the class of the loop, so the k characters in front of an M bit lie in the same maximal K-run as the bit itself and a run
+// holds at most one match (span_walk.cuh's rule "first M at or after the cursor, then the last A of the run" never finds a
+// second one: behind that A the run has no A left).  In stream terms:
+//     S   = M spread through K                      (forward carry between windows)
+//     FM  = M & ~(S advanced & K)                   first M of every run
+//     R   = A spread BACKWARDS through K            "an A follows inside the run" (carry from behind the window: a short scan
+//                                                   of the K / A words that follow, the streams are in device memory)
+//     occurrence starts = FM & R;  DROP = (S & R) | the k characters in front of every FM & R bit
 #pragma once
 
 constexpr int REPL_STRIDE = WIN64 - 64;
@@ -29,11 +41,18 @@ struct ReplArgs {
     const int32_t* item_slot;
     unsigned long long* slot_counts;      // count pass: output bytes per slot
     const unsigned long long* slot_base;  // write pass: exclusive scan of slot_counts
-    int32_t m, rlen;
+    int32_t m, rlen;                      // MODE 0: target length; MODE 1: shortest match in bytes (tile bound only)
     uint8_t pat[REPL_PAT_MAX];
     uint8_t repl[REPL_REPL_MAX];
     int32_t* new_off;                     // write pass outputs
     char* out;
+    // MODE 1: span streams of the chain kernel, one bit per byte from byte span_base (a multiple of 2048) on
+    const unsigned long long* span_m;
+    const unsigned long long* span_k;
+    const unsigned long long* span_a;
+    long long span_words;
+    int32_t span_base, k_chars;
+    unsigned int* flags;                  // bit 0: a K-run longer than the look-ahead bound (caller falls back)
 };
 
 struct __align__(64) WarpSmRepl {
@@ -46,7 +65,8 @@ struct __align__(64) WarpSmRepl {
 };
 
 // number of windows every work item touches (0 for an item without bytes)
-__global__ void k_repl_item_windows(const int32_t* __restrict__ offsets, const int32_t* __restrict__ item_bounds, int nitems, int32_t* __restrict__ out)
+__global__ void k_repl_item_windows(const int32_t* __restrict__ offsets, const int32_t* __restrict__ item_bounds, int nitems, int align_mask,
+                                    int32_t* __restrict__ out)
 {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= nitems) return;
@@ -54,7 +74,7 @@ __global__ void k_repl_item_windows(const int32_t* __restrict__ offsets, const i
     int w = 0;
     if (ra < rb) {
         const int a = offsets[ra], b = offsets[rb];
-        if (a < b) w = (b - (a & ~15) + REPL_STRIDE - 1) / REPL_STRIDE;
+        if (a < b) w = (b - (a & align_mask) + REPL_STRIDE - 1) / REPL_STRIDE;
     }
     out[item] = w;
 }
@@ -67,16 +87,33 @@ __device__ __forceinline__ u64 eq_byte64(const u64 (&p)[8], uint32_t c)
     return t;
 }
 
-template <bool WRITE>
+__device__ __forceinline__ u64 mirror64(u64 x)  // position p of the window -> 2047 - p
+{
+    return mk64(__shfl_xor_sync(FULL, __brev(hi32(x)), 31), __shfl_xor_sync(FULL, __brev(lo32(x)), 31));
+}
+// R[p] = A[p] | (R[p+1] & K[p+1]) over the window; `carry_in` = R[2048] & K[2048]
+__device__ __forceinline__ u64 rspread64(u64 a, u64 k, bool carry_in, const LaneCtx& L)
+{
+    const uint32_t cw = carry_in ? 0x80000000u : 0u;
+    // mirrored coordinates q = 2047 - p: R'[q] = A'[q] | (R'[q-1] & K'[q-1]), and spread64 wants the K of position q itself
+    return mirror64(spread64(mirror64(a), adv64(mirror64(k), cw, L), cw, L));
+}
+
+template <int MODE, bool WRITE>
 __global__ void __launch_bounds__(THREADS, 3)
-k_replace_lit64(const __grid_constant__ ReplArgs A)
+k_replace_splice64(const __grid_constant__ ReplArgs A)
 {
     extern __shared__ __align__(64) unsigned char repl_dsm[];
     WarpSmRepl* sm = (WarpSmRepl*)repl_dsm;
     __shared__ uint8_t s_repl[REPL_REPL_MAX];
     if (threadIdx.x < REPL_REPL_MAX) s_repl[threadIdx.x] = A.repl[threadIdx.x];
     __syncthreads();
-    const uint32_t lane = lane_id();
+    LaneCtx L;
+    L.lane = lane_id();
+    L.src = (L.lane + 31) & 31;
+    L.is31 = L.lane == 31;
+    L.m31 = L.lane == 31 ? 1u : 0u;
+    const uint32_t lane = L.lane;
     WarpSmRepl& W = sm[threadIdx.x >> 5];
     const uint32_t wb = (uint32_t)__cvta_generic_to_shared(&W);
     const uint32_t my0 = wb + ring_lane_offset(lane);
@@ -106,7 +143,8 @@ k_replace_lit64(const __grid_constant__ ReplArgs A)
                 for (int j = ra + (int)lane; j < rb; j += 32) A.new_off[j] = (int32_t)__ldg(A.slot_base + slot0);
             continue;
         }
-        int ws = byte_a & ~15;
+        int ws = byte_a & (MODE == 1 ? ~63 : ~15);
+        uint32_t carry_sp = 0;  // MODE 1: top word of S at the end of the previous window's owned bytes
         int kown = ra;  // next row whose new offset has not been written (rows ra .. rb-1 start in [byte_a, byte_b])
         int carry = 0;  // leading bytes of the window still covered by the last occurrence of the previous one
         int stage = 0;
@@ -128,7 +166,7 @@ k_replace_lit64(const __grid_constant__ ReplArgs A)
                 const int j = j0 + (int)lane;
                 const int o = j < A.n ? __ldg(A.offsets + j) : 0x7fffffff;
                 const bool inw = o < ws + WIN64;
-                if (inw) reds_or(rs_base + 4u * (uint32_t)((o - ws) >> 5), 1u << ((o - ws) & 31));
+                if (MODE == 0 && inw) reds_or(rs_base + 4u * (uint32_t)((o - ws) >> 5), 1u << ((o - ws) & 31));
                 kown += __popc(__ballot_sync(FULL, j < rb && (o < we || !more)));
                 if (__ballot_sync(FULL, inw) != FULL) break;
             }
@@ -147,14 +185,6 @@ k_replace_lit64(const __grid_constant__ ReplArgs A)
 #pragma unroll
                 for (int b = 0; b < 8; ++b) p[b] = mk64(pl[b], ph[b]);
             }
-            u64 X = eq_byte64(p, A.pat[m - 1]);
-#pragma unroll 1
-            for (int k = m - 2; k >= 0; --k) {
-                const u64 y = X & nrs;  // the byte behind must belong to the same row
-                const uint32_t dn = __shfl_down_sync(FULL, lo32(y), 1);
-                const uint32_t hi = __funnelshift_r(hi32(y), lane == 31 ? 0u : dn, 1), lo = __funnelshift_r(lo32(y), hi32(y), 1);
-                X = mk64(lo, hi) & eq_byte64(p, A.pat[k]);
-            }
             const int wp = ws + 64 * (int)lane;
             const int own_lo = byte_a > ws ? byte_a : ws, own_hi = byte_b < we ? byte_b : we;
             u64 own = 0;
@@ -163,22 +193,79 @@ k_replace_lit64(const __grid_constant__ ReplArgs A)
                 if (wp < own_lo) own &= ~0ull << (own_lo - wp);
                 if (wp + 64 > own_hi) own &= ~0ull >> (wp + 64 - own_hi);
             }
-            const u64 M = X & own;
-            // ---- DROP: M smeared upwards over m bytes (doubling), plus the tail of the previous window's last occurrence
-            u64 D = M;
-            for (int cover = 1; cover < m;) {
-                const int sh = cover < m - cover ? cover : m - cover;  // <= 16
-                const uint32_t up = __shfl_up_sync(FULL, hi32(D), 1);
-                const uint32_t lo = __funnelshift_l(lane == 0 ? 0u : up, lo32(D), sh), hi = __funnelshift_l(lo32(D), hi32(D), sh);
-                D |= mk64(lo, hi);
-                cover += sh;
-            }
-            if (lane == 0 && carry) D |= (1ull << carry) - 1ull;
-            {
-                const int top = M ? 64 * (int)lane + 63 - __clzll((long long)M) : -1;
-                const int mx = __reduce_max_sync(FULL, top);
-                carry = mx + m - REPL_STRIDE;
-                if (carry < 0) carry = 0;
+            u64 M, D;
+            if (MODE == 0) {
+                u64 X = eq_byte64(p, A.pat[m - 1]);
+#pragma unroll 1
+                for (int k = m - 2; k >= 0; --k) {
+                    const u64 y = X & nrs;  // the byte behind must belong to the same row
+                    const uint32_t dn = __shfl_down_sync(FULL, lo32(y), 1);
+                    const uint32_t hi = __funnelshift_r(hi32(y), lane == 31 ? 0u : dn, 1), lo = __funnelshift_r(lo32(y), hi32(y), 1);
+                    X = mk64(lo, hi) & eq_byte64(p, A.pat[k]);
+                }
+                M = X & own;
+                // ---- DROP: M smeared upwards over m bytes (doubling), plus the tail of the previous window's last occurrence
+                D = M;
+                for (int cover = 1; cover < m;) {
+                    const int sh = cover < m - cover ? cover : m - cover;  // <= 16
+                    const uint32_t up = __shfl_up_sync(FULL, hi32(D), 1);
+                    const uint32_t lo = __funnelshift_l(lane == 0 ? 0u : up, lo32(D), sh), hi = __funnelshift_l(lo32(D), hi32(D), sh);
+                    D |= mk64(lo, hi);
+                    cover += sh;
+                }
+                if (lane == 0 && carry) D |= (1ull << carry) - 1ull;
+                {
+                    const int top = M ? 64 * (int)lane + 63 - __clzll((long long)M) : -1;
+                    const int mx = __reduce_max_sync(FULL, top);
+                    carry = mx + m - REPL_STRIDE;
+                    if (carry < 0) carry = 0;
+                }
+            } else {
+                const long long wi = ((long long)ws + 64 * (int)lane - A.span_base) >> 6;
+                u64 Mw = 0, Kw = 0, Aw = 0;
+                if (wi < A.span_words) {
+                    Mw = __ldg(A.span_m + wi);
+                    Kw = __ldg(A.span_k + wi);
+                    Aw = __ldg(A.span_a + wi);
+                }
+                const u64 cont = p[7] & ~p[6];
+                // does the K-run that continues behind the window hold an A?  (warp-uniform scan, nearly always one word)
+                bool rc = false;
+                {
+                    long long w = ((long long)ws + WIN64 - A.span_base) >> 6;
+                    for (int it = 0; w < A.span_words; ++it, ++w) {
+                        const u64 kw = __ldg(A.span_k + w), aw = __ldg(A.span_a + w);
+                        const u64 nk = ~kw;
+                        const u64 run = nk ? ((nk & (0ull - nk)) - 1ull) : ~0ull;  // the bits of the run inside this word
+                        if (aw & run) { rc = true; break; }
+                        if (nk) break;
+                        if (it == 64) {  // a run of more than 4 KiB behind the window: not worth a serial scan per window
+                            if (lane == 0) atomicOr(A.flags, 1u);
+                            break;
+                        }
+                    }
+                }
+                const u64 S = spread64(Mw, Kw, carry_sp, L);
+                const u64 FM = Mw & ~(adv64(S, carry_sp, L) & Kw);
+                const u64 R = rspread64(Aw, Kw, rc, L);
+                const u64 FMv = FM & R;
+                carry_sp = __shfl_sync(FULL, hi32(S), 30);  // the next window starts behind lane 30
+                // the k characters in front of every occurrence's last step (lane 31 is the look-ahead for lane 30)
+                u64 X = FMv, acc = 0;
+#pragma unroll 1
+                for (int c = 0; c < A.k_chars; ++c) {
+                    X = shift_down64(X, 0u, L);
+                    acc |= X;
+#pragma unroll 1
+                    for (int r = 0; r < 3; ++r) {  // markers that landed on a continuation byte travel on to the lead byte
+                        const u64 T = X & cont;
+                        if (!__any_sync(FULL, T != 0)) break;
+                        X = (X & ~cont) | shift_down64(T, 0u, L);
+                        acc |= X;
+                    }
+                }
+                M = FMv & own;
+                D = acc | (S & R);
             }
             const u64 K = own & ~D;
             const uint32_t cnt = (uint32_t)__popcll(K) + (uint32_t)rlen * (uint32_t)__popcll(M);

@@ -221,3 +221,51 @@ def test_literal_replace_bitstream_equals_per_row_path(c2, oracle):
     for tgt, repl in (("aa", "b"), ("abab", "-")):  # bordered targets: per-row path
         got = dev.replace(tgt, repl, regex=False)
         assert got.to_host() == [None if x is None else x.decode() for x in ref.replace(tgt, repl).to_list()], (tgt, repl)
+
+
+def test_replace_re_bitsplice_equals_walk_and_vm(c2, oracle):
+    """replace_re of single-class chains (x{n,} / x+ with assertions) through the streaming splice over the chain kernel's span
+    streams (replace_bits.cuh MODE 1) against the per-row walk of the same streams (tier 3), the exact Pike VM (tier 1) and
+    the oracle: C2 rows, then rows built to put runs across lane / window / row boundaries, '_' inside \\w runs (a \\b that
+    holds in the middle of a run), multi-byte characters in front of and inside matches, empty and null rows."""
+    from custrings_b200 import nvstrings
+    from custrings_b200._lib import lib
+    from custrings_b200.workloads import slice_rows
+    n, chars, offsets, validity, nulls, col = c2
+
+    def tiers(column, pat, repl, which=(0, 3)):
+        res = []
+        for t in which:
+            lib().custr_set_regex_tier(t)
+            try:
+                res.append(column.replace(pat, repl))
+            finally:
+                lib().custr_set_regex_tier(0)
+        for r in res[1:]:
+            for a, b in zip(res[0].to_arrays(), r.to_arrays()):
+                assert np.array_equal(a, b), (pat, repl)
+        return res[0]
+
+    sub = col[0:1_000_000]
+    for pat, repl in ((r"\b\w{4,}\b", "#"), (r"\d+", ""), (r"\s+", " "), (r"[a-m]{2,}", "<>"), (r"\w+\b", "word!")):
+        tiers(sub, pat, repl)
+    m = 30_000
+    c, o, v, nn = slice_rows(chars, offsets, validity, 0, m)
+    want = oracle.RefStrings.from_arrays(c, o, v, nn).replace_re(r"\b\w{4,}\b", "#")
+    got = nvstrings.from_offsets(c, o, m, v, nn).replace(r"\b\w{4,}\b", "#")
+    assert got.to_host() == [None if x is None else x.decode() for x in want.to_list()]
+
+    rng = np.random.default_rng(12)
+    rows = []
+    for k in range(2500):
+        ln = int(rng.choice([0, 1, 2, 3, 4, 5, 30, 63, 64, 65, 127, 1983, 1984, 1985, 2047, 2048, 2049, 4000]))
+        rows.append(None if k % 89 == 7 else "".join(rng.choice(list("abc1_é日 ,"), ln).tolist()))
+    rows.append("word " * 30_000)
+    rows.append("w" * 70_000 + " tail")              # one run over many windows
+    rows.append("abcd_" * 20_000)                    # \b inside every run
+    rows += ["abcd", "", "abc", "_abcd_", None, "éabcd", "abcdé x", "日本語日本語"] * 40
+    dev = nvstrings.to_device(rows)
+    ref = oracle.RefStrings.from_list(rows)
+    for pat, repl in ((r"\b\w{4,}\b", "#"), (r"\w{3,}", ""), (r"[a-c]+", "ABC"), (r"\b[a-c1]{2,}", "_"), (r"\w+\b", "é"), (r"\s+", "")):
+        got = tiers(dev, pat, repl, which=(0, 3, 1))
+        assert got.to_host() == [None if x is None else x.decode() for x in ref.replace_re(pat, repl).to_list()], (pat, repl)
