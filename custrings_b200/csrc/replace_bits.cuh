@@ -288,23 +288,51 @@ k_replace_splice64(const __grid_constant__ ReplArgs A)
             asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(kk_base + 8u * lane), "r"(lo32(K)), "r"(hi32(K)) : "memory");
             asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(mm_base + 8u * lane), "r"(lo32(M)), "r"(hi32(M)) : "memory");
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(pre_base + 4u * lane), "r"(pre) : "memory");
-            // my kept bytes and replacements -> tile, in position order
+            // my kept bytes -> tile, in position order (straight line; an occurrence start only moves the cursor on by rlen: a
+            // window without any occurrence, warp-uniform, runs the copy of the loop that does not test for them), then the
+            // replacements: one short loop over my M bits
             {
                 const uint32_t tile = wb + (uint32_t)offsetof(WarpSmRepl, tile);
-                uint32_t o = phase + pre;
+                const uint32_t o0 = phase + pre;
                 const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+                uint32_t o = o0;
+                if (__any_sync(FULL, M != 0)) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t km = (uint32_t)(K >> (4 * i)) & 15u, mm4 = (uint32_t)(M >> (4 * i)) & 15u;
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t km = (uint32_t)(K >> (4 * i)) & 15u, mm4 = (uint32_t)(M >> (4 * i)) & 15u;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (mm4 & (1u << k)) {
-                            for (int q = 0; q < rlen; ++q) asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile + tile_pad(o + (uint32_t)q)), "r"(lds8(repl_base + (uint32_t)q)) : "memory");
-                            o += (uint32_t)rlen;
+                        for (int k = 0; k < 4; ++k) {
+                            if (mm4 & (1u << k)) o += (uint32_t)rlen;
+                            if (km & (1u << k)) {
+                                asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile + tile_pad(o)), "r"(w[i] >> (8 * k)) : "memory");
+                                ++o;
+                            }
                         }
-                        if (km & (1u << k)) {
-                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile + tile_pad(o)), "r"(w[i] >> (8 * k)) : "memory");
-                            ++o;
+                    }
+                    if (rlen > 0) {
+                        int nm = 0;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t m32 = h ? hi32(M) : lo32(M), k32 = h ? hi32(K) : lo32(K);
+                            const uint32_t ob = o0 + (h ? (uint32_t)__popc(lo32(K)) : 0u);
+                            for (uint32_t e = m32; e; e &= e - 1, ++nm) {
+                                const int b = __ffs((int)e) - 1;
+                                const uint32_t at = ob + (uint32_t)__popc(k32 & ((1u << b) - 1u)) + (uint32_t)(nm * rlen);
+                                for (int q = 0; q < rlen; ++q)
+                                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile + tile_pad(at + (uint32_t)q)), "r"(lds8(repl_base + (uint32_t)q)) : "memory");
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t km = (uint32_t)(K >> (4 * i)) & 15u;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (km & (1u << k)) {
+                                asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile + tile_pad(o)), "r"(w[i] >> (8 * k)) : "memory");
+                                ++o;
+                            }
                         }
                     }
                 }
