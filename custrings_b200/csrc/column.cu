@@ -5,6 +5,9 @@
 // The reference rebuilds a pointer-per-string object heap on import (3 passes + memmove per row); here the
 // Arrow triple IS the storage, so import is two memcpys and export is one.
 #include "common.cuh"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "device_utils.cuh"
 #include <cub/cub.cuh>
 #include <thrust/sort.h>
@@ -44,6 +47,16 @@ DeviceBuf::~DeviceBuf()
     if (ptr) cudaFreeAsync(ptr, g_stream);
 }
 
+void trace_point(const char* what)
+{
+    static const bool on = getenv("CUSTR_TRACE") != nullptr;
+    if (!on) return;
+    static thread_local std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    cudaStreamSynchronize(g_stream);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[custr trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+}
 int num_sms()
 {
     static std::atomic<int> sms[64];  // per device (custr_set_device may switch devices inside one process)

@@ -63,6 +63,8 @@ struct Scratch {  // typed RAII scratch
 };
 
 int num_sms();
+// CUSTR_TRACE=1: synchronise the stream and print the host time since the previous trace point (development aid)
+void trace_point(const char* what);
 
 }  // namespace custr
 

@@ -1265,7 +1265,9 @@ custr_column* custr_replace_re(const custr_column* col, const char* pattern, con
             int h_nul = 0;
             if (cd) {  // last-loop chain, bit streams + word scans
                 SpanRun sr;
+                trace_point("replace_re: entry");
                 if (run_span_streams(*c, col, sr)) {
+                    trace_point("replace_re: chain + spans");
                     const int k_chars = (int)cd->nsteps - 1;
                     if (maxrepl < 0 && !bits::g_chain_win && bits::replace_spans_ok(*cd) && read_dirty(sr) == 0) {
                         // single-class chain, every match: streaming splice over the span streams, no per-row walk
@@ -1273,6 +1275,7 @@ custr_column* custr_replace_re(const custr_column* col, const char* pattern, con
                         int64_t total2 = 0;
                         if (bits::replace_spans_flat(col, *cd, sr.ss, repl, repl_len, chars2, off2, total2)) {
                             g_last_tier = "bitsplice";
+                            trace_point("replace_re: splice");
                             return make_column(chars2, off2, copy_validity(col), n, col->nulls, total2);
                         }
                     }

@@ -571,7 +571,9 @@ static bool splice_run(const custr_column* col, ReplArgs& a, int mode, BufPtr& o
     const int resident = num_sms() * 3;
     if (blocks > resident) blocks = resident;
     a.item_counter = (unsigned int*)counter->ptr;
+    trace_point("splice: set-up");
     LAUNCH(kc, blocks, THREADS, smem, a);
+    trace_point("splice: count pass");
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, a.slot_counts, (unsigned long long*)base->ptr, (int)nslots, g_stream);
     BufPtr tmp = dev_alloc(tmp_bytes);
@@ -592,8 +594,10 @@ static bool splice_run(const custr_column* col, ReplArgs& a, int mode, BufPtr& o
     a.new_off = (int32_t*)out_off->ptr;
     a.out = (char*)out_chars->ptr;
     a.item_counter = (unsigned int*)counter->ptr + 1;
+    trace_point("splice: scan + allocs");
     LAUNCH(kw, blocks, THREADS, smem, a);
     CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+    trace_point("splice: write pass");
     return true;
 }
 // every occurrence adds rlen bytes and removes at least `shortest`: the most a 1984-byte window can emit must fit the tile
