@@ -5,6 +5,9 @@
 // The reference rebuilds a pointer-per-string object heap on import (3 passes + memmove per row); here the
 // Arrow triple IS the storage, so import is two memcpys and export is one.
 #include "common.cuh"
+#include <vector>
+#include <string>
+#include <cstring>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -47,15 +50,41 @@ DeviceBuf::~DeviceBuf()
     if (ptr) cudaFreeAsync(ptr, g_stream);
 }
 
+// CUSTR_TRACE=1: synchronise at every point and print host time deltas.  CUSTR_TRACE=2: record a CUDA event at every point (no
+// synchronisation, the call runs as it does untraced) and print the device time between consecutive points when a point
+// whose name ends in '.' is reached.
 void trace_point(const char* what)
 {
-    static const bool on = getenv("CUSTR_TRACE") != nullptr;
-    if (!on) return;
-    static thread_local std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
-    cudaStreamSynchronize(g_stream);
-    const auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "[custr trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
-    last = now;
+    static const int mode = getenv("CUSTR_TRACE") ? atoi(getenv("CUSTR_TRACE")) : 0;
+    if (!mode) return;
+    if (mode == 1) {
+        static thread_local std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+        cudaStreamSynchronize(g_stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[custr trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+        last = now;
+        return;
+    }
+    static thread_local std::vector<std::pair<std::string, cudaEvent_t>> evs;
+    static thread_local std::chrono::steady_clock::time_point h0;
+    if (evs.empty()) h0 = std::chrono::steady_clock::now();
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, g_stream);
+    evs.emplace_back(what, e);
+    const size_t len = strlen(what);
+    if (len && what[len - 1] == '.') {
+        cudaEventSynchronize(e);
+        const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+        for (size_t i = 1; i < evs.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, evs[i - 1].second, evs[i].second);
+            fprintf(stderr, "[custr trace/dev] %-28s %8.3f ms\n", evs[i].first.c_str(), ms);
+        }
+        fprintf(stderr, "[custr trace/dev] host wall first..last point %8.3f ms\n", host_ms);
+        for (auto& p : evs) cudaEventDestroy(p.second);
+        evs.clear();
+    }
 }
 int num_sms()
 {

@@ -24,7 +24,7 @@ enum FindMode { FM_FIND = 0, FM_RFIND = 1, FM_CONTAINS = 2, FM_STARTS = 3, FM_EN
 
 __global__ void __launch_bounds__(FIND_THREADS)
 k_find(ColView col, const uint8_t* __restrict__ needle, int m, int start, int end, int mode, int32_t* __restrict__ out_i,
-       uint8_t* __restrict__ out_b, unsigned long long* __restrict__ total)
+       uint8_t* __restrict__ out_b, unsigned long long* __restrict__ total, const uint8_t* __restrict__ hits = nullptr)
 {
     __shared__ uint8_t sm[NEEDLE_SMEM];
     const uint8_t* t = stage_needle(needle, m, sm);
@@ -36,7 +36,8 @@ k_find(ColView col, const uint8_t* __restrict__ needle, int m, int start, int en
             const uint8_t* s = (const uint8_t*)col.chars + col.offsets[i];
             int n = col.offsets[i + 1] - col.offsets[i];
             if (mode <= FM_RFIND) {
-                int r = ok ? row::find_chars(s, n, t, m, start, end, mode == FM_RFIND) : -2;
+                // `hits` (find / rfind on a large column): rows the chain kernel found the needle nowhere in need no scan
+                int r = !ok ? -2 : (hits && !hits[i]) ? -1 : row::find_chars(s, n, t, m, start, end, mode == FM_RFIND);
                 out_i[i] = r;
                 counted = r != -1;
             } else {
@@ -156,8 +157,24 @@ static int find_family(const custr_column* col, const char* str, int start, int 
     unsigned long long cnt;
     if (out_i) {
         ResultBuf<int32_t> out(out_i, n, devmem);
+        // large column: one coalesced pass of the chain kernel decides which rows hold the needle at all (most do not, and a
+        // row without it is -1 for any start / end); only those rows are scanned for the character position
+        BufPtr hits;
+        if (m > 0 && col->nbytes >= (1 << 20)) {
+            hits = dev_alloc((size_t)n);
+            Scratch<unsigned long long> nhit(1);
+            CUSTR_CUDA(cudaMemsetAsync(nhit.get(), 0, 8, g_stream));
+            int32_t* dirty_rows = nullptr;
+            unsigned int* dirty_count = nullptr;
+            BufPtr keep_rows, keep_count;
+            if (literal_contains_chain(col, str, (uint8_t*)hits->ptr, nhit.get(), &dirty_rows, &dirty_count, keep_rows, keep_count))
+                LAUNCH(k_contains_rows, 64, FIND_THREADS, 0, view_of(col), (const uint8_t*)d_needle->ptr, m, (const int32_t*)dirty_rows,
+                       (const unsigned int*)dirty_count, (uint8_t*)hits->ptr, nhit.get());
+            else
+                hits = nullptr;
+        }
         LAUNCH(k_find, row_grid(n, FIND_THREADS), FIND_THREADS, 0, view_of(col), (const uint8_t*)d_needle->ptr, m, start, end, mode,
-               out.dev, (uint8_t*)nullptr, total.get());
+               out.dev, (uint8_t*)nullptr, total.get(), hits ? (const uint8_t*)hits->ptr : (const uint8_t*)nullptr);
         cnt = fetch(total.get());
         out.finish();
     } else {

@@ -1275,7 +1275,7 @@ custr_column* custr_replace_re(const custr_column* col, const char* pattern, con
                         int64_t total2 = 0;
                         if (bits::replace_spans_flat(col, *cd, sr.ss, repl, repl_len, chars2, off2, total2)) {
                             g_last_tier = "bitsplice";
-                            trace_point("replace_re: splice");
+                            trace_point("replace_re: splice done.");
                             return make_column(chars2, off2, copy_validity(col), n, col->nulls, total2);
                         }
                     }

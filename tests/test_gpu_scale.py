@@ -269,3 +269,26 @@ def test_replace_re_bitsplice_equals_walk_and_vm(c2, oracle):
     for pat, repl in ((r"\b\w{4,}\b", "#"), (r"\w{3,}", ""), (r"[a-c]+", "ABC"), (r"\b[a-c1]{2,}", "_"), (r"\w+\b", "é"), (r"\s+", "")):
         got = tiers(dev, pat, repl, which=(0, 3, 1))
         assert got.to_host() == [None if x is None else x.decode() for x in ref.replace_re(pat, repl).to_list()], (pat, repl)
+
+
+def test_find_with_contains_prefilter_equals_plain_scan(c2, oracle):
+    """find / rfind on a large column first ask the chain kernel which rows hold the needle at all; the positions must equal the
+    plain per-row scan (tier 2 switches the pre-filter off) for any start / end, and the oracle's on a prefix."""
+    from custrings_b200._lib import lib
+    n, chars, offsets, validity, nulls, col = c2
+    sub = col[0:2_000_000]
+    for needle, start, end in (("abcd", 0, None), ("the", 0, None), ("e", 3, 40), ("é", 0, None), (" a", 2, None), ("zzzzq", 0, None)):
+        for right in (False, True):
+            fn = sub.rfind if right else sub.find
+            got = fn(needle, start, end)
+            lib().custr_set_regex_tier(2)
+            try:
+                ref = fn(needle, start, end)
+            finally:
+                lib().custr_set_regex_tier(0)
+            assert got == ref, (needle, start, end, right)
+    m = 50_000
+    from custrings_b200.workloads import slice_rows
+    want = oracle.RefStrings.from_arrays(*slice_rows(chars, offsets, validity, 0, m)).find("the")[0]
+    got = col[0:m].find("the")
+    assert [g for g in got if g is not None] == [int(x) for x, g in zip(want, got) if g is not None]
