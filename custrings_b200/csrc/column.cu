@@ -24,7 +24,25 @@ thread_local std::string g_error;
 thread_local cudaStream_t g_stream = 0;
 std::atomic<long long> g_launches{0};
 
-DeviceBuf::DeviceBuf(size_t n) : bytes(n)
+// Big-block cache in front of the driver's pool.  The pool keeps freed memory (release threshold = max), but it hands a freed
+// 1 GB block to the next 400 MB request and then has to stitch the 1 GB request that follows together from fragments — a
+// remap that idles the stream for 2-4 ms (CUSTR_TRACE=2 showed replace_re 2.2 ms in a fresh process and 4.4-4.9 ms after other
+// calls had populated the pool, all of it inside cudaMallocAsync).  Calls on the same column ask for the same sizes again and
+// again (result chars, span streams, offsets), so blocks >= 32 MiB are kept here per (device, stream) and reused for requests of
+// the same size or up to 1/8 smaller; at most 8 blocks / 6 GiB, oldest evicted to the pool.
+namespace {
+struct BigBlock { void* ptr; size_t cap; int dev; cudaStream_t stream; };
+struct BigCache {
+    std::vector<BigBlock> blocks;  // oldest first
+    size_t total = 0;
+    ~BigCache() { for (auto& b : blocks) cudaFreeAsync(b.ptr, b.stream); }
+};
+thread_local BigCache g_big;
+constexpr size_t BIG_MIN = 32ull << 20, BIG_TOTAL = 6ull << 30;
+constexpr size_t BIG_COUNT = 8;
+}  // namespace
+
+DeviceBuf::DeviceBuf(size_t n) : bytes(n), cap(n)
 {
     static std::atomic<unsigned long long> pools_ready{0};  // one bit per device ordinal
     int dev = 0;
@@ -38,7 +56,28 @@ DeviceBuf::DeviceBuf(size_t n) : bytes(n)
         }
         pools_ready.fetch_or(bit, std::memory_order_relaxed);
     }
+    if (n >= BIG_MIN) {
+        int best = -1;
+        for (int i = 0; i < (int)g_big.blocks.size(); ++i) {
+            const BigBlock& b = g_big.blocks[i];
+            if (b.dev == dev && b.stream == g_stream && b.cap >= n && b.cap - n <= n / 8 && (best < 0 || b.cap < g_big.blocks[best].cap)) best = i;
+        }
+        if (best >= 0) {
+            ptr = g_big.blocks[best].ptr;
+            cap = g_big.blocks[best].cap;
+            g_big.total -= cap;
+            g_big.blocks.erase(g_big.blocks.begin() + best);
+            return;
+        }
+    }
     cudaError_t e = cudaMallocAsync(&ptr, n, g_stream);
+    if (e != cudaSuccess && !g_big.blocks.empty()) {  // give the cached blocks back and retry
+        for (auto& b : g_big.blocks) cudaFreeAsync(b.ptr, b.stream);
+        g_big.blocks.clear();
+        g_big.total = 0;
+        cudaGetLastError();
+        e = cudaMallocAsync(&ptr, n, g_stream);
+    }
     if (e != cudaSuccess) {
         g_error = std::string("device allocation of ") + std::to_string(n) + " bytes failed: " + cudaGetErrorString(e);
         cudaGetLastError();
@@ -47,7 +86,19 @@ DeviceBuf::DeviceBuf(size_t n) : bytes(n)
 }
 DeviceBuf::~DeviceBuf()
 {
-    if (ptr) cudaFreeAsync(ptr, g_stream);
+    if (!ptr) return;
+    int dev = 0;
+    if (cap >= BIG_MIN && cap <= BIG_TOTAL / 2 && cudaGetDevice(&dev) == cudaSuccess) {
+        g_big.blocks.push_back(BigBlock{ptr, cap, dev, g_stream});
+        g_big.total += cap;
+        while (g_big.blocks.size() > BIG_COUNT || g_big.total > BIG_TOTAL) {
+            cudaFreeAsync(g_big.blocks.front().ptr, g_big.blocks.front().stream);
+            g_big.total -= g_big.blocks.front().cap;
+            g_big.blocks.erase(g_big.blocks.begin());
+        }
+        return;
+    }
+    cudaFreeAsync(ptr, g_stream);
 }
 
 // CUSTR_TRACE=1: synchronise at every point and print host time deltas.  CUSTR_TRACE=2: record a CUDA event at every point (no
@@ -82,6 +133,19 @@ void trace_point(const char* what)
             fprintf(stderr, "[custr trace/dev] %-28s %8.3f ms\n", evs[i].first.c_str(), ms);
         }
         fprintf(stderr, "[custr trace/dev] host wall first..last point %8.3f ms\n", host_ms);
+        {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaMemPool_t pool;
+            uint64_t reserved = 0, used = 0, thr = 0;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+            fprintf(stderr, "[custr trace/dev] pool reserved %.1f MB, used %.1f MB, release threshold %s\n", reserved / 1e6, used / 1e6,
+                    thr == UINT64_MAX ? "max" : std::to_string(thr).c_str());
+        }
         for (auto& p : evs) cudaEventDestroy(p.second);
         evs.clear();
     }

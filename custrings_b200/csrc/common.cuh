@@ -46,7 +46,8 @@ struct ArgError { int code; };
 // Stream-ordered device buffer (cudaMallocAsync from the default pool; pool keeps freed memory cached).
 struct DeviceBuf {
     void* ptr = nullptr;
-    size_t bytes = 0;
+    size_t bytes = 0;   // requested size
+    size_t cap = 0;     // size of the underlying block (>= bytes when it came from the big-block cache)
     explicit DeviceBuf(size_t n);
     ~DeviceBuf();
     DeviceBuf(const DeviceBuf&) = delete;
