@@ -324,17 +324,8 @@ k_replace_splice64(const __grid_constant__ ReplArgs A)
                         }
                     }
                 } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint32_t km = (uint32_t)(K >> (4 * i)) & 15u;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (km & (1u << k)) {
-                                asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile + tile_pad(o)), "r"(w[i] >> (8 * k)) : "memory");
-                                ++o;
-                            }
-                        }
-                    }
+                    tile_zero(tile, phase + total, lane);
+                    scatter_kept(tile, o0, w, K);
                 }
             }
             __syncwarp();

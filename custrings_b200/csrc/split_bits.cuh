@@ -212,19 +212,9 @@ k_split_record64(const __grid_constant__ SplitArgs A)
             // bytes of my word -> tile (as in tokenize)
             {
                 const uint32_t tile = wb + (uint32_t)offsetof(WarpSmSplit, tile);
-                uint32_t o = phase + (pre & 0xffffu);
                 const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t m = (uint32_t)(T >> (4 * i)) & 15u;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (m & (1u << k)) {
-                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile + tile_pad(o)), "r"(w[i] >> (8 * k)) : "memory");
-                            ++o;
-                        }
-                    }
-                }
+                tile_zero(tile, phase + (uint32_t)nbytes, lane);
+                scatter_kept(tile, phase + (pre & 0xffffu), w, T);
             }
             __syncwarp();
             // ---- row_offsets of the rows that start in this window: events before the row's first byte

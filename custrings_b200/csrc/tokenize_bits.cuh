@@ -38,7 +38,7 @@ constexpr int TOK_DELIMS_MAX = 8;
 // profiles/r2_ncu_splice.txt).  tile_pad maps a logical tile offset to its padded one; 16-byte aligned logical chunks stay
 // contiguous (they never straddle a 64-byte block) but are only word aligned.
 __device__ __forceinline__ uint32_t tile_pad(uint32_t o) { return o + ((o >> 6) << 2); }
-constexpr int tile_padded_bytes(int logical) { return logical + (logical / 64 + 1) * 4; }
+constexpr int tile_padded_bytes(int logical) { return (logical + (logical / 64 + 1) * 4 + 15) & ~15; }
 
 struct __align__(64) WarpSmTok {
     char ring[RING_STAGES][WIN64];
@@ -69,6 +69,56 @@ __global__ void k_tok_item_windows(const int32_t* __restrict__ offsets, const in
         if (a < b) w = ((b - 1) / WIN64) - (a / WIN64) + 1;
     }
     out[item] = w;
+}
+
+// Kept bytes (mask K, one bit per byte of my 16 words) -> padded tile from logical offset o0 on, without inserts.
+// CUSTR_SCATTER_BYTES: one predicated st.shared.u8 per input byte (the first version).  Default: every word is compacted with
+// one PRMT (selector from a 16-entry table indexed by its 4 keep bits), appended to a 4-byte shift register, and whole aligned
+// words are OR-ed into the ZEROED tile (red.shared.or.b32) — the partial words at either end of a lane's range combine with
+// the neighbours' by the OR, so no byte stores are needed: ~17 shared-memory operations per lane and window instead of 64.
+__constant__ uint16_t c_compact_sel[16] = {0x4444, 0x4440, 0x4441, 0x4410, 0x4442, 0x4420, 0x4421, 0x4210,
+                                           0x4443, 0x4430, 0x4431, 0x4310, 0x4432, 0x4320, 0x4321, 0x3210};
+__device__ __forceinline__ void tile_zero(uint32_t tile, uint32_t logical_bytes, uint32_t lane)
+{
+#ifndef CUSTR_SCATTER_BYTES
+    const uint32_t end = tile_pad(logical_bytes) + 4u;
+    for (uint32_t q = 16u * lane; q < end; q += 512u) asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(tile + q), "r"(0u) : "memory");
+    __syncwarp();
+#endif
+}
+__device__ __forceinline__ void scatter_kept(uint32_t tile, uint32_t o0, const uint32_t (&w)[16], u64 K)
+{
+#ifdef CUSTR_SCATTER_BYTES
+    uint32_t o = o0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t m = (uint32_t)(K >> (4 * i)) & 15u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (m & (1u << k)) {
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile + tile_pad(o)), "r"(w[i] >> (8 * k)) : "memory");
+                ++o;
+            }
+        }
+    }
+#else
+    uint32_t f = o0 & 3u, a = o0 & ~3u, lo = 0;  // f pending bytes in lo, next aligned logical word at a
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t m = (uint32_t)(K >> (4 * i)) & 15u;
+        const uint32_t c = __byte_perm(w[i], 0u, (uint32_t)c_compact_sel[m]);
+        const uint32_t hi = __funnelshift_l(c, 0u, 8u * f);  // c >> (32 - 8 f)
+        lo |= c << (8u * f);
+        f += (uint32_t)__popc(m);
+        if (f >= 4u) {
+            reds_or(tile + tile_pad(a), lo);
+            lo = hi;
+            a += 4u;
+            f -= 4u;
+        }
+    }
+    if (f) reds_or(tile + tile_pad(a), lo);
+#endif
 }
 
 // tile (shared address; its logical byte 0 = output byte out_a & ~15) -> out[out_a, out_a + nbytes): 16-byte stores on the
@@ -230,23 +280,12 @@ k_tokenize64(const __grid_constant__ TokArgs A)
                     off0 += __popc(t32);
                 }
             }
-            // bytes of my word -> tile: straight-line, one predicated byte store per input byte (the words are still in
-            // registers; delimiters are sparse, so nearly every store is taken)
+            // bytes of my word -> tile (the words are still in registers)
             {
                 const uint32_t tile = wb + (uint32_t)offsetof(WarpSmTok, tile);
-                uint32_t o = phase + (pre & 0xffffu);
                 const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t m = (uint32_t)(T >> (4 * i)) & 15u;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (m & (1u << k)) {
-                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile + tile_pad(o)), "r"(w[i] >> (8 * k)) : "memory");
-                            ++o;
-                        }
-                    }
-                }
+                tile_zero(tile, phase + (uint32_t)nbytes, lane);
+                scatter_kept(tile, phase + (pre & 0xffffu), w, T);
             }
             __syncwarp();
             if (stage_toks)
