@@ -72,15 +72,17 @@ __global__ void k_tok_item_windows(const int32_t* __restrict__ offsets, const in
 }
 
 // Kept bytes (mask K, one bit per byte of my 16 words) -> padded tile from logical offset o0 on, without inserts.
-// CUSTR_SCATTER_BYTES: one predicated st.shared.u8 per input byte (the first version).  Default: every word is compacted with
-// one PRMT (selector from a 16-entry table indexed by its 4 keep bits), appended to a 4-byte shift register, and whole aligned
-// words are OR-ed into the ZEROED tile (red.shared.or.b32) — the partial words at either end of a lane's range combine with
-// the neighbours' by the OR, so no byte stores are needed: ~17 shared-memory operations per lane and window instead of 64.
+// Default: one predicated st.shared.u8 per input byte, straight-line.  -DCUSTR_SCATTER_WORDS: every word is compacted with one
+// PRMT (selector from a 16-entry table indexed by its 4 keep bits), appended to a 4-byte shift register, and whole aligned
+// words are OR-ed into the ZEROED tile (red.shared.or.b32; the partial words at either end of a lane's range combine with the
+// neighbours' by the OR) — ~17 shared-memory operations per lane and window instead of 64 and ~200 fewer instructions, but
+// measured no faster on C2 (tokenize 1.606 vs 1.610 ms, replace 1.32 vs 1.34 ms, split_record 1.77 vs 1.66 ms): the write
+// passes are bound by issue efficiency (IPC 0.44 per scheduler), not by the shared-memory pipe, once the tile is padded.
 __constant__ uint16_t c_compact_sel[16] = {0x4444, 0x4440, 0x4441, 0x4410, 0x4442, 0x4420, 0x4421, 0x4210,
                                            0x4443, 0x4430, 0x4431, 0x4310, 0x4432, 0x4320, 0x4321, 0x3210};
 __device__ __forceinline__ void tile_zero(uint32_t tile, uint32_t logical_bytes, uint32_t lane)
 {
-#ifndef CUSTR_SCATTER_BYTES
+#ifdef CUSTR_SCATTER_WORDS
     const uint32_t end = tile_pad(logical_bytes) + 4u;
     for (uint32_t q = 16u * lane; q < end; q += 512u) asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(tile + q), "r"(0u) : "memory");
     __syncwarp();
@@ -88,7 +90,7 @@ __device__ __forceinline__ void tile_zero(uint32_t tile, uint32_t logical_bytes,
 }
 __device__ __forceinline__ void scatter_kept(uint32_t tile, uint32_t o0, const uint32_t (&w)[16], u64 K)
 {
-#ifdef CUSTR_SCATTER_BYTES
+#ifndef CUSTR_SCATTER_WORDS
     uint32_t o = o0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {

@@ -43,10 +43,13 @@ void custr_set_stream(void* cuda_stream);      /* cudaStream_t; thread local    
 int  custr_sync(void);
 /* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
 long long custr_launch_count(void);
-/* name of the regex execution tier used by the last regex call on this thread ("bitstream", "pikevm") */
+/* name of the regex execution tier used by the last regex call on this thread ("bitstream", "pikevm", "bitcount",
+ * "bitspans", "bitsplice", "chainspan", "literal") */
 const char* custr_last_regex_tier(void);
-/* force a tier for A/B testing: 0 = auto, 1 = exact Pike VM only, 2 = bitstream generic interpreter kernel,
- * 3 = boolean results from the window-at-a-time chain kernel (k_chain64) instead of the item-buffered one,
+/* force a tier for A/B testing: 0 = auto, 1 = exact Pike VM only, 2 = bitstream generic interpreter kernel (this also
+ * switches the bit-stream forms of tokenize / split_record / literal replace / find's pre-filter off: per-row kernels),
+ * 3 = boolean results from the window-at-a-time chain kernel (k_chain64) instead of the item-buffered one, and replace_re
+ * through the per-row walk of the span streams instead of the streaming splice,
  * 4 = no ahead-of-time shape specialisation (run-time compiled plan kernel when available), 5 = neither (generic kernels) */
 void custr_set_regex_tier(int tier);
 /* Run-time compiled plan kernels: the chain kernel specialised for the pattern at hand with NVRTC (about 0.6 s on first use,
