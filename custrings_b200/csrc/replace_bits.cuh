@@ -164,7 +164,7 @@ k_replace_splice64(const __grid_constant__ ReplArgs A)
             const int kfirst = kown;
             for (int j0 = kown;; j0 += 32) {
                 const int j = j0 + (int)lane;
-                const int o = j < A.n ? __ldg(A.offsets + j) : 0x7fffffff;
+                const int o = j <= A.n ? __ldg(A.offsets + j) : 0x7fffffff;  // offsets[n] too: the end of a row-slice view is a row start of its parent
                 const bool inw = o < ws + WIN64;
                 if (MODE == 0 && inw) reds_or(rs_base + 4u * (uint32_t)((o - ws) >> 5), 1u << ((o - ws) & 31));
                 kown += __popc(__ballot_sync(FULL, j < rb && (o < we || !more)));

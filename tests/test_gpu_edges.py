@@ -117,3 +117,33 @@ def test_ipc_export_import_between_processes(tmp_path):
     out = json.load(open(tmp_path / "out.json"))
     assert out["rows"] == rows
     assert out["hits"] == col.contains(r"\d+")
+
+
+def test_stream_paths_on_row_slice_views(oracle):
+    """The bit-stream forms of replace / replace_re / split_record / tokenize / find on row-slice VIEWS (first offset not zero and
+    not aligned, the bytes of the parent's neighbouring rows right next to the view's) against the oracle on the same rows.
+    The last row of the view ends where the parent's next row — which would complete an occurrence — begins."""
+    from custrings_b200 import nvstrings, nvtext
+    import random
+    rng = random.Random(9)
+    words = ["alpha", "be", "gamma7", "a", "ab", "b", "abab", "é", "x_y", "zz ", "delta,", ""]
+    strs = [" ".join(rng.choice(words) for _ in range(rng.choice([1, 3, 8, 20, 60]))) for _ in range(6000)]
+    strs[11] = None
+    for k in range(50, 6000, 97):  # "...a" | "b..." : 'ab' straddles the row boundary, "wor" | "ds": a word run does too
+        strs[k] = strs[k] + " xa"
+        strs[k + 1] = "b wor" if k % 2 else "bcde" + strs[k + 1]
+    col = nvstrings.to_device(strs)
+    for lo, hi in ((0, 6000), (51, 148), (7, 5001), (148, 149), (1000, 1000 + 2911)):
+        view = col[lo:hi]
+        ref = oracle.RefStrings.from_list(strs[lo:hi])
+        dec = lambda r: [None if x is None else x.decode() for x in r.to_list()]  # noqa: E731
+        assert view.replace("ab", "<>", regex=False).to_host() == dec(ref.replace("ab", "<>")), (lo, hi)
+        assert view.replace(" ", "", regex=False).to_host() == dec(ref.replace(" ", "")), (lo, hi)
+        assert view.replace(r"\b\w{4,}\b", "#").to_host() == dec(ref.replace_re(r"\b\w{4,}\b", "#")), (lo, hi)
+        assert view.replace(r"[a-z]+", "").to_host() == dec(ref.replace_re(r"[a-z]+", "")), (lo, hi)
+        got = view.split_record(" ")
+        want = ref.split_record(" ")[0]
+        assert [None if g is None else g.to_host() for g in got] == [None if w is None else dec(w) for w in want], (lo, hi)
+        assert nvtext.tokenize(view).to_host() == dec(ref.tokenize()), (lo, hi)
+        f = view.find("ab")
+        assert [g for g in f if g is not None] == [int(x) for x, g in zip(ref.find("ab")[0], f) if g is not None], (lo, hi)
