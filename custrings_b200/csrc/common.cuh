@@ -83,6 +83,7 @@ struct custr_column {
     // first row of every 32 KiB work item (4 bytes per 32 KiB of chars)
     mutable custr::BufPtr item_bounds;
     mutable int32_t item_bounds_count = 0;
+    mutable int32_t item_bounds_bytes = 0;   // item size the index was built for
     // CUDA IPC (custr_ipc_export / custr_ipc_import): the exported copy lives as long as the column it was made from; an
     // imported column keeps the opened mapping until it is freed
     mutable std::shared_ptr<void> ipc_owner;

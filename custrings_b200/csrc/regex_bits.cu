@@ -35,7 +35,7 @@ struct Plan {
 
 thread_local bool g_no_spec = false;        // A/B switch: never use the shape-specialised chain kernels
 thread_local bool g_force_generic = false;  // A/B switch: run chain-shaped plans on the generic interpreter kernel
-int g_item_bytes = 32 * 1024;              // size of a work item of the chain / tokenize kernels (bytes of chars; A/B: custr_set_item_kib)
+int g_item_bytes = 0;                      // forced size of a work item of the chain / tokenize kernels (custr_set_item_kib; 0 = item_bytes_for)
 thread_local bool g_chain_win = false;      // A/B switch: boolean results from k_chain64 (window at a time) instead of k_chain_item
 
 #include "regex_bits_dev.cuh"
@@ -231,18 +231,36 @@ __global__ void k_item_bounds(const int32_t* __restrict__ offsets, int n, int fi
     }
 }
 
+// Size of a work item for a column of `nbytes` chars: 32 KiB, except for columns too small to give every resident warp (W = SMs x
+// 3 CTAs x 8 warps) one such item — there the item shrinks (down to 4 KiB) so that all warps share the one round: a warp working
+// alone is latency-bound and the first item of a launch runs cold (tools/size_sweep.py: 1 MB 0.119 -> 0.035 ms, 34 MB 0.068 ->
+// 0.049 ms).  Balancing the rounds of LARGER columns the same way (item = nbytes / (W x rounds)) was measured and is worse
+// (537 MB: 0.307 vs 0.223 ms): with every warp finishing its item at the same moment the phases of all warps run in lock-step.
+static int item_bytes_for(int64_t nbytes)
+{
+    if (g_item_bytes) return g_item_bytes;
+    const int64_t W = (int64_t)num_sms() * 3 * WARPS;
+    if (nbytes >= W * 32768) return 32768;
+    int64_t ib = ((nbytes + W - 1) / W + 255) & ~255ll;
+    if (ib < 4096) ib = 4096;
+    if (ib > 32768) ib = 32768;
+    return (int)ib;
+}
 // the column's work-item index, built on first use; columns are shared read-only between threads, so the lazy build is
 // serialised (the kernel is stream-ordered before every consumer on this thread's stream; a second thread waits for it)
-static const int32_t* ensure_item_bounds(const custr_column* col, const int32_t* offsets, int first, int nitems)
+static const int32_t* ensure_item_bounds(const custr_column* col, const int32_t* offsets, int first, int& nitems)
 {
+    const int ib = item_bytes_for(col->nbytes);
+    nitems = (int)((col->nbytes + ib - 1) / ib);
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
-    if (!col->item_bounds || col->item_bounds_count != nitems) {
+    if (!col->item_bounds || col->item_bounds_count != nitems || col->item_bounds_bytes != ib) {
         BufPtr b = dev_alloc(sizeof(int32_t) * (size_t)(nitems + 2));
-        LAUNCH(k_item_bounds, (col->n + 1 + 255) / 256, 256, 0, offsets, col->n, first, nitems, g_item_bytes, (int32_t*)b->ptr);
+        LAUNCH(k_item_bounds, (col->n + 1 + 255) / 256, 256, 0, offsets, col->n, first, nitems, ib, (int32_t*)b->ptr);
         CUSTR_CUDA(cudaStreamSynchronize(g_stream));
         col->item_bounds = b;
         col->item_bounds_count = nitems;
+        col->item_bounds_bytes = ib;
     }
     return (const int32_t*)col->item_bounds->ptr;
 }
@@ -317,8 +335,7 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     a.first = col->first_off;
     a.end = col->first_off + (int32_t)col->nbytes;
     // (the DAG interpreter searches its own 32 KiB items; the chain kernels take theirs from the column's item index)
-    const int item_bytes = (plan.is_chain && !g_force_generic) ? g_item_bytes : ITEM_BYTES;
-    a.nitems = (int)((col->nbytes + item_bytes - 1) / item_bytes);
+    a.nitems = (int)((col->nbytes + ITEM_BYTES - 1) / ITEM_BYTES);  // the chain kernels take theirs from ensure_item_bounds below
     a.out = out;
     a.total = total;
     a.dirty_rows = *dirty_rows;
@@ -350,6 +367,7 @@ bool run(const Plan& plan, const custr_column* col, const uint8_t* prog_img, con
     if (plan.is_chain && !g_force_generic) {
         // 2048-byte windows, 64-bit streams, cp.async ring; grid = resident set (3 CTAs per SM), dynamic items
         a.item_bounds = ensure_item_bounds(col, a.offsets, a.first, a.nitems);  // once per column (it is immutable)
+        blocks = (a.nitems + WARPS - 1) / WARPS;
         const int resident = num_sms() * (use_item ? chain_item_ctas_per_sm() : 3);
         if (blocks > resident) blocks = resident;
         if (use_item) {
@@ -386,7 +404,6 @@ bool tokenize_flat(const custr_column* col, const uint8_t* delims, int ndelims, 
     a.n = n;
     a.first = col->first_off;
     a.end = col->first_off + (int32_t)col->nbytes;
-    a.nitems = (int)((col->nbytes + g_item_bytes - 1) / g_item_bytes);
     a.whitespace = delims ? 0u : 1u;
     a.ndelims = delims ? (uint32_t)ndelims : 0u;
     for (int k = 0; k < ndelims && delims; ++k) a.delims[k] = delims[k];
@@ -470,7 +487,6 @@ bool split_record_flat(const custr_column* col, uint8_t delim, BufPtr& out_chars
     a.n = n;
     a.first = col->first_off;
     a.end = col->first_off + (int32_t)col->nbytes;
-    a.nitems = (int)((col->nbytes + g_item_bytes - 1) / g_item_bytes);
     a.delim = delim;
     a.item_bounds = ensure_item_bounds(col, a.offsets, a.first, a.nitems);
     const int win_base = a.first & ~(WIN64 - 1);
@@ -541,7 +557,6 @@ static bool splice_run(const custr_column* col, ReplArgs& a, int mode, BufPtr& o
     a.n = n;
     a.first = col->first_off;
     a.end = col->first_off + (int32_t)col->nbytes;
-    a.nitems = (int)((col->nbytes + g_item_bytes - 1) / g_item_bytes);
     a.item_bounds = ensure_item_bounds(col, a.offsets, a.first, a.nitems);
     const size_t nslots = (size_t)col->nbytes / REPL_STRIDE + 2 * (size_t)a.nitems + 2;
     Scratch<int32_t> item_w((size_t)a.nitems + 1), item_slot((size_t)a.nitems + 1);

@@ -58,7 +58,8 @@ void custr_set_regex_tier(int tier);
 void custr_set_jit(int mode, long long min_bytes);
 long long custr_jit_launch_count(void);   /* launches served by run-time compiled kernels so far */
 const char* custr_jit_note(void);         /* why the last request on this thread was not served ("" if it was) */
-/* tuning / A-B switch: size of a work item of the chain and tokenize kernels in KiB of chars (default 32) */
+/* tuning / A-B switch: fixed size of a work item of the bit-stream kernels in KiB of chars (4..32); anything else = the default,
+ * chosen per column so that the item count is a whole number of rounds over the resident warps (at most 32 KiB) */
 void custr_set_item_kib(int kib);
 /* when on, regex calls bracket their dominant kernel(s) with CUDA events on the launch stream;
  * custr_last_kernel_ms() returns that device time for the last call on this thread (-1 if none) */

@@ -147,3 +147,44 @@ def test_stream_paths_on_row_slice_views(oracle):
         assert nvtext.tokenize(view).to_host() == dec(ref.tokenize()), (lo, hi)
         f = view.find("ab")
         assert [g for g in f if g is not None] == [int(x) for x, g in zip(ref.find("ab")[0], f) if g is not None], (lo, hi)
+
+
+def test_item_starts_inside_windows(oracle):
+    """Work items whose first row starts deep inside a 2 KiB window (odd item sizes, row-slice views, small columns whose item size
+    is derived from the column size): count_re once carried the match bits of the previous item's rows into a first row that
+    did not end in its first window.  Every bit-stream path against the oracle with item sizes of 5 / 7 / 13 KiB and the default."""
+    from custrings_b200 import nvstrings, nvtext
+    from custrings_b200._lib import lib
+    import random
+    rng = random.Random(21)
+    words = ["alpha", "be", "gamma7", "a", "ab", "b", "x_y", "é", "zz", "delta,", "12345", ""]
+    strs = []
+    for k in range(4000):
+        nw = rng.choice([1, 3, 8, 20, 60, 400, 900])  # rows of up to ~5 KB: many do not end in the window they start in
+        strs.append(None if k % 211 == 3 else " ".join(rng.choice(words) for _ in range(nw)))
+    col = nvstrings.to_device(strs)
+    ref = oracle.RefStrings.from_list(strs)
+    dec = lambda r: [None if x is None else x.decode() for x in r.to_list()]  # noqa: E731
+    want = {
+        "count": [int(x) for x in ref.count_re(r"\b\w{4,}\b")[0]],
+        "count2": [int(x) for x in ref.count_re(r"\d+")[0]],
+        "contains": [bool(x) for x in ref.contains_re(r"\b\w{4,}\b")[0]],
+        "replace_re": dec(ref.replace_re(r"\b\w{4,}\b", "#")),
+        "replace": dec(ref.replace("ab", "<>")),
+        "tokenize": dec(ref.tokenize()),
+    }
+    valid = [s is not None for s in strs]
+    for kib in (0, 5, 7, 13, 32):
+        lib().custr_set_item_kib(kib)
+        try:
+            for view_lo in (0, 17):
+                v = col[view_lo:len(strs)] if view_lo else col
+                ok = valid[view_lo:]
+                assert [c for c, k in zip(v.count(r"\b\w{4,}\b"), ok) if k] == [c for c, k in zip(want["count"][view_lo:], ok) if k], (kib, view_lo)
+                assert [c for c, k in zip(v.count(r"\d+"), ok) if k] == [c for c, k in zip(want["count2"][view_lo:], ok) if k], (kib, view_lo)
+                assert [c for c, k in zip(v.contains(r"\b\w{4,}\b"), ok) if k] == [c for c, k in zip(want["contains"][view_lo:], ok) if k], (kib, view_lo)
+                assert v.replace(r"\b\w{4,}\b", "#").to_host() == want["replace_re"][view_lo:], (kib, view_lo)
+                assert v.replace("ab", "<>", regex=False).to_host() == want["replace"][view_lo:], (kib, view_lo)
+            assert nvtext.tokenize(col).to_host() == want["tokenize"], kib
+        finally:
+            lib().custr_set_item_kib(0)
