@@ -1033,7 +1033,11 @@ const char* custr_last_regex_tier(void) { return g_last_tier; }
 void custr_set_profiling(int on) { g_profile = on; }
 float custr_last_kernel_ms(void) { return g_last_kernel_ms; }
 // A/B: size of a work item of the chain / tokenize kernels in KiB (default 32)
-void custr_set_item_kib(int kib) { bits::g_item_bytes = (kib >= 4 && kib <= 32) ? kib * 1024 : 0; }
+void custr_set_item_kib(int kib)
+{
+    bits::g_item_bytes = (kib >= 4 && kib <= 32) ? kib * 1024 : 0;
+    bits::g_item_stagger = kib != -1;  // -1: default sizes without the graded first round (A/B)
+}
 // run-time compiled plan kernels (regex_jit.cu): mode 0 never, 1 = large columns whose plan has no ahead-of-time shape
 // (default), 2 = always; min_bytes > 0 also sets the column size from which mode 1 compiles
 void custr_set_jit(int mode, long long min_bytes)

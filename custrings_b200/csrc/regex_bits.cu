@@ -35,6 +35,7 @@ struct Plan {
 
 thread_local bool g_no_spec = false;        // A/B switch: never use the shape-specialised chain kernels
 thread_local bool g_force_generic = false;  // A/B switch: run chain-shaped plans on the generic interpreter kernel
+bool g_item_stagger = true;               // graded first-round items on large columns (A/B: custr_set_item_kib(-1) turns it off)
 int g_item_bytes = 0;                      // forced size of a work item of the chain / tokenize kernels (custr_set_item_kib; 0 = item_bytes_for)
 thread_local bool g_chain_win = false;      // A/B switch: boolean results from k_chain64 (window at a time) instead of k_chain_item
 
@@ -212,23 +213,37 @@ k_bitstream(const __grid_constant__ PlanDev plan, const Args A)
 }
 
 
-// item_bounds[t] = first row r with offsets[r] >= first + t*ITEM_BYTES, for t = 0..nitems (bounds[nitems] = n): one coalesced
-// pass over the offsets instead of two dependent binary searches at the head of every work item
-__global__ void k_item_bounds(const int32_t* __restrict__ offsets, int n, int first, int nitems, int item_bytes, int32_t* __restrict__ bounds)
+// Byte position (relative to the first char) at which work item t begins.  Plain: t * ib.  Staggered (large columns): the first W
+// items — the first item of every resident warp — have graded sizes ib/8, 2 ib/8, .. ib, so that the warps, which all start at
+// the same moment, finish their first item at different times and never run their phases in lock-step (row bookkeeping of
+// some warps then overlaps the window loop of others from the first round on); behind them every item has ib bytes.
+constexpr int ITEM_STAGGER = 8;
+__host__ __device__ inline long long item_start(long long t, long long W, long long ib, bool staggered)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // row index 0..n (offsets has n+1 entries)
-    if (i > n) return;
-    const long long cur = (long long)offsets[i] - first;
-    const long long prev = i == 0 ? -1 : (long long)offsets[i - 1] - first;
-    // boundaries t with prev < t*ITEM <= cur get row i
-    long long t_lo = prev < 0 ? 0 : prev / item_bytes + 1;
-    long long t_hi = cur / item_bytes;
-    if (t_hi > nitems) t_hi = nitems;
-    for (long long t = t_lo; t <= t_hi; ++t) bounds[t] = i;
-    if (i == n) {  // boundaries past the last offset (only bounds[nitems] when the span is not a multiple of the item size)
-        for (long long t = t_hi + 1; t <= nitems; ++t) bounds[t] = n;
-        bounds[nitems] = n;
+    if (!staggered) return t * ib;
+    const long long unit = ib / ITEM_STAGGER, group = unit * (ITEM_STAGGER * (ITEM_STAGGER + 1) / 2);
+    if (t <= W) {
+        const long long q = t / ITEM_STAGGER, r = t % ITEM_STAGGER;
+        return q * group + unit * (r * (r + 1) / 2);
     }
+    return (W / ITEM_STAGGER) * group + (t - W) * ib;
+}
+// item_bounds[t] = first row r with offsets[r] >= first + item_start(t), for t = 0..nitems (bounds[nitems] = n): one thread per
+// boundary, a binary search over the offsets (once per column)
+__global__ void k_item_bounds(const int32_t* __restrict__ offsets, int n, int first, int nitems, int item_bytes, int W, int staggered,
+                              int32_t* __restrict__ bounds)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > nitems) return;
+    if (t == nitems) { bounds[t] = n; return; }
+    const long long target = (long long)first + item_start(t, W, item_bytes, staggered != 0);
+    int lo = 0, hi = n;  // first r in [0, n] with offsets[r] >= target
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((long long)offsets[mid] >= target) hi = mid;
+        else lo = mid + 1;
+    }
+    bounds[t] = lo;
 }
 
 // Size of a work item for a column of `nbytes` chars: 32 KiB, except for columns too small to give every resident warp (W = SMs x
@@ -251,16 +266,20 @@ static int item_bytes_for(int64_t nbytes)
 static const int32_t* ensure_item_bounds(const custr_column* col, const int32_t* offsets, int first, int& nitems)
 {
     const int ib = item_bytes_for(col->nbytes);
-    nitems = (int)((col->nbytes + ib - 1) / ib);
+    const long long W = (long long)num_sms() * 3 * WARPS;
+    const bool staggered = g_item_stagger && !g_item_bytes && col->nbytes >= W * 32768;  // at least one full round of 32 KiB items
+    if (!staggered) nitems = (int)((col->nbytes + ib - 1) / ib);
+    else nitems = (int)(W + (col->nbytes - item_start(W, W, ib, true) + ib - 1) / ib);
+    const int key = staggered ? -ib : ib;
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
-    if (!col->item_bounds || col->item_bounds_count != nitems || col->item_bounds_bytes != ib) {
+    if (!col->item_bounds || col->item_bounds_count != nitems || col->item_bounds_bytes != key) {
         BufPtr b = dev_alloc(sizeof(int32_t) * (size_t)(nitems + 2));
-        LAUNCH(k_item_bounds, (col->n + 1 + 255) / 256, 256, 0, offsets, col->n, first, nitems, ib, (int32_t*)b->ptr);
+        LAUNCH(k_item_bounds, (nitems + 1 + 255) / 256, 256, 0, offsets, col->n, first, nitems, ib, (int)W, staggered ? 1 : 0, (int32_t*)b->ptr);
         CUSTR_CUDA(cudaStreamSynchronize(g_stream));
         col->item_bounds = b;
         col->item_bounds_count = nitems;
-        col->item_bounds_bytes = ib;
+        col->item_bounds_bytes = key;
     }
     return (const int32_t*)col->item_bounds->ptr;
 }

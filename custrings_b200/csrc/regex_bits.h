@@ -59,6 +59,7 @@ extern thread_local bool g_force_generic;
 extern thread_local bool g_no_spec;
 extern thread_local bool g_chain_win;
 extern int g_item_bytes;
+extern bool g_item_stagger;
 extern thread_local bool g_no_jit;
 extern int g_jit_mode;               // 0 never, 1 large columns without an ahead-of-time shape (default), 2 always
 extern long long g_jit_min_bytes;

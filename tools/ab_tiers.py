@@ -18,7 +18,7 @@ ap.add_argument("--pattern", default=r"\b\w{4,}\b")
 ap.add_argument("--reps", type=int, default=30)
 ap.add_argument("--rows", type=int, default=10_000_000)
 ap.add_argument("--bytes", type=int, default=1 << 30)
-ap.add_argument("--item-kib", type=int, default=32)
+ap.add_argument("--item-kib", type=int, default=0, help="0 = library default, -1 = default without the graded first round, 4..32 = fixed")
 ap.add_argument("--jit", type=int, default=1, help="0 never, 1 default policy, 2 always")
 a = ap.parse_args()
 chars, offsets, validity, nulls = c2_corpus(a.rows, a.bytes)
