@@ -26,6 +26,24 @@
 //     the general body.  NUL bytes are only ACCUMULATED per lane; an item that saw one re-checks its rows in phase B (rare).
 #pragma once
 
+#ifdef CUSTR_ITEM_TIMING  // development aid (tools/build_variant.py T -DCUSTR_ITEM_TIMING): per-warp time stamps of the first items
+constexpr int ITEM_TIMING_SLOTS = 4 + 4 * 6;  // [entry, first item known, -, -] then per item [start, phase 0 done, phase A done, phase B done]
+__device__ unsigned long long g_item_times[148 * 3 * WARPS * ITEM_TIMING_SLOTS];
+__device__ __forceinline__ unsigned long long item_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define ITEM_STAMP(slot)                                                                                        \
+    do {                                                                                                        \
+        if (L.lane == 0 && (slot) < ITEM_TIMING_SLOTS)                                                          \
+            g_item_times[(blockIdx.x * WARPS + (threadIdx.x >> 5)) * ITEM_TIMING_SLOTS + (slot)] = item_now();  \
+    } while (0)
+#else
+#define ITEM_STAMP(slot) do { } while (0)
+#endif
+
 #ifndef ITEM_SEG_WINS
 #define ITEM_SEG_WINS 18
 #endif
@@ -57,7 +75,10 @@ static __device__ __noinline__ void ring_issue_item_tail(uint32_t wr, const char
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(chars + pos) : "memory");
             continue;
         }
-        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+        // bytes behind the end of the buffer are staged as SPACES, not zeros: a zero would count as a NUL byte and send the rows
+        // of the column's last item through the per-row NUL check of phase B (item_dirty_row) on every call — 75-100 us for one
+        // warp while the rest of the GPU idles (tools/item_timing.py); a row start sits on `end`, so no row sees these bytes
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0x20202020u) : "memory");
         for (uint32_t q = pos; q < end; ++q) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst + (q - pos)), "r"((uint32_t)(uint8_t)chars[q]) : "memory");
     }
 }
@@ -172,6 +193,16 @@ __device__ __forceinline__ void chain_item_body(const ChainDev& cd, const Args& 
     // fetched while the current item is being processed (the chain atomic -> item_bounds -> offsets is three dependent
     // memory latencies, ~7 % of an item's time when it sits at the top of the item)
     int nxt_item = 0, nxt_ra = 0, nxt_rb = 0, nxt_ba = 0, nxt_bb = 0;
+    int timing_item = 0;
+    (void)timing_item;
+    ITEM_STAMP(0);
+#ifdef CUSTR_ITEM_TIMING
+    if (L.lane == 0) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        g_item_times[(blockIdx.x * WARPS + (threadIdx.x >> 5)) * ITEM_TIMING_SLOTS + 2] = smid;
+    }
+#endif
     if (lane == 0) nxt_item = (int)atomicAdd(A.item_counter, 1u);
     nxt_item = __shfl_sync(FULL, nxt_item, 0);
     if (nxt_item < A.nitems) {
@@ -180,9 +211,11 @@ __device__ __forceinline__ void chain_item_body(const ChainDev& cd, const Args& 
         nxt_ba = __ldg(A.offsets + nxt_ra);
         nxt_bb = __ldg(A.offsets + nxt_rb);
     }
+    ITEM_STAMP(1);
     for (;;) {
         const int item = nxt_item;
         if (item >= A.nitems) break;
+        ITEM_STAMP(4 + 4 * timing_item);
         const int ra = nxt_ra, rb = nxt_rb;
         const int byte_a = nxt_ba, byte_b = nxt_bb;
         int fetched = 0;  // lane 0: index of the item after this one (requested now, looked at after phase 0)
@@ -255,6 +288,7 @@ __device__ __forceinline__ void chain_item_body(const ChainDev& cd, const Args& 
                 prefetch_stage = 1;
             }
 
+            ITEM_STAMP(4 + 4 * timing_item + 1);
             // ---- phase A: the windows of the segment
             for (int w = 0; w < nw; ++w, ws += WIN64, stage ^= 1u) {
                 const bool more = (w + 1 < nw) || (wins_left > nw);
@@ -374,6 +408,7 @@ __device__ __forceinline__ void chain_item_body(const ChainDev& cd, const Args& 
                 __syncwarp();  // ring stage and stream words are free for the next iteration / phase B
             }
 
+            ITEM_STAMP(4 + 4 * timing_item + 2);
             // ---- phase B: the rows that end inside the segment
             if (prefetch_stage == 1) {  // ... and now its byte bounds (they are back when phase B is through)
                 if (nxt_item < A.nitems) {
@@ -412,9 +447,11 @@ __device__ __forceinline__ void chain_item_body(const ChainDev& cd, const Args& 
                     oa0 = na0; oa1 = na1; ob0 = nb0; ob1 = nb1;
                 }
             }
+            ITEM_STAMP(4 + 4 * timing_item + 3);
             wins_left -= nw;
             __syncwarp();
         } while (wins_left > 0);
+        ++timing_item;
     }
     cnt = __reduce_add_sync(FULL, cnt);
     if (lane == 0 && cnt) atomicAdd(A.total, (unsigned long long)cnt);

@@ -36,3 +36,20 @@ void ITEM_ENTRY_NAME(ITEM_NS_GROUP)(const ChainDev& cd, const Args& a, int block
 
 }  // namespace bits
 }  // namespace custr
+
+#if defined(CUSTR_ITEM_TIMING) && ITEM_NS_GROUP == 1
+extern "C" int custr_dbg_item_times(unsigned long long* out, int max_words)
+{
+    const int n = 148 * 3 * custr::bits::WARPS * custr::bits::ITEM_TIMING_SLOTS;
+    if (max_words < n) return -n;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, custr::bits::g_item_times, sizeof(unsigned long long) * n);
+    return n;
+}
+extern "C" void custr_dbg_item_times_clear(void)
+{
+    void* p = nullptr;
+    cudaGetSymbolAddress(&p, custr::bits::g_item_times);
+    cudaMemset(p, 0, sizeof(custr::bits::g_item_times));
+}
+#endif
