@@ -944,9 +944,18 @@ static int bool_search(const custr_column* col, const char* pattern, uint8_t* re
                 g_timer.stop();
                 g_last_tier = "bitstream";
                 done = true;
-                struct { unsigned long long total; unsigned int dirty, items; } h{};
-                CUSTR_CUDA(cudaMemcpyAsync(&h, keep_count->ptr, 16, cudaMemcpyDeviceToHost, g_stream));
-                CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+                struct Counters { unsigned long long total; unsigned int dirty, items; } h{};
+                {   // the one read-back of the call lands in page-locked memory (a pageable target makes the driver stage the copy)
+                    static thread_local Counters* pinned = nullptr;
+                    if (!pinned && cudaHostAlloc((void**)&pinned, sizeof(Counters), cudaHostAllocDefault) != cudaSuccess) {
+                        cudaGetLastError();
+                        pinned = nullptr;
+                    }
+                    Counters* dst = pinned ? pinned : &h;
+                    CUSTR_CUDA(cudaMemcpyAsync(dst, keep_count->ptr, 16, cudaMemcpyDeviceToHost, g_stream));
+                    CUSTR_CUDA(cudaStreamSynchronize(g_stream));
+                    h = *dst;
+                }
                 if (h.dirty) {  // rows holding a NUL byte: exact VM over the work list (rare: no launch at all otherwise)
                     int grid = vm_grid(n < 1 << 20 ? n : 1 << 20);
                     DISPATCH_CAP(cap, k_vm_bool_rows, grid, smem_for(*c), view_of(col), (const uint8_t*)c->dev_image->ptr,

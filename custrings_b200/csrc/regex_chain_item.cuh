@@ -472,14 +472,30 @@ custr_jit_chain_item(const __grid_constant__ ChainDev cd, const __grid_constant_
 #endif
 
 #if !defined(ITEM_EXPERIMENT) && !defined(CUSTR_JIT) && !defined(CUSTR_NO_ITEM_LAUNCHERS)
+// function attributes are per (function, device): set on the first launch there, not on every call
+static bool item_attrs_needed(const void* fn)
+{
+    static std::mutex mu;
+    static std::unordered_map<const void*, unsigned long long> done;  // bit = device ordinal
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    std::lock_guard<std::mutex> lock(mu);
+    unsigned long long& m = done[fn];
+    if (m & bit) return false;
+    m |= bit;
+    return true;
+}
 template <int NS>
 static void launch_item_ns(const ChainDev& cd, const Args& a, int blocks)
 {
 #define ITEM_LAUNCH(K)                                                                                                   \
     do {                                                                                                                 \
         auto kfn = K;                                                                                                    \
-        CUSTR_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES));             \
-        CUSTR_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        if (item_attrs_needed((const void*)kfn)) {                                                                       \
+            CUSTR_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES));         \
+            CUSTR_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        }                                                                                                                \
         LAUNCH(kfn, blocks, THREADS, ITEM_SMEM_BYTES, cd, a);                                                            \
     } while (0)
     bool plain = true;  // no optional step, END only behind the last step

@@ -4,6 +4,8 @@
 #include "regex_bits_plan.h"
 #include "regex_vm.cuh"
 #include <cstddef>
+#include <mutex>
+#include <unordered_map>
 
 #ifndef ITEM_NS_GROUP
 #define ITEM_NS_GROUP 0
