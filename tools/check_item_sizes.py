@@ -1,6 +1,9 @@
+#!/usr/bin/env python3
+"""contains_re / count_re on C2 prefixes with several forced work-item sizes against the exact Pike VM: a quick GPU check that
+results do not depend on where the items start (the count-mode carry bug of round 2 showed up here first)."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from custrings_b200 import nvstrings
 from custrings_b200._lib import lib
 from custrings_b200.workloads import c2_corpus
