@@ -36,6 +36,7 @@ _SIGNATURES = {
     "custr_ipc_export": (ci, [vp, vp]),
     "custr_ipc_import": (vp, [vp]),
     "custr_column_free": (None, [vp]),
+    "custr_release_cached_memory": (None, []),
     "custr_size": (cu, [vp]),
     "custr_chars_bytes": (cl, [vp]),
     "custr_null_count": (ci, [vp]),

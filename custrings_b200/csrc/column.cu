@@ -42,6 +42,18 @@ constexpr size_t BIG_MIN = 32ull << 20, BIG_TOTAL = 6ull << 30;
 constexpr size_t BIG_COUNT = 8;
 }  // namespace
 
+// custr_release_cached_memory: hand this thread's cached big blocks and the pool's unused memory back to the driver
+void release_cached_memory()
+{
+    for (auto& b : g_big.blocks) cudaFreeAsync(b.ptr, b.stream);
+    g_big.blocks.clear();
+    g_big.total = 0;
+    cudaStreamSynchronize(g_stream);
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+}
+
 DeviceBuf::DeviceBuf(size_t n) : bytes(n), cap(n)
 {
     static std::atomic<unsigned long long> pools_ready{0};  // one bit per device ordinal
@@ -743,6 +755,7 @@ void custr_column_free(custr_column* col) { delete col; }
 uint32_t custr_size(const custr_column* col) { return col ? (uint32_t)col->n : 0; }
 int64_t custr_chars_bytes(const custr_column* col) { return col ? col->nbytes : 0; }
 int32_t custr_null_count(const custr_column* col) { return col ? col->nulls : 0; }
+void custr_release_cached_memory(void) { custr::release_cached_memory(); }
 const char* custr_chars_ptr(const custr_column* col) { return col->chars + col->first_off; }
 const int32_t* custr_offsets_ptr(const custr_column* col) { return col->offsets; }
 const uint8_t* custr_validity_ptr(const custr_column* col) { return col->validity; }

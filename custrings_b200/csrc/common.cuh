@@ -64,6 +64,7 @@ struct Scratch {  // typed RAII scratch
 };
 
 int num_sms();
+void release_cached_memory();
 // CUSTR_TRACE=1: synchronise the stream and print the host time since the previous trace point (development aid)
 void trace_point(const char* what);
 

@@ -43,6 +43,10 @@ void custr_set_stream(void* cuda_stream);      /* cudaStream_t; thread local    
 int  custr_sync(void);
 /* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
 long long custr_launch_count(void);
+/* Device memory is stream-ordered pool memory that the library keeps for reuse (the pool's release threshold is raised, and blocks of
+ * 32 MiB and more sit in a per-thread cache of at most 6 GiB).  This returns what is not in use to the driver: for a process that
+ * shares the GPU with another allocator and is done with a batch of calls. */
+void custr_release_cached_memory(void);
 /* name of the regex execution tier used by the last regex call on this thread ("bitstream", "pikevm", "bitcount",
  * "bitspans", "bitsplice", "chainspan", "literal") */
 const char* custr_last_regex_tier(void);

@@ -188,3 +188,17 @@ def test_item_starts_inside_windows(oracle):
             assert nvtext.tokenize(col).to_host() == want["tokenize"], kib
         finally:
             lib().custr_set_item_kib(0)
+
+
+def test_release_cached_memory_between_calls():
+    """custr_release_cached_memory hands the big-block cache and the pool's unused memory back; calls after it allocate afresh."""
+    from custrings_b200 import nvstrings
+    from custrings_b200._lib import lib
+    rows = ["alpha beta gamma delta " * 40] * 20000  # ~18 MB in, ~18 MB out: above and below the 32 MiB cache threshold mix
+    col = nvstrings.to_device(rows + rows)
+    first = col.replace("alpha", "A", regex=False).to_host()
+    lib().custr_release_cached_memory()
+    again = col.replace("alpha", "A", regex=False).to_host()
+    assert first == again and again[0].startswith("A beta")
+    lib().custr_release_cached_memory()
+    assert col.contains(r"\bgamma\b")[:2] == [True, True]
