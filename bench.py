@@ -282,7 +282,78 @@ def secondary_workloads(args, rank, world, peak, reduce_max):
         want, e["cpu_baseline"] = oracle_rate(lambda: ref.RefStrings.from_arrays(c, o, v, nn), lambda r: r.replace_re(PATTERN, "#").to_arrays(), m)
         got = nvstrings.from_offsets(c, o, m, v, nn).replace(PATTERN, "#").to_arrays()
         e["parity"] = all(np.array_equal(a, b) for a, b in zip(got, want))
-    del col
+
+    # ---- the other entry points of the path on the same C2 shard (device-resident results; same bar: time, bytes, parity).
+    # A failure here must not take the headline down or desynchronise the ranks: it is recorded in the entry instead.
+    import ctypes as C
+    from custrings_b200._lib import lib as _lib
+    L = _lib()
+    res32 = torch.empty(n, dtype=torch.int32, device="cuda")
+    row_off_dev = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    io = col_io_bytes(col)
+
+    def split_dev():
+        tok = C.c_void_p()
+        k = L.custr_split_record(col.m_cptr, b" ", -1, C.byref(tok), row_off_dev.data_ptr(), 1)
+        if k < 0:
+            raise RuntimeError("split_record failed")
+        return tok
+
+    def op_split():
+        tok = split_dev()
+        L.custr_column_free(tok)
+
+    def split_bytes():
+        tok = nvstrings.nvstrings(split_dev().value)
+        return io + col_io_bytes(tok) + 4 * (n + 1)
+
+    def replace_bytes():
+        r = col.replace("ab", "X", regex=False)
+        return io + col_io_bytes(r)
+
+    ops = [
+        ("ops: split_record(' ') flat over the C2 shard", op_split, split_bytes),
+        ("ops: replace('ab','X') literal over the C2 shard", lambda: col.replace("ab", "X", regex=False), replace_bytes),
+        ("ops: find('abcd') over the C2 shard", lambda: L.custr_find(col.m_cptr, b"abcd", 0, -1, res32.data_ptr(), 1), lambda: io + 4 * n),
+        ("ops: count_re(\\b\\w{4,}\\b) over the C2 shard", lambda: L.custr_count_re(col.m_cptr, PATTERN.encode(), res32.data_ptr(), 1), lambda: io + 4 * n),
+    ]
+    for name, fn, nbytes_of in ops:
+        err, ms, alg = None, 0.0, 0
+        try:
+            alg = int(nbytes_of())
+            ms, _ = timed_ms(fn, reps=5)
+        except Exception as ex:  # noqa: BLE001
+            err = "%s: %s" % (type(ex).__name__, ex)
+        if err or not ms > 0:
+            reduce_max(0.0)  # the collective every rank's entry() performs
+            out.append({"workload": name, "error": err or "no time measured"})
+            continue
+        e = entry(name, ms, alg, n)
+        if have_ref:
+            try:
+                m = 20_000
+                c, o, v, nn = W.slice_rows(chars, offsets, validity, 0, m)
+                sub = nvstrings.from_offsets(c, o, m, v, nn)
+                mk = lambda: ref.RefStrings.from_arrays(c, o, v, nn)  # noqa: E731
+                if "split_record" in name:
+                    want, e["cpu_baseline"] = oracle_rate(mk, lambda r: r.split_record(" ")[0], m)
+                    got = sub.split_record(" ")
+                    e["parity"] = [None if g is None else g.to_host() for g in got] == \
+                                  [None if w is None else [x.decode() for x in w.to_list()] for w in want]
+                elif "replace" in name:
+                    want, e["cpu_baseline"] = oracle_rate(mk, lambda r: r.replace("ab", "X").to_arrays(), m)
+                    e["parity"] = all(np.array_equal(a, b) for a, b in zip(sub.replace("ab", "X", regex=False).to_arrays(), want))
+                elif "find" in name:
+                    want, e["cpu_baseline"] = oracle_rate(mk, lambda r: r.find("abcd")[0], m)
+                    got = sub.find("abcd")
+                    e["parity"] = [g for g in got if g is not None] == [int(x) for x, g in zip(want, got) if g is not None]
+                else:
+                    want, e["cpu_baseline"] = oracle_rate(mk, lambda r: r.count_re(PATTERN)[0], m)
+                    got = sub.count(PATTERN)
+                    e["parity"] = [g for g in got if g is not None] == [int(x) for x, g in zip(want, got) if g is not None]
+            except Exception as ex:  # noqa: BLE001
+                e["parity_error"] = "%s: %s" % (type(ex).__name__, ex)
+    del col, res32, row_off_dev
 
     # ---- C3a: README chain — split(',') -> column 4 -> 7 x replace(day, str(i)) (regex=True => replace_re)
     n3 = args.rows
